@@ -1,0 +1,113 @@
+// Host thread-emulator for the FFT pass bodies (TEST HARNESS ONLY).
+//
+// The build container has no GPU, so the device code in xcb_passes.h is written
+// as barrier-separated phases over an explicit per-thread context.  This file
+// runs those same phases thread-by-thread on the CPU so that the index algebra,
+// twiddles, pair product and lag epilogue can be checked against the oracle
+// before any GPU time is spent.  It is compiled only by tests/ (g++), is not
+// part of libxcorr_b200.so, and is never used by the product path.
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "../../xcorr_b200/csrc/xcb_plan.h"
+
+using namespace xcb;
+
+template <class T, int R1, int R2> static void emu_col(const PassParams<T>& p) {
+  using P = ColPass<T, R1, R2>;
+  using G = Cfg<T, R1, R2>;
+  std::vector<unsigned char> smem(G::COL_SMEM + 64);
+  std::vector<typename P::Ctx> ctx(G::THREADS);
+  int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    for (int t = 0; t < G::THREADS; ++t) { ctx[t].tid = t; ctx[t].bid = b; P::phase_a(p, ctx[t], smem.data()); }
+    for (int t = 0; t < G::THREADS; ++t) P::phase_b(p, ctx[t], smem.data());
+  }
+}
+
+template <class T, int R1, int R2> static void emu_row(const PassParams<T>& p) {
+  using P = RowPass<T, R1, R2>;
+  using G = Cfg<T, R1, R2>;
+  std::vector<unsigned char> smem(G::ROW_SMEM + 64);
+  std::vector<typename P::Ctx> ctx(G::THREADS);
+  int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
+  for (int64_t b = 0; b < nblocks; ++b) {
+    for (int t = 0; t < G::THREADS; ++t) { ctx[t].tid = t; ctx[t].bid = b; P::phase_info(p, ctx[t], smem.data()); }
+    for (int t = 0; t < G::THREADS; ++t) P::phase_load(p, ctx[t], smem.data());
+    for (int t = 0; t < G::THREADS; ++t) P::phase_s1_read(p, ctx[t], smem.data());
+    for (int t = 0; t < G::THREADS; ++t) P::phase_s1_write(p, ctx[t], smem.data());
+    for (int t = 0; t < G::THREADS; ++t) P::phase_s2(p, ctx[t], smem.data());
+    for (int t = 0; t < G::THREADS; ++t) P::phase_store(p, ctx[t], smem.data());
+  }
+}
+
+template <class T> static bool run_pass(const PassParams<T>& p, bool row) {
+  switch (p.N) {
+#define X(n, a, b) case n: if (row) emu_row<T, a, b>(p); else emu_col<T, a, b>(p); return true;
+    XCB_MENU(X)
+#undef X
+  }
+  return false;
+}
+
+template <class T>
+static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_stride, int n_signals,
+                    const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased,
+                    T* out, double* sumsq_out, T* spec_out) {
+  PlanGeom g;
+  int d[kMaxDims], k = nd;
+  if (nd == 0) { if (!plan_choose_dims(n, d, &k)) return -1; }
+  else for (int a = 0; a < nd; ++a) d[a] = dims[a];
+  if (!plan_geom_init(g, n, d, k)) return -2;
+  HostTables<T> ht;
+  build_tables(g, ht);
+  DevTables<T> tb;
+  tb.hi = ht.hi.data(); tb.lo = ht.lo.data();
+  for (int a = 0; a < g.nd; ++a) tb.inner[a] = ht.inner[a].data();
+
+  std::vector<cx<T>> spec((size_t)n_signals * g.M);
+  std::vector<double> sumsq(n_signals, 0.0);
+  {
+    PassParams<T> p0 = make_forward_pass<T>(g, tb, 0, x, x_stride, spec.data(), g.M, n_signals, nullptr);
+    std::vector<double> partial((size_t)n_signals * p0.tiles_per_batch, 0.0);
+    for (int a = 0; a < g.nd; ++a) {
+      PassParams<T> p = make_forward_pass<T>(g, tb, a, x, x_stride, spec.data(), g.M, n_signals, partial.data());
+      if (!run_pass(p, a == g.nd - 1)) return -3;
+    }
+    for (int s = 0; s < n_signals; ++s)
+      for (int64_t t = 0; t < p0.tiles_per_batch; ++t) sumsq[s] += partial[(size_t)s * p0.tiles_per_batch + t];
+  }
+  if (sumsq_out) memcpy(sumsq_out, sumsq.data(), sizeof(double) * n_signals);
+  if (spec_out) memcpy(spec_out, spec.data(), sizeof(cx<T>) * spec.size());
+
+  const int64_t K = i1 - i0;
+  std::vector<Job> jobs(n_pairs);
+  for (int q = 0; q < n_pairs; ++q) {
+    jobs[q].sig_i = pairs[2 * q]; jobs[q].sig_j = pairs[2 * q + 1];
+    jobs[q].spec_i = (int64_t)pairs[2 * q] * g.M; jobs[q].spec_j = (int64_t)pairs[2 * q + 1] * g.M;
+    jobs[q].out_off = (int64_t)q * K;
+  }
+  std::vector<cx<T>> work((size_t)n_pairs * g.M);
+  CorrFlags f; f.i0 = i0; f.i1 = i1; f.normalize = normalize; f.unbiased = unbiased; f.accumulate = 0;
+  for (int a = g.nd - 1; a >= 0; --a) {
+    PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec.data(), sumsq.data(), jobs.data(), n_pairs, work.data(), out, f);
+    if (!run_pass(p, a == g.nd - 1)) return -4;
+  }
+  return 0;
+}
+
+extern "C" {
+
+int emu_choose_dims(int64_t n, int* dims, int* nd) { return plan_choose_dims(n, dims, nd) ? 0 : -1; }
+
+// dtype: 0 = f32, 1 = f64.  x: [n_signals][x_stride]; pairs: [n_pairs][2]; out: [n_pairs][i1-i0]
+int emu_cc(int dtype, int64_t n, const int* dims, int nd, const void* x, int64_t x_stride, int n_signals,
+           const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased, void* out,
+           double* sumsq_out, void* spec_out) {
+  if (dtype == 0)
+    return emu_cc_t<float>(n, dims, nd, (const float*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
+                           unbiased, (float*)out, sumsq_out, (float*)spec_out);
+  return emu_cc_t<double>(n, dims, nd, (const double*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
+                          unbiased, (double*)out, sumsq_out, (double*)spec_out);
+}
+}

@@ -1,0 +1,102 @@
+"""CPU checks of the CUDA pass bodies through the host thread-emulator
+(tests/host_emu): the same xcb_passes.h / xcb_plan.h code the kernels compile,
+run thread-by-thread, compared with the oracle."""
+import numpy as np
+import pytest
+
+from oracle import cc_oracle as orc
+from tests.emu_util import choose_dims, emu_cc
+from tests.algo_model import forward_packed
+
+MENU = [64, 80, 96, 100, 120, 128, 144, 150, 160, 180, 192, 200, 225, 240, 256, 300, 320, 400]
+
+
+def _check(x, pairs, dims, tol, **kw):
+    out, ss, _ = emu_cc(x, pairs, dims=dims, **kw)
+    n = x.shape[1]
+    i0 = kw.get("i0") or 0
+    i1 = kw.get("i1") or 2 * n - 1
+    for q, (i, j) in enumerate(pairs):
+        ref = orc.cc(x[i].astype(np.float64), x[j].astype(np.float64),
+                     normalize=kw.get("normalize", True), unbiased=kw.get("unbiased", False))
+        peak = np.max(np.abs(ref))
+        ref = ref[i0:i1]
+        assert np.max(np.abs(out[q] - ref)) <= tol * peak, (dims, q)
+        if not kw.get("unbiased", False) and i0 <= np.argmax(np.abs(orc.cc(x[i].astype(np.float64), x[j].astype(np.float64), unbiased=False))) < i1:
+            assert np.argmax(np.abs(out[q])) == np.argmax(np.abs(ref))
+    assert np.allclose(ss, np.sum(x.astype(np.float64) ** 2, axis=1), rtol=1e-13)
+
+
+@pytest.mark.parametrize("N", MENU)
+def test_every_menu_size_single_pass_f64(N):
+    rng = np.random.default_rng(N)
+    n = N - 3
+    x = orc.synthetic_receivers(3, n, seed=N, delay=5)
+    _check(x, [(0, 1), (2, 0)], (N,), 1e-13)
+
+
+@pytest.mark.parametrize("N", MENU)
+def test_every_menu_size_as_column_pass_f64(N):
+    # N leads (column pass, real input / lag epilogue); inner = 100 is not a
+    # multiple of the 8-column tile -> exercises partial tiles too
+    n = N * 100 - 7
+    x = orc.synthetic_receivers(2, n, seed=N + 1, delay=11)
+    _check(x, [(0, 1)], (N, 100), 1e-13)
+
+
+@pytest.mark.parametrize("dims", [(64, 64, 64), (100, 96, 80), (64, 80, 64, 64)])
+def test_multi_pass_f64(dims):
+    M = int(np.prod(dims))
+    n = min(M, 300_000) - 1
+    if len(dims) == 4:
+        n = 70_000          # heavily padded: most of the transform is zeros
+    x = orc.synthetic_receivers(2, n, seed=7, delay=137)
+    _check(x, [(0, 1), (1, 0)], dims, 1e-13)
+
+
+@pytest.mark.parametrize("N", [64, 150, 240, 300, 400])
+def test_f32_single_and_two_pass(N):
+    x = orc.synthetic_receivers(3, N * 64 - 1, seed=N, delay=29).astype(np.float32)
+    _check(x, [(0, 1), (1, 2)], (N, 64), 1e-5)
+    x = orc.synthetic_receivers(2, N - 1, seed=N, delay=3).astype(np.float32)
+    _check(x, [(0, 1)], (N,), 1e-5)
+
+
+def test_crop_unbiased_nonorm_and_odd_lengths():
+    for n in (1, 2, 3, 63, 64, 1000, 4095, 4096):
+        x = orc.synthetic_receivers(2, n, seed=n, delay=1)
+        _check(x, [(0, 1)], None, 1e-13)
+    n = 5000
+    x = orc.synthetic_receivers(2, n, seed=1, delay=137)
+    i0, i1 = orc.lag_clip_indices(n, 0.02, (0.0, 30.0))
+    _check(x, [(0, 1)], None, 1e-13, i0=i0, i1=i1)
+    _check(x, [(0, 1)], None, 1e-13, i0=100, i1=4000)
+    _check(x, [(0, 1)], None, 1e-13, normalize=False)
+    _check(x, [(0, 1)], None, 1e-12, unbiased=True, i0=i0, i1=i1)
+    out, _, _ = emu_cc(x, [(0, 1)], i0=i0, i1=i1)
+    assert np.argmax(out[0]) == 137
+
+
+def test_zero_vector_gives_nan_like_reference():
+    x = np.zeros((2, 50))
+    x[1] = np.random.default_rng(0).standard_normal(50)
+    out, _, _ = emu_cc(x, [(0, 1)])
+    with np.errstate(all="ignore"):
+        ref = orc.cc(x[0], x[1], unbiased=False)
+    assert np.all(np.isnan(out)) and np.all(np.isnan(ref))
+
+
+def test_spectrum_layout_is_digit_transposed():
+    dims = (64, 80)
+    x = np.random.default_rng(2).standard_normal((1, 5000))
+    _, _, spec = emu_cc(x, [(0, 0)], dims=dims, want_spec=True)
+    Z = forward_packed(x[0], dims)
+    assert np.max(np.abs(spec[0] - Z)) < 1e-12 * np.max(np.abs(Z))
+
+
+def test_planner_named_shapes_are_exact():
+    for n in (21_600_000, 4_320_000):
+        assert int(np.prod(choose_dims(n))) == n
+    d = choose_dims(900_000)
+    assert 900_000 <= int(np.prod(d)) <= 1.03 * 900_000
+    assert choose_dims(5) == (64,)

@@ -1,0 +1,477 @@
+// FFT pass bodies for the packed-real multi-pass correlation.
+//
+// A transform of M = N_1*...*N_p complex points is done as p passes over HBM.
+// Pass a computes length-N_a sub-FFTs along axis a of the C-ordered array
+// (N_1,...,N_p); the spectrum stays in digit-transposed order so no pass ever
+// transposes through HBM.  Two kernel families:
+//
+//   ColPass  axis a < p : sub-FFT elements are `inner` apart; a CTA owns a
+//            tile of C adjacent columns (C*sizeof(cx<T>) = 128 B) so every
+//            global access is a full 128-byte line, and shared memory is
+//            [N][C] = one bank sweep per row -> conflict free.
+//   RowPass  axis p     : rows are contiguous; a CTA owns C rows, staged
+//            through shared memory transposed ([N][C+1]).
+//
+// Each sub-FFT N = R1*R2 is two register-resident radix stages (Stockham):
+// stage 1 reads x[j + r*R2], stage 2 reads s[j + r*R1] * W_N^(r*j).
+//
+// The bodies are split into phases separated by block barriers and keep all
+// per-thread state in ThreadCtx, so that tests/host_emu can run the very same
+// code thread-by-thread on the CPU (there is no GPU in the build container).
+// That emulator is a test harness only; the product never runs it.
+#pragma once
+#include <math.h>
+#include "xcb_radix_gen.h"
+#include "xcb_types.h"
+
+namespace xcb {
+
+enum ColLoad : int32_t { CL_REAL = 0, CL_CPLX = 1, CL_CPLX_INV = 2 };
+enum ColStore : int32_t { CS_TW = 0, CS_CONJ = 1, CS_EPI = 2 };
+enum RowLoad : int32_t { RL_CPLX = 0, RL_REAL = 1, RL_PROLOGUE = 2 };
+enum RowStore : int32_t { RS_CPLX = 0, RS_CONJ = 1, RS_EPI = 2 };
+
+constexpr int kMaxDims = 4;
+
+// One (pair, window) correlation: where its two spectra live and where its
+// cropped CCF goes.  Offsets are in elements.
+struct Job {
+  int64_t spec_i, spec_j;   // complex-element offsets into the spectrum buffer
+  int64_t out_off;          // real-element offset into the CCF buffer
+  int32_t sig_i, sig_j;     // indices into sumsq[]
+};
+
+template <class T> struct PassParams {
+  // ---- geometry ----
+  int32_t N;                 // sub-FFT length of this pass
+  int32_t load_mode, store_mode;
+  int32_t n_batch;           // signals (forward) or jobs (inverse) in this launch
+  int64_t M;                 // complex points per transform
+  int64_t inner;             // col pass: stride between sub-FFT elements
+  int64_t col_tiles;         // col pass: ceil(inner / C)
+  int64_t rows;              // row pass: M / N
+  int64_t tiles_per_batch;   // CTAs per signal/job
+  // ---- buffers ----
+  const void* in;            // cx<T>[n_batch][in_stride] (or T[...] for *_REAL)
+  void* out;                 // cx<T>[n_batch][out_stride]
+  int64_t in_stride, out_stride;
+  // ---- real input (forward first pass) ----
+  int64_t n_real;            // valid samples per signal; the rest of 2M is zero
+  int32_t real_vec_ok;       // 1: every signal base is 2*sizeof(T)-aligned
+  int32_t pad0;
+  double* sumsq_partial;     // [n_batch][tiles_per_batch] or null
+  // ---- twiddles: W_M^e = tw_hi[e >> shift] * tw_lo[e & mask] ----
+  const cx<T>* tw_hi;
+  const cx<T>* tw_lo;
+  const cx<T>* tw_inner;     // W_N^t, t in [0, N)
+  int32_t tw_shift;
+  uint32_t tw_mask;
+  uint32_t tw_scale;         // col pass: exponent = tw_scale * column * index
+  // ---- pair product (inverse first pass) ----
+  int32_t nd;                // number of passes p
+  int32_t dims[kMaxDims];    // N_1..N_p
+  int32_t n_regions;         // p - 1 mirror regions over rows
+  int32_t normalize;
+  int64_t region_lo[kMaxDims], region_hi[kMaxDims];  // row ranges
+  int64_t pair_start[kMaxDims + 1];                  // first pair id of region g (pair 0 = row 0)
+  int64_t n_pairs_rows;      // total row pairs
+  const Job* jobs;           // [n_batch]
+  const double* sumsq;       // per signal
+  const cx<T>* spec;         // spectrum buffer base
+  // ---- lag epilogue (inverse last pass) ----
+  int64_t n;                 // samples per window
+  int64_t L;                 // 2M
+  int64_t i0, i1;            // kept output indices [i0, i1) of the 2n-1 lags
+  T* ccf;                    // CCF buffer base (jobs[].out_off applies)
+  T escale;                  // 1/M
+  int32_t unbiased;          // multiply by n/(n-|k|)
+  int32_t accumulate;        // ccf += instead of ccf =
+};
+
+template <class T, int R1_, int R2_> struct Cfg {
+  static constexpr int R1 = R1_, R2 = R2_;
+  static constexpr int N = R1 * R2;
+  static constexpr int C = 128 / (2 * (int)sizeof(T));   // 16 (f32) / 8 (f64)
+  static constexpr int TJ = R1 > R2 ? R1 : R2;
+  static constexpr int THREADS = C * TJ;
+  static constexpr int CP = C + 1;                        // padded row-pass pitch
+  static constexpr int COL_SMEM = N * C * 2 * (int)sizeof(T) + THREADS * 8;
+  static constexpr int ROW_SMEM = N * CP * 2 * (int)sizeof(T) + C * 32 + THREADS * 8;
+};
+
+template <class T, int RMAX> struct ThreadCtx {
+  int32_t tid;
+  int64_t bid;
+  cx<T> v[RMAX];
+  double ss;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+template <class T> XCB_HD cx<T> ld_ro(const cx<T>* p) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (sizeof(T) == 4) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    cx<T> r; r.x = t.x; r.y = t.y; return r;
+  } else {
+    double2 t = __ldg(reinterpret_cast<const double2*>(p));
+    cx<T> r; r.x = t.x; r.y = t.y; return r;
+  }
+#else
+  return *p;
+#endif
+}
+
+template <class T> XCB_HD cx<T> tw_big(const PassParams<T>& p, uint32_t e) {
+  return cmul(ld_ro(p.tw_hi + (e >> p.tw_shift)), ld_ro(p.tw_lo + (e & p.tw_mask)));
+}
+
+// packed real load: complex index m of signal `x` -> (x[2m], x[2m+1]), zero past n_real
+template <class T> XCB_HD cx<T> load_real_packed(const PassParams<T>& p, const T* x, int64_t m, double& ss) {
+  cx<T> r; r.x = T(0); r.y = T(0);
+  int64_t q = 2 * m;
+  if (q + 1 < p.n_real) {
+    if (p.real_vec_ok) r = *reinterpret_cast<const cx<T>*>(x + q);
+    else { r.x = x[q]; r.y = x[q + 1]; }
+  } else if (q < p.n_real) {
+    r.x = x[q];
+  }
+  ss += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+  return r;
+}
+
+// final packed element m = (r[2m], r[2m+1]) -> cropped, scaled lag samples
+template <class T> XCB_HD void epilogue_store(const PassParams<T>& p, T* outp, int64_t m, T re, T im) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int64_t l = 2 * m + h;
+    int64_t i;
+    if (l < p.n) i = l + p.n - 1;
+    else if (l > p.L - p.n) i = l - p.L + p.n - 1;
+    else continue;
+    if (i < p.i0 || i >= p.i1) continue;
+    T val = (h ? im : re) * p.escale;
+    if (p.unbiased) {
+      int64_t k = i - (p.n - 1);
+      if (k < 0) k = -k;
+      val *= T((double)p.n / (double)(p.n - k));
+    }
+    T* dst = outp + (i - p.i0);
+    *dst = p.accumulate ? (*dst + val) : val;
+  }
+}
+
+
+// per-CTA sum of the threads' partial sums of squares (deterministic order);
+// `red` holds one double per thread, written before the preceding barrier.
+template <int THREADS> XCB_HD void block_sumsq(double* out, const double* red, int tid) {
+#if defined(__CUDA_ARCH__)
+  if (tid < 32) {
+    double a = 0.0;
+    for (int i = tid; i < THREADS; i += 32) a += red[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (tid == 0) *out = a;
+  }
+#else
+  if (tid == 0) {
+    // same association order as the device path: 32 strided lanes, then a tree
+    double lane[32];
+    for (int l = 0; l < 32; ++l) { lane[l] = 0.0; for (int i = l; i < THREADS; i += 32) lane[l] += red[i]; }
+    for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < o; ++l) lane[l] += lane[l + o];
+    *out = lane[0];
+  }
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// Column pass
+// ---------------------------------------------------------------------------
+template <class T, int R1, int R2> struct ColPass {
+  using G = Cfg<T, R1, R2>;
+  using Ctx = ThreadCtx<T, G::TJ>;
+  static constexpr int N = G::N, C = G::C;
+
+  struct Tile {
+    int64_t batch, base, col0;   // base: element offset of (n=0, c=0) within the signal
+    bool col_ok;
+    int c, j;
+  };
+
+  static XCB_HD Tile decode(const PassParams<T>& p, const Ctx& ctx) {
+    Tile t;
+    t.c = ctx.tid % C;
+    t.j = ctx.tid / C;
+    t.batch = ctx.bid / p.tiles_per_batch;
+    int64_t rem = ctx.bid - t.batch * p.tiles_per_batch;
+    int64_t o = rem / p.col_tiles;
+    int64_t cb = rem - o * p.col_tiles;
+    t.col0 = cb * C;
+    t.base = o * (int64_t)N * p.inner + t.col0;
+    t.col_ok = (t.col0 + t.c) < p.inner;
+    return t;
+  }
+
+  // stage 1: global -> registers -> radix-R1 -> shared
+  static XCB_HD void phase_a(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + (size_t)N * C * sizeof(cx<T>));
+    Tile t = decode(p, ctx);
+    ctx.ss = 0.0;
+    if (t.j < R2 && t.col_ok) {
+      cx<T>* v = ctx.v;
+      if (p.load_mode == CL_REAL) {
+        const T* x = reinterpret_cast<const T*>(p.in) + t.batch * p.in_stride;
+#pragma unroll
+        for (int r = 0; r < R1; ++r) {
+          int64_t m = t.base + (int64_t)(t.j + r * R2) * p.inner + t.c;
+          v[r] = load_real_packed(p, x, m, ctx.ss);
+        }
+      } else {
+        const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + t.batch * p.in_stride + t.base + t.c;
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = src[(int64_t)(t.j + r * R2) * p.inner];
+        if (p.load_mode == CL_CPLX_INV) {
+          uint32_t col = (uint32_t)(t.col0 + t.c) * p.tw_scale;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) {
+            cx<T> w = tw_big(p, col * (uint32_t)(t.j + r * R2));
+            v[r] = cmul(cconj(v[r]), w);
+          }
+        }
+      }
+      fft_reg<R1>(v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) smem[(t.j * R1 + r) * C + t.c] = v[r];
+    }
+    if (p.sumsq_partial) red[ctx.tid] = ctx.ss;
+  }
+
+  // stage 2: shared -> registers -> radix-R2 -> global
+  static XCB_HD void phase_b(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+    double* red = reinterpret_cast<double*>(smem_raw + (size_t)N * C * sizeof(cx<T>));
+    Tile t = decode(p, ctx);
+    if (t.j < R1 && t.col_ok) {
+      cx<T>* v = ctx.v;
+#pragma unroll
+      for (int r = 0; r < R2; ++r) v[r] = smem[(t.j + r * R1) * C + t.c];
+#pragma unroll
+      for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ld_ro(p.tw_inner + r * t.j));
+      fft_reg<R2>(v);
+      if (p.store_mode == CS_TW) {
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + t.batch * p.out_stride + t.base + t.c;
+        uint32_t col = (uint32_t)(t.col0 + t.c) * p.tw_scale;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          int k = t.j + r * R1;
+          dst[(int64_t)k * p.inner] = cmul(v[r], tw_big(p, col * (uint32_t)k));
+        }
+      } else if (p.store_mode == CS_CONJ) {
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + t.batch * p.out_stride + t.base + t.c;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) dst[(int64_t)(t.j + r * R1) * p.inner] = cconj(v[r]);
+      } else {
+        T* outp = p.ccf + p.jobs[t.batch].out_off;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          int64_t m = t.base + (int64_t)(t.j + r * R1) * p.inner + t.c;
+          epilogue_store(p, outp, m, v[r].x, -v[r].y);
+        }
+      }
+    }
+    if (p.sumsq_partial) block_sumsq<G::THREADS>(p.sumsq_partial + ctx.bid, red, ctx.tid);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Row pass
+// ---------------------------------------------------------------------------
+template <class T> struct RowInfo {   // per tile column, kept in shared memory
+  int64_t row;      // global row index, or -1 if the column is unused
+  int32_t store;    // 1: this column's result is written back
+  int32_t pad;
+  cx<T> wrow;       // W_M^{klow(row)} for the pair product
+};
+
+template <class T, int R1, int R2> struct RowPass {
+  using G = Cfg<T, R1, R2>;
+  using Ctx = ThreadCtx<T, G::TJ>;
+  static constexpr int N = G::N, C = G::C, CP = G::CP;
+
+  static XCB_HD RowInfo<T>* info_ptr(unsigned char* smem_raw) {
+    return reinterpret_cast<RowInfo<T>*>(smem_raw + (size_t)N * CP * sizeof(cx<T>));
+  }
+  static XCB_HD double* red_ptr(unsigned char* smem_raw) {
+    return reinterpret_cast<double*>(smem_raw + (size_t)N * CP * sizeof(cx<T>) + C * 32);
+  }
+
+  // frequency index contributed by the leading p-1 digits of a row
+  static XCB_HD uint32_t klow_of_row(const PassParams<T>& p, int64_t row) {
+    // row = ((k_1 N_2 + k_2) N_3 + ...) + k_{p-1};  klow = sum k_a * (N_1..N_{a-1})
+    uint32_t digits[kMaxDims];
+    int64_t r = row;
+    for (int a = p.nd - 2; a >= 0; --a) { digits[a] = (uint32_t)(r % p.dims[a]); r /= p.dims[a]; }
+    uint32_t k = 0, base = 1;
+    for (int a = 0; a < p.nd - 1; ++a) { k += digits[a] * base; base *= (uint32_t)p.dims[a]; }
+    return k;
+  }
+
+  // phase 0: column -> row bookkeeping
+  static XCB_HD void phase_info(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    if (ctx.tid >= C) return;
+    RowInfo<T>* info = info_ptr(smem_raw);
+    int c = ctx.tid;
+    int64_t tile = ctx.bid % p.tiles_per_batch;
+    RowInfo<T> ri;
+    ri.row = -1; ri.store = 0; ri.pad = 0; ri.wrow.x = T(1); ri.wrow.y = T(0);
+    if (p.load_mode == RL_PROLOGUE) {
+      int64_t q = tile * (C / 2) + (c >> 1);
+      if (q < p.n_pairs_rows) {
+        int64_t ra = 0, rb = 0;
+        if (q > 0) {
+          int g = 0;
+          while (g + 1 < p.n_regions && q >= p.pair_start[g + 1]) ++g;
+          int64_t tt = q - p.pair_start[g];
+          ra = p.region_lo[g] + tt;
+          rb = p.region_hi[g] - 1 - tt;
+        }
+        ri.row = (c & 1) ? rb : ra;
+        ri.store = ((c & 1) && ra == rb) ? 0 : 1;
+        // both columns of a pair carry the twiddle of the first row
+        ri.wrow = tw_big(p, klow_of_row(p, ra));
+      }
+    } else {
+      int64_t row = tile * C + c;
+      if (row < p.rows) { ri.row = row; ri.store = 1; }
+    }
+    info[c] = ri;
+  }
+
+  // phase 1: global -> shared (transposed)
+  static XCB_HD void phase_load(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+    const RowInfo<T>* info = info_ptr(smem_raw);
+    int64_t batch = ctx.bid / p.tiles_per_batch;
+    ctx.ss = 0.0;
+    if (p.load_mode == RL_PROLOGUE) {
+      const Job jb = p.jobs[batch];
+      const cx<T>* zi = p.spec + jb.spec_i;
+      const cx<T>* zj = p.spec + jb.spec_j;
+      T scale = T(0.25);
+      if (p.normalize) scale = T(0.25 / sqrt(p.sumsq[jb.sig_i] * p.sumsq[jb.sig_j]));
+      for (int idx = ctx.tid; idx < (C / 2) * N; idx += G::THREADS) {
+        int lp = idx / N, e = idx - lp * N;
+        const RowInfo<T> ia = info[2 * lp], ib = info[2 * lp + 1];
+        cx<T> va, vb;
+        va.x = va.y = vb.x = vb.y = T(0);
+        int em = N - 1 - e;
+        if (ia.row >= 0) {
+          if (ia.row == 0) em = (e == 0) ? 0 : N - e;
+          int64_t oa = ia.row * N + e, ob = ib.row * N + em;
+          cx<T> A = zi[oa], Ap = cconj(zi[ob]);
+          cx<T> B = zj[oa], Bp = cconj(zj[ob]);
+          cx<T> Si = cadd(A, Ap), Di = csub(A, Ap);
+          cx<T> Sj = cadd(B, Bp), Dj = csub(B, Bp);
+          cx<T> P1 = cmulc(Si, Sj), P2 = cmulc(Di, Dj), P3 = cmulc(Di, Sj), P4 = cmulc(Si, Dj);
+          // u = conj(W_M^k), k = klow(row) + (M/N) e
+          cx<T> u = cconj(cmul(ia.wrow, ld_ro(p.tw_inner + e)));
+          cx<T> uP4 = cmul(u, P4);
+          cx<T> s12 = cadd(P1, P2);
+          cx<T> V = csub(cadd(s12, P3), uP4);             // V[k]
+          cx<T> Vm = cadd(csub(s12, P3), uP4);            // conj(V[M-k])
+          // shared memory holds conj(V) (inverse via conj . FFT . conj)
+          va.x = V.x * scale;  va.y = -V.y * scale;
+          vb.x = Vm.x * scale; vb.y = Vm.y * scale;
+        }
+        smem[e * CP + 2 * lp] = va;
+        smem[em * CP + 2 * lp + 1] = vb;
+      }
+    } else if (p.load_mode == RL_REAL) {
+      const T* x = reinterpret_cast<const T*>(p.in) + batch * p.in_stride;
+      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
+        int c = idx / N, e = idx - c * N;
+        cx<T> v; v.x = v.y = T(0);
+        int64_t row = info[c].row;
+        if (row >= 0) v = load_real_packed(p, x, row * N + e, ctx.ss);
+        smem[e * CP + c] = v;
+      }
+      if (p.sumsq_partial) red_ptr(smem_raw)[ctx.tid] = ctx.ss;
+    } else {
+      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + batch * p.in_stride;
+      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
+        int c = idx / N, e = idx - c * N;
+        cx<T> v; v.x = v.y = T(0);
+        int64_t row = info[c].row;
+        if (row >= 0) v = src[row * N + e];
+        smem[e * CP + c] = v;
+      }
+    }
+  }
+
+  static XCB_HD void phase_s1_read(const PassParams<T>&, Ctx& ctx, unsigned char* smem_raw) {
+    const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
+    int c = ctx.tid % C, j = ctx.tid / C;
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r) ctx.v[r] = smem[(j + r * R2) * CP + c];
+    }
+  }
+
+  static XCB_HD void phase_s1_write(const PassParams<T>&, Ctx& ctx, unsigned char* smem_raw) {
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+    int c = ctx.tid % C, j = ctx.tid / C;
+    if (j < R2) {
+      fft_reg<R1>(ctx.v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) smem[(j * R1 + r) * CP + c] = ctx.v[r];
+    }
+  }
+
+  static XCB_HD void phase_s2(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+    int c = ctx.tid % C, j = ctx.tid / C;
+    if (j < R1) {
+      cx<T>* v = ctx.v;
+#pragma unroll
+      for (int r = 0; r < R2; ++r) v[r] = smem[(j + r * R1) * CP + c];
+#pragma unroll
+      for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ld_ro(p.tw_inner + r * j));
+      fft_reg<R2>(v);
+#pragma unroll
+      for (int r = 0; r < R2; ++r) smem[(j + r * R1) * CP + c] = v[r];
+    }
+  }
+
+  static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
+    const RowInfo<T>* info = info_ptr(smem_raw);
+    int64_t batch = ctx.bid / p.tiles_per_batch;
+    if (p.store_mode == RS_EPI) {
+      T* outp = p.ccf + p.jobs[batch].out_off;
+      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
+        int c = idx / N, e = idx - c * N;
+        const RowInfo<T> ri = info[c];
+        if (ri.row < 0 || !ri.store) continue;
+        cx<T> v = smem[e * CP + c];
+        epilogue_store(p, outp, ri.row * N + e, v.x, -v.y);
+      }
+    } else {
+      cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride;
+      const bool cj = p.store_mode == RS_CONJ;
+      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
+        int c = idx / N, e = idx - c * N;
+        const RowInfo<T> ri = info[c];
+        if (ri.row < 0 || !ri.store) continue;
+        cx<T> v = smem[e * CP + c];
+        if (cj) v.y = -v.y;
+        dst[ri.row * N + e] = v;
+      }
+    }
+    if (p.sumsq_partial && p.load_mode == RL_REAL)
+      block_sumsq<G::THREADS>(p.sumsq_partial + ctx.bid, red_ptr(smem_raw), ctx.tid);
+  }
+};
+
+}  // namespace xcb

@@ -1,0 +1,253 @@
+// Host-side planning for the multi-pass packed-real FFT correlation: choice of
+// the transform length and its factorisation into passes, twiddle tables, the
+// mirrored-row regions of the pair product, and PassParams construction.
+// Pure C++ (no CUDA) so the CPU tests can exercise it.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <algorithm>
+#include <vector>
+#include "xcb_passes.h"
+
+namespace xcb {
+
+struct MenuEntry { int N, R1, R2; };
+
+// Sub-FFT lengths with compiled kernels: N = R1*R2, radices in {8,10,12,15,16,20}.
+#define XCB_MENU(X) \
+  X(64, 8, 8) X(80, 10, 8) X(96, 12, 8) X(100, 10, 10) X(120, 12, 10) X(128, 16, 8) \
+  X(144, 12, 12) X(150, 15, 10) X(160, 16, 10) X(180, 15, 12) X(192, 16, 12) X(200, 20, 10) \
+  X(225, 15, 15) X(240, 16, 15) X(256, 16, 16) X(300, 20, 15) X(320, 20, 16) X(400, 20, 20)
+
+static const MenuEntry kMenu[] = {
+#define X(n, a, b) {n, a, b},
+    XCB_MENU(X)
+#undef X
+};
+static const int kMenuSize = (int)(sizeof(kMenu) / sizeof(kMenu[0]));
+
+inline const MenuEntry* menu_find(int N) {
+  for (int i = 0; i < kMenuSize; ++i) if (kMenu[i].N == N) return &kMenu[i];
+  return nullptr;
+}
+
+struct PlanGeom {
+  int64_t n = 0, M = 0, L = 0;
+  int nd = 0;
+  int dims[kMaxDims] = {0, 0, 0, 0};
+  int64_t S[kMaxDims + 1] = {1, 1, 1, 1, 1};   // suffix products, S[nd] = 1
+  int tw_shift = 0;
+  int n_regions = 0;
+  int64_t region_lo[kMaxDims] = {0, 0, 0, 0}, region_hi[kMaxDims] = {0, 0, 0, 0};
+  int64_t pair_start[kMaxDims + 1] = {0, 0, 0, 0, 0};
+  int64_t n_pairs_rows = 0;
+};
+
+inline int pow2_exponent(int v) { int e = 0; while (v % 2 == 0) { v /= 2; ++e; } return e; }
+
+// Smallest-cost factorisation M = prod(dims) >= n_min over the menu (<= 4 passes).
+// cost ~ HBM traffic: M * (passes + 0.5).  Returns false if nothing fits.
+inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
+  double best = 1e300;
+  int bd[kMaxDims] = {0, 0, 0, 0}, bn = 0;
+  int idx[kMaxDims];
+  for (int p = 1; p <= kMaxDims; ++p) {
+    // non-decreasing index tuples
+    for (int i = 0; i < p; ++i) idx[i] = 0;
+    while (true) {
+      double m = 1;
+      for (int i = 0; i < p; ++i) m *= kMenu[idx[i]].N;
+      if (m >= (double)n_min && m < 2147483648.0) {
+        double cost = m * (p + 0.5);
+        if (cost < best) { best = cost; bn = p; for (int i = 0; i < p; ++i) bd[i] = kMenu[idx[i]].N; }
+      }
+      int k = p - 1;
+      while (k >= 0 && idx[k] == kMenuSize - 1) --k;
+      if (k < 0) break;
+      ++idx[k];
+      for (int i = k + 1; i < p; ++i) idx[i] = idx[k];
+    }
+  }
+  if (bn == 0) return false;
+  // Axis order: the size with the most factors of two goes last (its length is
+  // the inner stride of the pass before it -> 128-byte aligned column tiles);
+  // the rest in decreasing order.
+  std::sort(bd, bd + bn, [](int a, int b) { return a > b; });
+  int last = 0;
+  for (int i = 1; i < bn; ++i) if (pow2_exponent(bd[i]) > pow2_exponent(bd[last])) last = i;
+  int lv = bd[last];
+  for (int i = last; i + 1 < bn; ++i) bd[i] = bd[i + 1];
+  bd[bn - 1] = lv;
+  for (int i = 0; i < bn; ++i) dims[i] = bd[i];
+  *nd = bn;
+  return true;
+}
+
+inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd) {
+  if (n < 1 || nd < 1 || nd > kMaxDims) return false;
+  g.n = n;
+  g.nd = nd;
+  int64_t M = 1;
+  for (int a = 0; a < nd; ++a) {
+    if (!menu_find(dims[a])) return false;
+    g.dims[a] = dims[a];
+    M *= dims[a];
+  }
+  if (M < n || M >= 2147483648LL) return false;
+  g.M = M;
+  g.L = 2 * M;
+  g.S[nd] = 1;
+  for (int a = nd - 1; a >= 0; --a) g.S[a] = g.S[a + 1] * dims[a];
+  int sh = 1;
+  while ((1LL << (2 * sh)) < M) ++sh;
+  g.tw_shift = sh;
+  // mirrored-row regions (rows of length N_p): region r <-> first non-zero digit a0 = r+1
+  const int64_t Np = dims[nd - 1];
+  g.n_regions = nd - 1;
+  int64_t next = 1;                       // pair 0 is row 0 paired with itself
+  for (int r = 0; r < g.n_regions; ++r) {
+    g.region_lo[r] = g.S[r + 1] / Np;
+    g.region_hi[r] = g.S[r] / Np;
+    g.pair_start[r] = next;
+    next += (g.region_hi[r] - g.region_lo[r] + 1) / 2;
+  }
+  g.pair_start[g.n_regions] = next;
+  g.n_pairs_rows = next;
+  return true;
+}
+
+// ---- twiddle tables (computed in long double, stored in T) ----
+template <class T> inline cx<T> unit_root(int64_t num, int64_t den) {   // exp(-2 pi i num/den)
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  long double a = two_pi * (long double)(num % den) / (long double)den;
+  cx<T> r;
+  r.x = (T)cosl(a);
+  r.y = (T)(-sinl(a));
+  return r;
+}
+
+template <class T> struct HostTables {
+  std::vector<cx<T>> hi, lo;
+  std::vector<cx<T>> inner[kMaxDims];
+};
+
+template <class T> inline void build_tables(const PlanGeom& g, HostTables<T>& t) {
+  const int64_t step = 1LL << g.tw_shift;
+  t.lo.resize(step);
+  for (int64_t j = 0; j < step; ++j) t.lo[j] = unit_root<T>(j, g.M);
+  int64_t nh = (g.M + step - 1) / step;
+  t.hi.resize(nh);
+  for (int64_t h = 0; h < nh; ++h) t.hi[h] = unit_root<T>(h * step, g.M);
+  for (int a = 0; a < g.nd; ++a) {
+    t.inner[a].resize(g.dims[a]);
+    for (int k = 0; k < g.dims[a]; ++k) t.inner[a][k] = unit_root<T>(k, g.dims[a]);
+  }
+}
+
+template <class T> struct DevTables {      // pointers valid where the passes run
+  const cx<T>* hi = nullptr;
+  const cx<T>* lo = nullptr;
+  const cx<T>* inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+template <class T> inline int tile_cols() { return 128 / (2 * (int)sizeof(T)); }
+
+template <class T> inline void pass_common(PassParams<T>& p, const PlanGeom& g, const DevTables<T>& tb, int a) {
+  p = PassParams<T>();
+  const int C = tile_cols<T>();
+  p.N = g.dims[a];
+  p.M = g.M;
+  p.tw_hi = tb.hi;
+  p.tw_lo = tb.lo;
+  p.tw_inner = tb.inner[a];
+  p.tw_shift = g.tw_shift;
+  p.tw_mask = (uint32_t)((1LL << g.tw_shift) - 1);
+  p.nd = g.nd;
+  for (int i = 0; i < kMaxDims; ++i) p.dims[i] = g.dims[i];
+  p.n = g.n;
+  p.L = g.L;
+  if (a < g.nd - 1) {
+    p.inner = g.S[a + 1];
+    p.col_tiles = (p.inner + C - 1) / C;
+    p.tiles_per_batch = (g.M / g.S[a]) * p.col_tiles;
+    p.tw_scale = (uint32_t)(g.M / g.S[a]);
+  } else {
+    p.inner = 1;
+    p.rows = g.M / p.N;
+    p.tiles_per_batch = (p.rows + C - 1) / C;
+  }
+}
+
+// forward pass a: x (real) -> spec for a == 0, spec in place otherwise
+template <class T>
+inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb, int a, const T* x,
+                                       int64_t x_stride, cx<T>* spec, int64_t spec_stride, int n_signals,
+                                       double* sumsq_partial) {
+  PassParams<T> p;
+  pass_common(p, g, tb, a);
+  p.n_batch = n_signals;
+  p.out = spec;
+  p.out_stride = spec_stride;
+  if (a == 0) {
+    p.in = x;
+    p.in_stride = x_stride;
+    p.n_real = g.n;
+    p.real_vec_ok = ((reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T))) == 0 && x_stride % 2 == 0) ? 1 : 0;
+    p.sumsq_partial = sumsq_partial;
+  } else {
+    p.in = spec;
+    p.in_stride = spec_stride;
+  }
+  if (a < g.nd - 1) {
+    p.load_mode = (a == 0) ? CL_REAL : CL_CPLX;
+    p.store_mode = CS_TW;
+  } else {
+    p.load_mode = (a == 0) ? RL_REAL : RL_CPLX;
+    p.store_mode = RS_CPLX;
+  }
+  return p;
+}
+
+struct CorrFlags {
+  int64_t i0 = 0, i1 = 0;
+  int normalize = 1, unbiased = 0, accumulate = 0;
+};
+
+// inverse pass a (run a = nd-1 down to 0) over `n_jobs` jobs using work[n_jobs][M]
+template <class T>
+inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb, int a, const cx<T>* spec,
+                                       const double* sumsq, const Job* jobs, int n_jobs, cx<T>* work,
+                                       T* ccf, const CorrFlags& f) {
+  PassParams<T> p;
+  pass_common(p, g, tb, a);
+  const int C = tile_cols<T>();
+  p.n_batch = n_jobs;
+  p.in = work;
+  p.out = work;
+  p.in_stride = p.out_stride = g.M;
+  p.jobs = jobs;
+  p.sumsq = sumsq;
+  p.spec = spec;
+  p.normalize = f.normalize;
+  p.ccf = ccf;
+  p.i0 = f.i0;
+  p.i1 = f.i1;
+  p.escale = (T)(1.0 / (double)g.M);
+  p.unbiased = f.unbiased;
+  p.accumulate = f.accumulate;
+  p.n_regions = g.n_regions;
+  for (int r = 0; r < kMaxDims; ++r) { p.region_lo[r] = g.region_lo[r]; p.region_hi[r] = g.region_hi[r]; }
+  for (int r = 0; r <= kMaxDims; ++r) p.pair_start[r] = g.pair_start[r];
+  p.n_pairs_rows = g.n_pairs_rows;
+  if (a == g.nd - 1) {
+    p.load_mode = RL_PROLOGUE;
+    p.store_mode = (g.nd == 1) ? RS_EPI : RS_CONJ;
+    p.tiles_per_batch = (g.n_pairs_rows + (C / 2) - 1) / (C / 2);
+  } else {
+    p.load_mode = CL_CPLX_INV;
+    p.store_mode = (a == 0) ? CS_EPI : CS_CONJ;
+  }
+  return p;
+}
+
+}  // namespace xcb
