@@ -1,0 +1,128 @@
+/* xcorr_b200 -- C ABI of the B200 cross-correlation hot path.
+ *
+ * The reference (psmsmets/xcorr) is pure Python and has no FFI; these entry
+ * points are what a binding for its hot path would call.  Each one names the
+ * reference interface it replaces (paths relative to the reference's xcorr/).
+ *
+ * Conventions
+ *   - every function returns 0 (XCB_OK) or a negative xcb_status; no C++
+ *     exception crosses the boundary; xcb_strerror() explains a code;
+ *   - "device" pointers are caller-owned CUDA device memory (the Python host
+ *     side passes torch tensors' data_ptr()); `stream` is a cudaStream_t passed
+ *     as void* (NULL = default stream); device calls are asynchronous on it;
+ *   - a plan is immutable after creation and may be shared by threads; the
+ *     workspace belongs to one stream at a time;
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with XCB_ERR_CUDA.
+ */
+#ifndef XCORR_B200_H
+#define XCORR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XCB_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define XCB_API __attribute__((visibility("default")))
+#else
+#define XCB_API
+#endif
+
+typedef enum xcb_status {
+  XCB_OK = 0,
+  XCB_ERR_ARG = -1,      /* invalid argument / descriptor                      */
+  XCB_ERR_SIZE = -2,     /* no supported transform length covers n             */
+  XCB_ERR_CUDA = -3,     /* CUDA runtime error (see xcb_last_cuda_error)       */
+  XCB_ERR_ALLOC = -4,    /* host or device allocation failed                   */
+  XCB_ERR_UNSUPPORTED = -5
+} xcb_status;
+
+typedef enum xcb_dtype { XCB_F32 = 0, XCB_F64 = 1 } xcb_dtype;
+
+typedef struct xcb_plan xcb_plan;
+
+/* Describes one batch of the reference's hot loop (core/process.py:82-165):
+ * n_receivers signals per window, n_windows windows, n_pairs receiver pairs,
+ * one cc() per (pair, window) cropped to [lag_index_min, lag_index_max). */
+typedef struct xcb_desc {
+  int64_t n;               /* samples per window at the correlation rate (lag.attrs['npts'], core/init.py:120) */
+  int32_t dtype;           /* xcb_dtype: dataset.cc.dtype (core/init.py:30); inputs are cast to it before the FFT (util/cc.py:68-71) */
+  int32_t nd;              /* 0: choose the transform automatically; else number of passes */
+  int32_t dims[4];         /* pass lengths when nd > 0 (testing / tuning) */
+  int32_t n_receivers;
+  int32_t n_windows;
+  int32_t n_pairs;
+  int32_t recv_stride;     /* signal index of (receiver r, window w) = r*recv_stride + w*win_stride; 0,0 -> [receiver][window] */
+  int32_t win_stride;
+  int32_t normalize;       /* util/cc.py:76-77 */
+  int32_t unbiased;        /* intended util/cc.py:79 == signal/unbias.py:85 weights n/(n-|k|) */
+  int32_t stack;           /* 1: ccf[pair][lag] accumulates over windows instead of ccf[pair][window][lag] */
+  const int32_t* pairs;    /* host, [n_pairs][2] receiver indices (i, j): Rxy[k] = sum_m x_i[m+k] x_j[m] */
+  int64_t lag_index_min;   /* lag.attrs['index_min'] (core/init.py:191-208, util/time.py:94-108) */
+  int64_t lag_index_max;   /* exclusive; both 0 -> full 2n-1 lags */
+  int64_t max_work_bytes;  /* cap for the inverse-transform scratch; 0 -> 4 GiB */
+} xcb_desc;
+
+typedef struct xcb_plan_info {
+  int64_t n, fft_len;      /* L = 2M >= 2n-1 */
+  int64_t spectrum_elems;  /* M complex elements per signal in `spec` */
+  int64_t n_lags;          /* K = lag_index_max - lag_index_min */
+  int64_t n_signals;       /* n_receivers * n_windows */
+  int64_t n_jobs;          /* n_pairs * n_windows */
+  int64_t jobs_in_flight;
+  size_t workspace_bytes;
+  int32_t nd;
+  int32_t dims[4];
+  int32_t dtype;
+} xcb_plan_info;
+
+XCB_API const char* xcb_strerror(int status);
+XCB_API const char* xcb_last_cuda_error(void);   /* thread-local text of the last CUDA failure */
+XCB_API int xcb_version(void);
+
+/* Transform length the planner picks for n samples (host only, no GPU needed). */
+XCB_API int xcb_choose_transform(int64_t n, int32_t dims[4], int32_t* nd);
+
+/* Creates twiddle tables and the job table on the current CUDA device. */
+XCB_API int xcb_plan_create(xcb_plan** plan, const xcb_desc* desc);
+XCB_API int xcb_plan_destroy(xcb_plan* plan);
+XCB_API int xcb_plan_get_info(const xcb_plan* plan, xcb_plan_info* info);
+
+/* Per receiver-window: cast/zero-pad, forward transform, sum of squares.
+ * Replaces the two fft() calls and both np.linalg.norm() of util/cc.py:66-77,
+ * done once per receiver-window instead of once per pair.
+ *   x      device, dtype[n_signals][x_stride] (x_stride >= n)
+ *   spec   device, complex<dtype>[n_signals][spectrum_elems] (digit-transposed packed spectrum)
+ *   sumsq  device, double[n_signals] */
+XCB_API int xcb_forward(const xcb_plan* plan, const void* x, int64_t x_stride, void* spec, double* sumsq,
+                void* workspace, void* stream);
+
+/* Per (pair, window): conjugate product, inverse transform, fftshift, crop,
+ * scaling.  Replaces util/cc.py:75-79 and the [index_min:index_max] slice of
+ * core/process.py:155-162 (+ signal/unbias.py:85 when desc.unbiased).
+ *   ccf    device, dtype[n_pairs][n_windows][n_lags]  (or [n_pairs][n_lags] when stacking;
+ *          the caller zero-fills it before the first stacked call) */
+XCB_API int xcb_correlate(const xcb_plan* plan, const void* spec, const double* sumsq, void* ccf,
+                  void* workspace, void* stream);
+
+/* First index of the maximum of each row (np.argmax semantics, util/cc.py:144-206).
+ *   rows   device, dtype[n_rows][row_len];  index device int64[n_rows];  value device dtype[n_rows] or NULL */
+XCB_API int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64_t row_len, int64_t* index,
+               void* value, void* stream);
+
+/* cc(x, y, normalize, pad=True, unbiased, dtype) with HOST buffers
+ * (util/cc.py:22-79): copies in, runs the device path, copies the
+ * [lag_index_min, lag_index_max) lags back, synchronises.  out has
+ * (lag_index_max - lag_index_min) elements (both 0 -> 2n-1). */
+XCB_API int xcb_cc_host(int32_t dtype, int64_t n, const void* x, const void* y, int32_t normalize,
+                int32_t unbiased, int64_t lag_index_min, int64_t lag_index_max, void* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XCORR_B200_H */

@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle and the golden vectors generated from the reference itself.
+
+Tolerances (BASELINE.json north_star): argmax lag bit-exact; float64 within
+1e-12 of the peak; float32 within 1e-5 of the peak.
+"""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+@pytest.fixture(scope="module")
+def xb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import xcorr_b200
+    return xcorr_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import cc_oracle
+    return cc_oracle
+
+
+def test_cc_matches_reference_golden_vectors(xb, golden):
+    checked = 0
+    for name, kw in zip(golden["_cases"].tolist(), golden["_kwargs"].tolist()):
+        kw = json.loads(kw)
+        if "dtype" in kw:
+            kw["dtype"] = np.dtype(kw["dtype"])
+        x, y, r = golden[name + "_x"], golden[name + "_y"], golden[name + "_r"]
+        got = xb.cc(x, y, unbiased=False, **kw)
+        assert got.shape == r.shape and got.dtype == r.dtype, name
+        if name == "zero":
+            assert np.all(np.isnan(got)) and np.all(np.isnan(r))
+            continue
+        peak = np.max(np.abs(r))
+        assert np.max(np.abs(got - r)) <= TOL[r.dtype] * peak, name
+        if r.dtype == np.float64 and len(r) > 8:
+            assert np.argmax(got) == np.argmax(r), name
+        checked += 1
+    assert checked >= 29
+
+
+def test_shift_helpers_and_unbiased(xb, orc, golden):
+    x, y = golden["shift7_x"], golden["shift7_y"]
+    assert xb.compute_shift(x, y, unbiased=False) == -7
+    s, m = xb.compute_shift_and_max(x, y, 0.02, unbiased=False)
+    assert s == golden["shift7_extract_max"][0]
+    assert abs(m - golden["shift7_extract_max"][1]) < 1e-12
+    ub = xb.cc(x, y, unbiased=True)
+    ref = orc.cc(x, y, unbiased=True)
+    assert np.max(np.abs(ub - ref)) <= 1e-12 * np.max(np.abs(ref))
+    with pytest.raises(AssertionError):
+        xb.cc(np.zeros(3), np.zeros(4))
+    with pytest.raises(AssertionError):
+        xb.cc(np.zeros(3), np.zeros(3, dtype=np.float32))
+
+
+MENU = [64, 80, 96, 100, 120, 128, 144, 150, 160, 180, 192, 200, 225, 240, 256, 300, 320, 400]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_every_kernel_size_in_every_role(xb, orc, dtype):
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    for N in MENU:
+        # single pass: row kernel with real-input load + pair product + lag epilogue
+        n = N - 3
+        rec = orc.synthetic_receivers(3, n, seed=N, delay=5)
+        plan = xb.CorrelationPlan(n, 3, [(0, 1), (2, 0)], dtype=tdt, dims=(N,))
+        got = plan(torch.from_numpy(rec.astype(dtype)).cuda()).cpu().numpy()[:, 0]
+        for q, (i, j) in enumerate([(0, 1), (2, 0)]):
+            ref = orc.cc(rec[i], rec[j], unbiased=False)
+            assert np.max(np.abs(got[q] - ref)) <= TOL[np.dtype(dtype)] * np.max(np.abs(ref)), (N, "row")
+        # three passes: N as first (column, real in / epilogue) and middle column pass
+        dims = (N, N, 64)
+        n = N * N * 64 - 11
+        rec = orc.synthetic_receivers(2, n, seed=N + 1, delay=137)
+        plan = xb.CorrelationPlan(n, 2, [(0, 1)], dtype=tdt, dims=dims, index_min=n - 1 - 500, index_max=n - 1 + 1500)
+        got = plan(torch.from_numpy(rec.astype(dtype)).cuda()).cpu().numpy()[0, 0]
+        ref = orc.cc_smooth(rec[0], rec[1])
+        peak = np.max(np.abs(ref))
+        ref = ref[n - 1 - 500:n - 1 + 1500]
+        assert np.max(np.abs(got - ref)) <= TOL[np.dtype(dtype)] * peak, (N, "col")
+        assert np.argmax(got) == np.argmax(ref) == 500 + 137
+        del plan
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batched_plan_all_pairs_windows_crop(xb, orc, dtype):
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    n, R, W = 20_000, 4, 3
+    pairs = xb.all_pairs(R, auto=True)
+    rec = np.stack([orc.synthetic_receivers(R, n, seed=100 + w, delay=61) for w in range(W)], axis=1)  # [R, W, n]
+    i0, i1 = orc.lag_clip_indices(n, 0.02, (-50.0, 120.0))
+    x = torch.from_numpy(rec.astype(dtype)).cuda()
+    plan = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i1)
+    ccf = plan(x)
+    idx, val = plan.argmax(ccf)
+    got = ccf.cpu().numpy()
+    assert got.shape == (len(pairs), W, i1 - i0)
+    for q, (i, j) in enumerate(pairs):
+        for w in range(W):
+            ref = orc.cc(rec[i, w], rec[j, w], unbiased=False)
+            peak = np.max(np.abs(ref))
+            ref = ref[i0:i1]
+            assert np.max(np.abs(got[q, w] - ref)) <= TOL[np.dtype(dtype)] * peak
+            assert int(idx[q, w]) == int(np.argmax(ref)) == (n - 1 - i0) + 61 * (j - i)
+            assert float(val[q, w]) == got[q, w, int(idx[q, w])]
+    # unbiased weights fused into the epilogue == signal/unbias.py:85
+    plan_u = xb.CorrelationPlan(n, R, pairs[:3], n_windows=W, dtype=tdt, index_min=i0, index_max=i1, unbiased=True)
+    got_u = plan_u(x).cpu().numpy()
+    for q, (i, j) in enumerate(pairs[:3]):
+        ref = orc.process_cell(rec[i, 0], rec[j, 0], n, i0, i1, dtype=np.float64, bias_correct=True)
+        assert np.max(np.abs(got_u[q, 0] - ref)) <= 20 * TOL[np.dtype(dtype)] * np.max(np.abs(ref))
+    # stacking over windows
+    plan_s = xb.CorrelationPlan(n, R, pairs[:4], n_windows=W, dtype=tdt, index_min=i0, index_max=i1, stack=True)
+    got_s = plan_s(x).cpu().numpy()
+    for q in range(4):
+        ref = got[q].astype(np.float64).sum(axis=0)
+        assert np.max(np.abs(got_s[q] - ref)) <= 4 * TOL[np.dtype(dtype)] * np.max(np.abs(ref))
+    # normalize=False
+    plan_n = xb.CorrelationPlan(n, R, [(0, 1)], n_windows=W, dtype=tdt, normalize=False)
+    got_n = plan_n(x).cpu().numpy()
+    ref = orc.cc(rec[0, 1], rec[1, 1], normalize=False, unbiased=False)
+    assert np.max(np.abs(got_n[0, 1] - ref)) <= TOL[np.dtype(dtype)] * np.max(np.abs(ref))
+
+
+def test_spectra_are_bit_reproducible(xb, orc):
+    import torch
+    rec = orc.synthetic_receivers(3, 100_000, seed=9)
+    x = torch.from_numpy(rec.astype(np.float32)).cuda()
+    plan = xb.CorrelationPlan(100_000, 3, xb.all_pairs(3), dtype=torch.float32)
+    a = plan(x).clone()
+    ss = plan.sumsq.clone()
+    b = plan(x)
+    assert torch.equal(a, b) and torch.equal(ss, plan.sumsq)
+    assert np.allclose(ss.cpu().numpy(), np.sum(rec.astype(np.float32).astype(np.float64) ** 2, axis=1), rtol=1e-13)
+
+
+def test_argmax_semantics(xb):
+    import torch
+    plan = xb.CorrelationPlan(100, 2, [(0, 1)])
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((7, 100_003)).astype(np.float32)
+    a[1, 500] = a[1, 90_000] = 9.0          # tie -> first index
+    a[2, :] = -1.0                           # all equal
+    a[3, 77_777] = np.nan                    # NaN wins, like np.argmax
+    a[4, 0] = 50.0
+    a[5, -1] = 50.0
+    idx, val = plan.argmax(torch.from_numpy(a).cuda())
+    assert idx.cpu().tolist() == np.argmax(a, axis=1).tolist()
+    v = val.cpu().numpy()
+    assert np.isnan(v[3]) and v[1] == 9.0 and v[4] == 50.0
+    a64 = rng.standard_normal((3, 1000))
+    idx, _ = plan.argmax(torch.from_numpy(a64).cuda())
+    assert idx.cpu().tolist() == np.argmax(a64, axis=1).tolist()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_day_at_50hz_against_oracle(xb, orc, dtype):
+    """BASELINE config 1 shape: 24 h @ 50 Hz, n = 4.32 M, production crop (0, 9 h)."""
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    n = 4_320_000
+    rec = orc.synthetic_receivers(2, n, seed=1000, delay=137)
+    i0, i1 = n - 1, n - 1 + 1_620_000
+    plan = xb.CorrelationPlan(n, 2, [(0, 1)], dtype=tdt, index_min=i0, index_max=i1)
+    assert int(np.prod(plan.dims)) == n
+    got = plan(torch.from_numpy(rec.astype(dtype)).cuda()).cpu().numpy()[0, 0]
+    ref = orc.cc_smooth(rec[0], rec[1])
+    peak = np.max(np.abs(ref))
+    ref = ref[i0:i1]
+    assert np.argmax(got) == np.argmax(ref) == 137
+    assert np.max(np.abs(got - ref)) <= TOL[np.dtype(dtype)] * peak
+    if dtype == np.float64:
+        # full cc() through the host-buffer C entry, all 2n-1 lags
+        full = xb.cc(rec[0], rec[1], unbiased=False)
+        assert np.max(np.abs(full[i0:i1] - ref)) <= 1e-12 * peak
+        assert xb.extract_shift(full) == 137
+
+
+def test_day_at_250hz_full_size(xb, orc):
+    """BASELINE configs 2-3 shape: n = 21.6 M, L = 43.2 M, K = 8.1 M lags, float32;
+    oracle = smooth-length rfft restatement (the reference's own Bluestein path
+    takes ~75 s per pair) plus size-independent properties."""
+    import torch
+    n = 21_600_000
+    rec = orc.synthetic_receivers(3, n, seed=3000, delay=137).astype(np.float32)
+    i0, i1 = n - 1, n - 1 + 8_100_000
+    pairs = [(0, 1), (0, 2), (1, 2), (1, 0)]
+    plan = xb.CorrelationPlan(n, 3, pairs, dtype=torch.float32, index_min=i0, index_max=i1)
+    assert int(np.prod(plan.dims)) == n
+    x = torch.from_numpy(rec).cuda()
+    ccf = plan(x)
+    idx, val = plan.argmax(ccf)
+    assert idx[:, 0].cpu().tolist()[:3] == [137, 274, 137]
+    got = ccf[0, 0].cpu().numpy()
+    ref = orc.cc_smooth(rec[0].astype(np.float64), rec[1].astype(np.float64))
+    peak = np.max(np.abs(ref))
+    assert np.max(np.abs(got - ref[i0:i1])) <= 1e-5 * peak
+    # symmetry: cc(y, x)[k] == cc(x, y)[-k]  -> zero lag agrees between (0,1) and (1,0)
+    assert abs(float(ccf[0, 0, 0]) - float(ccf[3, 0, 0])) <= 1e-6
+    # linearity in the first argument: cc(a*x0 + x2', x1) -- checked through un-normalised plan
+    plan_n = xb.CorrelationPlan(n, 3, [(0, 1), (2, 1)], dtype=torch.float32, index_min=i0, index_max=i0 + 4096, normalize=False)
+    base = plan_n(x).double()
+    x2 = x.clone()
+    x2[0] = 2.0 * x[0] + x[2]
+    mix = plan_n(x2).double()
+    lin = 2.0 * base[0] + base[1]
+    assert float((mix[0] - lin).abs().max()) <= 1e-5 * float(lin.abs().max())

@@ -1,0 +1,461 @@
+// C ABI of libxcorr_b200 (see include/xcorr_b200.h): plans, forward
+// transforms, pair correlation, argmax, and the host-buffer cc() entry.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/xcorr_b200.h"
+#include "xcb_launch.h"
+#include "xcb_plan.h"
+
+using namespace xcb;
+
+// ---------------------------------------------------------------------------
+// launch table
+// ---------------------------------------------------------------------------
+namespace xcb {
+
+static LaunchTable g_tables[2];
+static std::once_flag g_tables_once;
+
+static void init_tables() {
+  g_tables[0].count = g_tables[1].count = 0;
+  xcb_register_dt0_g0(&g_tables[0]); xcb_register_dt0_g1(&g_tables[0]); xcb_register_dt0_g2(&g_tables[0]);
+  xcb_register_dt0_g3(&g_tables[0]); xcb_register_dt0_g4(&g_tables[0]); xcb_register_dt0_g5(&g_tables[0]);
+  xcb_register_dt1_g0(&g_tables[1]); xcb_register_dt1_g1(&g_tables[1]); xcb_register_dt1_g2(&g_tables[1]);
+  xcb_register_dt1_g3(&g_tables[1]); xcb_register_dt1_g4(&g_tables[1]); xcb_register_dt1_g5(&g_tables[1]);
+}
+
+LaunchTable& launch_table(int dtype) {
+  std::call_once(g_tables_once, init_tables);
+  return g_tables[dtype ? 1 : 0];
+}
+
+const PassLauncher* find_launcher(int dtype, int N) {
+  LaunchTable& t = launch_table(dtype);
+  for (int i = 0; i < t.count; ++i) if (t.e[i].N == N) return &t.e[i];
+  return nullptr;
+}
+
+}  // namespace xcb
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* where) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+  return XCB_ERR_CUDA;
+}
+#define XCB_CUDA(call)                                         \
+  do {                                                         \
+    cudaError_t e_ = (call);                                   \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
+  } while (0)
+
+extern "C" const char* xcb_strerror(int status) {
+  switch (status) {
+    case XCB_OK: return "ok";
+    case XCB_ERR_ARG: return "invalid argument";
+    case XCB_ERR_SIZE: return "no supported transform length for this n";
+    case XCB_ERR_CUDA: return "CUDA error (see xcb_last_cuda_error)";
+    case XCB_ERR_ALLOC: return "allocation failed";
+    case XCB_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown status";
+}
+extern "C" const char* xcb_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int xcb_version(void) { return XCB_VERSION; }
+
+extern "C" int xcb_choose_transform(int64_t n, int32_t dims[4], int32_t* nd) {
+  if (n < 1 || !dims || !nd) return XCB_ERR_ARG;
+  int d[kMaxDims] = {0, 0, 0, 0}, k = 0;
+  if (!plan_choose_dims(n, d, &k)) return XCB_ERR_SIZE;
+  for (int i = 0; i < 4; ++i) dims[i] = d[i];
+  *nd = k;
+  return XCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------
+// sumsq[s] = sum of the per-tile partial sums, fixed order -> bit-reproducible
+__global__ void __launch_bounds__(256) xcb_sumsq_finish(const double* __restrict__ partial, int64_t tiles,
+                                                        double* __restrict__ sumsq) {
+  __shared__ double red[256];
+  const double* p = partial + (int64_t)blockIdx.x * tiles;
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < tiles; i += 256) a += p[i];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  block_sumsq<256>(sumsq + blockIdx.x, red, threadIdx.x);
+}
+
+// First index of the row maximum (np.argmax): two stages, ties -> lowest index.
+template <class T>
+__global__ void __launch_bounds__(256) xcb_argmax_partial(const T* __restrict__ rows, int64_t row_len, int chunks,
+                                                          T* __restrict__ pval, int64_t* __restrict__ pidx) {
+  const int64_t row = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int64_t per = (row_len + chunks - 1) / chunks;
+  const int64_t lo = (int64_t)chunk * per;
+  int64_t hi = lo + per;
+  if (hi > row_len) hi = row_len;
+  const T* r = rows + row * row_len;
+  bool have = false, isnan_ = false;
+  T best = T(0);
+  int64_t bi = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    T v = r[i];
+    if (v != v) { if (!isnan_) { isnan_ = true; best = v; bi = i; have = true; } continue; }  // np.argmax: first NaN wins
+    if (!isnan_ && (!have || v > best)) { best = v; bi = i; have = true; }
+  }
+  __shared__ T sv[256];
+  __shared__ int64_t si[256];
+  __shared__ int sh[256];   // 0 none, 1 value, 2 nan
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi; sh[threadIdx.x] = have ? (isnan_ ? 2 : 1) : 0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      int a = threadIdx.x, b = threadIdx.x + o;
+      bool take = false;
+      if (sh[b] > sh[a]) take = true;
+      else if (sh[b] == sh[a] && sh[b] == 2) take = si[b] < si[a];
+      else if (sh[b] == sh[a] && sh[b] == 1) take = (sv[b] > sv[a]) || (sv[b] == sv[a] && si[b] < si[a]);
+      if (take) { sv[a] = sv[b]; si[a] = si[b]; sh[a] = sh[b]; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    pval[row * chunks + chunk] = sv[0];
+    pidx[row * chunks + chunk] = sh[0] ? si[0] : (int64_t)-1;
+  }
+}
+
+template <class T>
+__global__ void xcb_argmax_final_rows(const T* __restrict__ pval, const int64_t* __restrict__ pidx, int chunks,
+                                      int64_t n_rows, int64_t* __restrict__ index, T* __restrict__ value) {
+  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  bool have = false, isnan_ = false;
+  T best = T(0);
+  int64_t bi = 0;
+  for (int c = 0; c < chunks; ++c) {        // chunks are in index order
+    int64_t i = pidx[row * chunks + c];
+    if (i < 0) continue;
+    T v = pval[row * chunks + c];
+    if (v != v) { if (!isnan_) { isnan_ = true; best = v; bi = i; have = true; } continue; }
+    if (!isnan_ && (!have || v > best)) { best = v; bi = i; have = true; }
+  }
+  index[row] = have ? bi : 0;
+  if (value) value[row] = best;
+}
+
+// ---------------------------------------------------------------------------
+// plan
+// ---------------------------------------------------------------------------
+struct xcb_plan {
+  xcb_desc desc;
+  std::vector<int32_t> pairs;
+  PlanGeom g;
+  int dtype = 0;
+  int device = 0;
+  int64_t K = 0, i0 = 0, i1 = 0;
+  int64_t n_signals = 0, n_jobs = 0, jobs_in_flight = 0;
+  int64_t tiles0 = 0;               // CTAs per signal of the first forward pass
+  size_t work_bytes = 0, partial_bytes = 0;
+  void* d_hi = nullptr;
+  void* d_lo = nullptr;
+  void* d_inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+  Job* d_jobs = nullptr;
+  const PassLauncher* launch[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+template <class T> static int upload_tables(xcb_plan* pl) {
+  HostTables<T> ht;
+  build_tables(pl->g, ht);
+  XCB_CUDA(cudaMalloc(&pl->d_hi, ht.hi.size() * sizeof(cx<T>)));
+  XCB_CUDA(cudaMemcpy(pl->d_hi, ht.hi.data(), ht.hi.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  XCB_CUDA(cudaMalloc(&pl->d_lo, ht.lo.size() * sizeof(cx<T>)));
+  XCB_CUDA(cudaMemcpy(pl->d_lo, ht.lo.data(), ht.lo.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  for (int a = 0; a < pl->g.nd; ++a) {
+    XCB_CUDA(cudaMalloc(&pl->d_inner[a], ht.inner[a].size() * sizeof(cx<T>)));
+    XCB_CUDA(cudaMemcpy(pl->d_inner[a], ht.inner[a].data(), ht.inner[a].size() * sizeof(cx<T>),
+                        cudaMemcpyHostToDevice));
+  }
+  return XCB_OK;
+}
+
+template <class T> static DevTables<T> dev_tables(const xcb_plan* pl) {
+  DevTables<T> tb;
+  tb.hi = static_cast<const cx<T>*>(pl->d_hi);
+  tb.lo = static_cast<const cx<T>*>(pl->d_lo);
+  for (int a = 0; a < pl->g.nd; ++a) tb.inner[a] = static_cast<const cx<T>*>(pl->d_inner[a]);
+  return tb;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" int xcb_plan_destroy(xcb_plan* pl) {
+  if (!pl) return XCB_OK;
+  cudaFree(pl->d_hi);
+  cudaFree(pl->d_lo);
+  for (int a = 0; a < kMaxDims; ++a) cudaFree(pl->d_inner[a]);
+  cudaFree(pl->d_jobs);
+  delete pl;
+  return XCB_OK;
+}
+
+extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
+  if (!out || !d) return XCB_ERR_ARG;
+  *out = nullptr;
+  if (d->n < 1 || (d->dtype != XCB_F32 && d->dtype != XCB_F64)) return XCB_ERR_ARG;
+  if (d->n_receivers < 1 || d->n_windows < 1 || d->n_pairs < 0 || (d->n_pairs > 0 && !d->pairs)) return XCB_ERR_ARG;
+  if (d->nd < 0 || d->nd > kMaxDims) return XCB_ERR_ARG;
+  xcb_plan* pl = new (std::nothrow) xcb_plan();
+  if (!pl) return XCB_ERR_ALLOC;
+  pl->desc = *d;
+  pl->dtype = d->dtype;
+  pl->pairs.assign(d->pairs, d->pairs + 2 * (size_t)d->n_pairs);
+  pl->desc.pairs = nullptr;
+  for (int q = 0; q < 2 * d->n_pairs; ++q)
+    if (pl->pairs[q] < 0 || pl->pairs[q] >= d->n_receivers) { delete pl; return XCB_ERR_ARG; }
+
+  int dims[kMaxDims] = {0, 0, 0, 0}, nd = d->nd;
+  if (nd == 0) {
+    if (!plan_choose_dims(d->n, dims, &nd)) { delete pl; return XCB_ERR_SIZE; }
+  } else {
+    for (int a = 0; a < nd; ++a) dims[a] = d->dims[a];
+  }
+  if (!plan_geom_init(pl->g, d->n, dims, nd)) { delete pl; return XCB_ERR_SIZE; }
+
+  pl->i0 = d->lag_index_min;
+  pl->i1 = d->lag_index_max;
+  if (pl->i0 == 0 && pl->i1 == 0) pl->i1 = 2 * d->n - 1;
+  if (pl->i0 < 0 || pl->i1 > 2 * d->n - 1 || pl->i0 >= pl->i1) { delete pl; return XCB_ERR_ARG; }
+  pl->K = pl->i1 - pl->i0;
+  pl->n_signals = (int64_t)d->n_receivers * d->n_windows;
+  pl->n_jobs = (int64_t)d->n_pairs * d->n_windows;
+
+  { cudaError_t e = cudaGetDevice(&pl->device); if (e != cudaSuccess) { delete pl; return cuda_fail(e, "cudaGetDevice"); } }
+  for (int a = 0; a < nd; ++a) {
+    pl->launch[a] = find_launcher(pl->dtype, dims[a]);
+    if (!pl->launch[a]) { delete pl; return XCB_ERR_SIZE; }
+    int e = pl->launch[a]->prepare();
+    if (e) { delete pl; return cuda_fail((cudaError_t)e, "cudaFuncSetAttribute"); }
+  }
+  int rc = pl->dtype == XCB_F32 ? upload_tables<float>(pl) : upload_tables<double>(pl);
+  if (rc) { xcb_plan_destroy(pl); return rc; }
+
+  // job table: job = w * n_pairs + p  (window-major, so a stacked launch never
+  // holds two jobs that write the same output row)
+  const int64_t rs = (d->recv_stride == 0 && d->win_stride == 0) ? d->n_windows : d->recv_stride;
+  const int64_t ws = (d->recv_stride == 0 && d->win_stride == 0) ? 1 : d->win_stride;
+  if (pl->n_jobs > 0) {
+    std::vector<Job> jobs((size_t)pl->n_jobs);
+    for (int64_t w = 0; w < d->n_windows; ++w)
+      for (int64_t q = 0; q < d->n_pairs; ++q) {
+        Job& j = jobs[(size_t)(w * d->n_pairs + q)];
+        int64_t si = pl->pairs[2 * q] * rs + w * ws, sj = pl->pairs[2 * q + 1] * rs + w * ws;
+        j.sig_i = (int32_t)si;
+        j.sig_j = (int32_t)sj;
+        j.spec_i = si * pl->g.M;
+        j.spec_j = sj * pl->g.M;
+        j.out_off = d->stack ? q * pl->K : (q * d->n_windows + w) * pl->K;
+      }
+    cudaError_t e = cudaMalloc(&pl->d_jobs, jobs.size() * sizeof(Job));
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "job table"); }
+  }
+
+  // workspace: [sumsq partials][inverse scratch]
+  const int C = pl->dtype == XCB_F32 ? tile_cols<float>() : tile_cols<double>();
+  if (nd > 1) pl->tiles0 = (pl->g.M / pl->g.S[0]) * ((pl->g.S[1] + C - 1) / C);
+  else pl->tiles0 = (pl->g.M / dims[0] + C - 1) / C;
+  pl->partial_bytes = align_up((size_t)pl->n_signals * pl->tiles0 * sizeof(double), 256);
+  const size_t per_job = (size_t)pl->g.M * (pl->dtype == XCB_F32 ? 8 : 16);
+  size_t cap = d->max_work_bytes > 0 ? (size_t)d->max_work_bytes : ((size_t)4 << 30);
+  int64_t fl = (int64_t)(cap / per_job);
+  if (fl < 1) fl = 1;
+  if (d->stack && fl > d->n_pairs) fl = d->n_pairs > 0 ? d->n_pairs : 1;   // one window per launch
+  if (fl > pl->n_jobs) fl = pl->n_jobs > 0 ? pl->n_jobs : 1;
+  pl->jobs_in_flight = fl;
+  pl->work_bytes = align_up((size_t)fl * per_job, 256);
+  *out = pl;
+  return XCB_OK;
+}
+
+extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
+  if (!pl || !info) return XCB_ERR_ARG;
+  memset(info, 0, sizeof(*info));
+  info->n = pl->g.n;
+  info->fft_len = pl->g.L;
+  info->spectrum_elems = pl->g.M;
+  info->n_lags = pl->K;
+  info->n_signals = pl->n_signals;
+  info->n_jobs = pl->n_jobs;
+  info->jobs_in_flight = pl->jobs_in_flight;
+  info->workspace_bytes = pl->partial_bytes + pl->work_bytes;
+  info->nd = pl->g.nd;
+  for (int a = 0; a < kMaxDims; ++a) info->dims[a] = pl->g.dims[a];
+  info->dtype = pl->dtype;
+  return XCB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forward / correlate
+// ---------------------------------------------------------------------------
+template <class T>
+static int forward_t(const xcb_plan* pl, const void* x, int64_t x_stride, void* spec, double* sumsq, void* ws,
+                     cudaStream_t st) {
+  DevTables<T> tb = dev_tables<T>(pl);
+  const PlanGeom& g = pl->g;
+  double* partial = static_cast<double*>(ws);
+  // launches are split so that a grid never exceeds 2^31-1 CTAs
+  for (int a = 0; a < g.nd; ++a) {
+    PassParams<T> p = make_forward_pass<T>(g, tb, a, static_cast<const T*>(x), x_stride, static_cast<cx<T>*>(spec),
+                                           g.M, (int)pl->n_signals, a == 0 ? partial : nullptr);
+    int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
+    if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
+    int e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+    if (e) return cuda_fail((cudaError_t)e, "forward pass launch");
+  }
+  xcb_sumsq_finish<<<(unsigned)pl->n_signals, 256, 0, st>>>(partial, pl->tiles0, sumsq);
+  XCB_CUDA(cudaGetLastError());
+  return XCB_OK;
+}
+
+extern "C" int xcb_forward(const xcb_plan* pl, const void* x, int64_t x_stride, void* spec, double* sumsq,
+                           void* workspace, void* stream) {
+  if (!pl || !x || !spec || !sumsq || !workspace || x_stride < pl->g.n) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return pl->dtype == XCB_F32 ? forward_t<float>(pl, x, x_stride, spec, sumsq, workspace, st)
+                              : forward_t<double>(pl, x, x_stride, spec, sumsq, workspace, st);
+}
+
+template <class T>
+static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq, void* ccf, void* ws,
+                       cudaStream_t st) {
+  DevTables<T> tb = dev_tables<T>(pl);
+  const PlanGeom& g = pl->g;
+  cx<T>* work = reinterpret_cast<cx<T>*>(static_cast<unsigned char*>(ws) + pl->partial_bytes);
+  CorrFlags f;
+  f.i0 = pl->i0;
+  f.i1 = pl->i1;
+  f.normalize = pl->desc.normalize;
+  f.unbiased = pl->desc.unbiased;
+  f.accumulate = pl->desc.stack;
+  for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
+    int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
+    for (int a = g.nd - 1; a >= 0; --a) {
+      PassParams<T> p = make_inverse_pass<T>(g, tb, a, static_cast<const cx<T>*>(spec), sumsq, pl->d_jobs + j0, nj,
+                                             work, static_cast<T*>(ccf), f);
+      int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
+      if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
+      int e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+      if (e) return cuda_fail((cudaError_t)e, "inverse pass launch");
+    }
+  }
+  return XCB_OK;
+}
+
+extern "C" int xcb_correlate(const xcb_plan* pl, const void* spec, const double* sumsq, void* ccf, void* workspace,
+                             void* stream) {
+  if (!pl || !spec || !sumsq || !ccf || !workspace) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return pl->dtype == XCB_F32 ? correlate_t<float>(pl, spec, sumsq, ccf, workspace, st)
+                              : correlate_t<double>(pl, spec, sumsq, ccf, workspace, st);
+}
+
+// ---------------------------------------------------------------------------
+// argmax
+// ---------------------------------------------------------------------------
+template <class T>
+static int argmax_t(const void* rows, int64_t n_rows, int64_t row_len, int64_t* index, void* value, cudaStream_t st) {
+  int chunks = (int)std::min<int64_t>(1024, (row_len + 16383) / 16384);
+  if (chunks < 1) chunks = 1;
+  T* pval = nullptr;
+  int64_t* pidx = nullptr;
+  XCB_CUDA(cudaMallocAsync(&pval, sizeof(T) * n_rows * chunks, st));
+  XCB_CUDA(cudaMallocAsync(&pidx, sizeof(int64_t) * n_rows * chunks, st));
+  for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+    int64_t nr = std::min<int64_t>(65535, n_rows - r0);
+    dim3 grid((unsigned)chunks, (unsigned)nr);
+    xcb_argmax_partial<T><<<grid, 256, 0, st>>>(static_cast<const T*>(rows) + r0 * row_len, row_len, chunks,
+                                               pval + r0 * chunks, pidx + r0 * chunks);
+  }
+  XCB_CUDA(cudaGetLastError());
+  xcb_argmax_final_rows<T><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(pval, pidx, chunks, n_rows, index,
+                                                                          static_cast<T*>(value));
+  XCB_CUDA(cudaGetLastError());
+  XCB_CUDA(cudaFreeAsync(pval, st));
+  XCB_CUDA(cudaFreeAsync(pidx, st));
+  return XCB_OK;
+}
+
+extern "C" int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64_t row_len, int64_t* index,
+                          void* value, void* stream) {
+  if (!rows || !index || n_rows < 1 || row_len < 1) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == XCB_F32) return argmax_t<float>(rows, n_rows, row_len, index, value, st);
+  if (dtype == XCB_F64) return argmax_t<double>(rows, n_rows, row_len, index, value, st);
+  return XCB_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------
+// cc() with host buffers
+// ---------------------------------------------------------------------------
+extern "C" int xcb_cc_host(int32_t dtype, int64_t n, const void* x, const void* y, int32_t normalize,
+                           int32_t unbiased, int64_t i0, int64_t i1, void* out) {
+  if (!x || !y || !out || n < 1) return XCB_ERR_ARG;
+  if (dtype != XCB_F32 && dtype != XCB_F64) return XCB_ERR_ARG;
+  const size_t b = dtype == XCB_F32 ? 4 : 8;
+  int32_t pr[2] = {0, 1};
+  xcb_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n = n;
+  d.dtype = dtype;
+  d.n_receivers = 2;
+  d.n_windows = 1;
+  d.n_pairs = 1;
+  d.pairs = pr;
+  d.normalize = normalize;
+  d.unbiased = unbiased;
+  d.lag_index_min = i0;
+  d.lag_index_max = i1;
+  xcb_plan* pl = nullptr;
+  int rc = xcb_plan_create(&pl, &d);
+  if (rc) return rc;
+  xcb_plan_info info;
+  xcb_plan_get_info(pl, &info);
+  const int64_t stride = (n + 1) / 2 * 2;     // even stride keeps both signals vector-aligned
+  unsigned char* buf = nullptr;
+  const size_t x_bytes = align_up((size_t)2 * stride * b, 256);
+  const size_t spec_bytes = align_up((size_t)2 * info.spectrum_elems * 2 * b, 256);
+  const size_t ccf_bytes = align_up((size_t)info.n_lags * b, 256);
+  const size_t total = x_bytes + spec_bytes + 256 + ccf_bytes + info.workspace_bytes;
+  cudaError_t e = cudaMalloc(&buf, total);
+  if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "cudaMalloc(cc_host)"); }
+  unsigned char* dx = buf;
+  unsigned char* dspec = dx + x_bytes;
+  double* dss = reinterpret_cast<double*>(dspec + spec_bytes);
+  unsigned char* dccf = dspec + spec_bytes + 256;
+  unsigned char* dws = dccf + ccf_bytes;
+  rc = XCB_OK;
+  do {
+    if ((e = cudaMemcpy(dx, x, n * b, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((e = cudaMemcpy(dx + stride * b, y, n * b, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+    if ((rc = xcb_forward(pl, dx, stride, dspec, dss, dws, nullptr)) != XCB_OK) break;
+    if ((rc = xcb_correlate(pl, dspec, dss, dccf, dws, nullptr)) != XCB_OK) break;
+    if ((e = cudaMemcpy(out, dccf, (size_t)info.n_lags * b, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+  } while (0);
+  cudaFree(buf);
+  xcb_plan_destroy(pl);
+  if (rc) return rc;
+  if (e != cudaSuccess) return cuda_fail(e, "xcb_cc_host");
+  return XCB_OK;
+}
