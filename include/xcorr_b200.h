@@ -115,6 +115,14 @@ XCB_API int xcb_correlate(const xcb_plan* plan, const void* spec, const double* 
 XCB_API int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64_t row_len, int64_t* index,
                void* value, void* stream);
 
+/* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
+ * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
+ * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not
+ * thread-safe; read after synchronising the stream.  total_ms / launches hold
+ * 8 entries. */
+XCB_API int xcb_profile_enable(xcb_plan* plan, int32_t enable);
+XCB_API int xcb_profile_read(xcb_plan* plan, int32_t* n_kinds, double* total_ms, int64_t* launches);
+
 /* cc(x, y, normalize, pad=True, unbiased, dtype) with HOST buffers
  * (util/cc.py:22-79): copies in, runs the device path, copies the
  * [lag_index_min, lag_index_max) lags back, synchronises.  out has

@@ -44,7 +44,8 @@ def test_cc_matches_reference_golden_vectors(xb, golden):
         peak = np.max(np.abs(r))
         assert np.max(np.abs(got - r)) <= TOL[r.dtype] * peak, name
         if r.dtype == np.float64 and len(r) > 8:
-            assert np.argmax(got) == np.argmax(r), name
+            # (the delta case peaks at -1: compare the location of the extremum)
+            assert np.argmax(np.abs(got)) == np.argmax(np.abs(r)), name
         checked += 1
     assert checked >= 29
 

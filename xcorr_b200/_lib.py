@@ -68,6 +68,9 @@ SYMBOLS = {
     "xcb_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "xcb_correlate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "xcb_argmax": (ctypes.c_int, [_i32, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "xcb_profile_enable": (ctypes.c_int, [_vp, _i32]),
+    "xcb_profile_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(_i64)]),
     "xcb_cc_host": (ctypes.c_int, [_i32, _i64, _vp, _vp, _i32, _i32, _i64, _i64, _vp]),
 }
 

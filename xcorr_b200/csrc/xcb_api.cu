@@ -173,7 +173,23 @@ struct xcb_plan {
   void* d_inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
   Job* d_jobs = nullptr;
   const PassLauncher* launch[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+  // measurement aid (xcb_profile_*): events around every pass launch
+  struct Timed { cudaEvent_t a, b; int kind; };
+  mutable bool profiling = false;
+  mutable std::vector<Timed> timed;
 };
+
+namespace {
+struct LaunchTimer {
+  const xcb_plan* pl; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int kind;
+  LaunchTimer(const xcb_plan* p, int k, cudaStream_t s) : pl(p), st(s), kind(k) {
+    if (pl->profiling && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+  }
+  ~LaunchTimer() {
+    if (pl->profiling && a && b) { cudaEventRecord(b, st); pl->timed.push_back({a, b, kind}); }
+  }
+};
+}  // namespace
 
 template <class T> static int upload_tables(xcb_plan* pl) {
   HostTables<T> ht;
@@ -321,7 +337,11 @@ static int forward_t(const xcb_plan* pl, const void* x, int64_t x_stride, void* 
                                            g.M, (int)pl->n_signals, a == 0 ? partial : nullptr);
     int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
     if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
-    int e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+    int e;
+    {
+      LaunchTimer tm(pl, a, st);
+      e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+    }
     if (e) return cuda_fail((cudaError_t)e, "forward pass launch");
   }
   xcb_sumsq_finish<<<(unsigned)pl->n_signals, 256, 0, st>>>(partial, pl->tiles0, sumsq);
@@ -356,7 +376,11 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
                                              work, static_cast<T*>(ccf), f);
       int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
       if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
-      int e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+      int e;
+      {
+        LaunchTimer tm(pl, g.nd + a, st);
+        e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+      }
       if (e) return cuda_fail((cudaError_t)e, "inverse pass launch");
     }
   }
@@ -369,6 +393,34 @@ extern "C" int xcb_correlate(const xcb_plan* pl, const void* spec, const double*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return pl->dtype == XCB_F32 ? correlate_t<float>(pl, spec, sumsq, ccf, workspace, st)
                               : correlate_t<double>(pl, spec, sumsq, ccf, workspace, st);
+}
+
+// ---------------------------------------------------------------------------
+// per-kernel timing (measurement aid)
+// ---------------------------------------------------------------------------
+extern "C" int xcb_profile_enable(xcb_plan* pl, int32_t enable) {
+  if (!pl) return XCB_ERR_ARG;
+  pl->profiling = enable != 0;
+  return XCB_OK;
+}
+
+extern "C" int xcb_profile_read(xcb_plan* pl, int32_t* n_kinds, double* total_ms, int64_t* launches) {
+  if (!pl || !n_kinds || !total_ms || !launches) return XCB_ERR_ARG;
+  for (int k = 0; k < 8; ++k) { total_ms[k] = 0.0; launches[k] = 0; }
+  *n_kinds = 2 * pl->g.nd;
+  cudaError_t err = cudaSuccess;
+  for (auto& t : pl->timed) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(t.b);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t.a, t.b);
+    if (e == cudaSuccess && t.kind >= 0 && t.kind < 8) { total_ms[t.kind] += ms; launches[t.kind] += 1; }
+    if (e != cudaSuccess) err = e;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  pl->timed.clear();
+  if (err != cudaSuccess) return cuda_fail(err, "xcb_profile_read");
+  return XCB_OK;
 }
 
 // ---------------------------------------------------------------------------

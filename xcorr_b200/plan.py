@@ -159,6 +159,22 @@ class CorrelationPlan:
                                         idx.data_ptr(), val.data_ptr(), stream), "xcb_argmax")
         return idx.reshape(ccf.shape[:-1]), val.reshape(ccf.shape[:-1])
 
+    # -- measurement aid ------------------------------------------------------
+    def profile(self, enable=True):
+        """Bracket every pass kernel with CUDA events (see ``xcb_profile_enable``)."""
+        _lib.check(self._lib.xcb_profile_enable(self._plan, int(bool(enable))), "xcb_profile_enable")
+
+    def profile_read(self):
+        """``[(name, total_ms, launches)]`` per pass kind since the last read."""
+        nk = ctypes.c_int32()
+        ms = (ctypes.c_double * 8)()
+        cnt = (ctypes.c_int64 * 8)()
+        _lib.check(self._lib.xcb_profile_read(self._plan, ctypes.byref(nk), ms, cnt), "xcb_profile_read")
+        nd = len(self.dims)
+        names = [f"fwd_pass{a}_N{self.dims[a]}" for a in range(nd)] + \
+                [f"inv_pass{a}_N{self.dims[a]}" for a in range(nd)]
+        return [(names[k], float(ms[k]), int(cnt[k])) for k in range(nk.value)]
+
     def __call__(self, x, out=None):
         self.forward(x)
         return self.correlate(out)
