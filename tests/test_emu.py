@@ -24,7 +24,8 @@ def _check(x, pairs, dims, tol, **kw):
         assert np.max(np.abs(out[q] - ref)) <= tol * peak, (dims, q)
         if not kw.get("unbiased", False) and i0 <= np.argmax(np.abs(orc.cc(x[i].astype(np.float64), x[j].astype(np.float64), unbiased=False))) < i1:
             assert np.argmax(np.abs(out[q])) == np.argmax(np.abs(ref))
-    assert np.allclose(ss, np.sum(x.astype(np.float64) ** 2, axis=1), rtol=1e-13)
+    # float32 mode squares in float32 (exact promotion costs a conversion per sample)
+    assert np.allclose(ss, np.sum(x.astype(np.float64) ** 2, axis=1), rtol=1e-13 if x.dtype == np.float64 else 1e-6)
 
 
 @pytest.mark.parametrize("N", MENU)

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Sweep pass factorisations for one transform length on the GPU and print the
+per-kernel times (tuning aid; not a test)."""
+import itertools
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import xcorr_b200 as xb
+from bench import make_inputs
+
+MENU = [64, 80, 96, 100, 120, 128, 144, 150, 160, 180, 192, 200, 225, 240, 256, 300, 320, 400]
+n = int(os.environ.get("XCB_N", 21_600_000))
+R = int(os.environ.get("XCB_R", 16))
+P = int(os.environ.get("XCB_P", 24))
+dtype = torch.float64 if os.environ.get("XCB_DTYPE", "f32") == "f64" else torch.float32
+slack = float(os.environ.get("XCB_SLACK", 1.0))
+cands = set()
+for combo in itertools.combinations_with_replacement(MENU, 3):
+    m = combo[0] * combo[1] * combo[2]
+    if n <= m <= n * slack:
+        for perm in set(itertools.permutations(combo)):
+            cands.add(perm)
+if os.environ.get("XCB_DIMS"):
+    cands = {tuple(int(v) for v in d.split(",")) for d in os.environ["XCB_DIMS"].split(";")}
+dev = torch.device("cuda:0")
+x = make_inputs(torch, R, n, dev, dtype, seed=1)
+pairs = xb.all_pairs(R)[:P]
+rows = []
+for dims in sorted(cands):
+    try:
+        plan = xb.CorrelationPlan(n, R, pairs, dtype=dtype, index_min=n - 1, index_max=n - 1 + 3 * n // 8, dims=dims)
+    except Exception as e:
+        print(dims, "skip", e)
+        continue
+    for _ in range(2):
+        ccf = plan(x)
+    torch.cuda.synchronize()
+    plan.profile(True)
+    for _ in range(3):
+        ccf = plan(x)
+    torch.cuda.synchronize()
+    k = plan.profile_read()
+    fwd = sum(ms / c for name, ms, c in k if name.startswith("fwd"))
+    inv = sum(ms / c for name, ms, c in k if name.startswith("inv"))
+    idx, _ = plan.argmax(ccf)
+    ok = idx[0, 0].item() == 137
+    rows.append((fwd + inv * 120 / P, dims, fwd, inv, ok, [round(ms / c, 3) for _, ms, c in k]))
+    del plan, ccf
+    torch.cuda.empty_cache()
+rows.sort()
+for est, dims, fwd, inv, ok, ks in rows:
+    print(f"{dims}  est step {est:7.2f} ms  fwd {fwd:6.2f}  inv/{P} {inv:6.2f}  ok={ok}  {ks}")

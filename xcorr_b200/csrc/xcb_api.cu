@@ -1,5 +1,6 @@
 // C ABI of libxcorr_b200 (see include/xcorr_b200.h): plans, forward
 // transforms, pair correlation, argmax, and the host-buffer cc() entry.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -10,6 +11,7 @@
 #include "../../include/xcorr_b200.h"
 #include "xcb_launch.h"
 #include "xcb_plan.h"
+#include "xcb_tma.cuh"
 
 using namespace xcb;
 
@@ -38,6 +40,36 @@ const PassLauncher* find_launcher(int dtype, int N) {
   LaunchTable& t = launch_table(dtype);
   for (int i = 0; i < t.count; ++i) if (t.e[i].N == N) return &t.e[i];
   return nullptr;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is
+// not linked; the build container has no driver).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_col_tile_map(CUtensorMap* map, int dtype, const void* base, int64_t row_elems, int64_t rows,
+                        int64_t batches, int64_t row_pitch_bytes, int64_t batch_pitch_bytes, int box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  }
+  if (!fn) return -1;
+  const cuuint64_t esz = dtype == 0 ? 4 : 8;
+  cuuint64_t gdim[3] = {(cuuint64_t)row_elems, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t gstride[2] = {(cuuint64_t)row_pitch_bytes, (cuuint64_t)batch_pitch_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)(128 / esz), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
 }
 
 }  // namespace xcb

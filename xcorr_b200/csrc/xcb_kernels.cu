@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include "xcb_launch.h"
 #include "xcb_passes.h"
+#include "xcb_tma.cuh"
+#include <stdlib.h>
 
 #ifndef XCB_DT
 #error "XCB_DT must be 0 (float) or 1 (double)"
@@ -68,16 +70,87 @@ xcb_row_pass(const __grid_constant__ PassParams<T> p) {
   P::phase_store(p, ctx, smem);
 }
 
+static int resident_ctas(const void* kernel, int threads, int smem) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  return per_sm * (sms > 0 ? sms : 148);
+}
+
+// TMA path: the pass input viewed as [batch][rows][128-byte column tiles] with
+// 16-byte aligned pitches.  Real input (first forward pass) additionally needs
+// whole rows (n a multiple of the row length): the zero padding is then the
+// tensor map's out-of-bounds fill and costs no traffic.
+template <class T> struct TmaGeom { bool ok; int64_t row_elems, rows, row_pitch, batch_pitch; };
+
+template <class T> TmaGeom<T> tma_geom(const PassParams<T>& p) {
+  TmaGeom<T> g;
+  g.ok = false;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("XCB_TMA"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled) return g;
+  if (reinterpret_cast<uintptr_t>(p.in) % 16 != 0) return g;
+  g.row_elems = 2 * p.inner;
+  g.row_pitch = g.row_elems * (int64_t)sizeof(T);
+  if (g.row_pitch % 16 != 0) return g;
+  if (p.load_mode == CL_REAL) {
+    if (p.n_real % g.row_elems != 0) return g;
+    g.rows = p.n_real / g.row_elems;
+    g.batch_pitch = p.in_stride * (int64_t)sizeof(T);
+  } else {
+    g.rows = p.M / p.inner;
+    g.batch_pitch = p.in_stride * (int64_t)sizeof(cx<T>);
+  }
+  if (g.batch_pitch % 16 != 0 || g.rows < 1) return g;
+  g.ok = true;
+  return g;
+}
+
 template <class T, int R1, int R2> int launch_col(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
   const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+  const TmaGeom<T> tg = tma_geom(p);
+  if (tg.ok) {
+    using K = ColTma<T, R1, R2>;
+    CUtensorMap map;
+    int rc = encode_col_tile_map(&map, sizeof(T) == 4 ? 0 : 1, p.in, tg.row_elems, tg.rows, p.n_batch, tg.row_pitch,
+                                 tg.batch_pitch, K::BOX_ROWS);
+    if (rc == 0) {
+      static int resident = 0;   // persistent grid: as many CTAs as stay resident
+      if (!resident) resident = resident_ctas((const void*)xcb_col_pass_tma<T, R1, R2>, K::THREADS, K::SMEM);
+      int64_t grid = nblocks < resident ? nblocks : resident;
+      xcb_col_pass_tma<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, p);
+      return (int)cudaGetLastError();
+    }
+  }
   xcb_col_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::COL_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
 
+template <class T> bool bulk_eligible(const PassParams<T>& p) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("XCB_BULK"); enabled = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower than the plain kernel
+  if (!enabled) return false;
+  if (p.store_mode == RS_EPI) return false;
+  if (p.load_mode == RL_PROLOGUE) return reinterpret_cast<uintptr_t>(p.spec) % 16 == 0;
+  if (p.load_mode == RL_CPLX)
+    return reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && (p.in_stride * (int64_t)sizeof(cx<T>)) % 16 == 0;
+  return false;
+}
+
 template <class T, int R1, int R2> int launch_row(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
+  using K = RowBulk<T, R1, R2>;
   const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+  if (K::kRowsAligned && bulk_eligible(p)) {
+    static int resident = 0;
+    if (!resident) resident = resident_ctas((const void*)xcb_row_pass_bulk<T, R1, R2>, K::THREADS, K::SMEM);
+    int64_t grid = nblocks < resident ? nblocks : resident;
+    xcb_row_pass_bulk<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(p);
+    return (int)cudaGetLastError();
+  }
   xcb_row_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
@@ -87,6 +160,12 @@ template <class T, int R1, int R2> int prepare() {
   cudaError_t e = cudaFuncSetAttribute(xcb_col_pass<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::COL_SMEM);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_row_pass<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROW_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           ColTma<T, R1, R2>::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(xcb_row_pass_bulk<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           RowBulk<T, R1, R2>::SMEM);
   return (int)e;
 }
 

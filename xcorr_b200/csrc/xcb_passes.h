@@ -86,6 +86,9 @@ template <class T> struct PassParams {
   T escale;                  // 1/M
   int32_t unbiased;          // multiply by n/(n-|k|)
   int32_t accumulate;        // ccf += instead of ccf =
+  // last inverse column pass: output rows k (element m = k*inner + col) that
+  // can hold a kept lag: [keep_lo[0], keep_hi[0]) U [keep_lo[1], keep_hi[1])
+  int32_t keep_lo[2], keep_hi[2];
 };
 
 template <class T, int R1_, int R2_> struct Cfg {
@@ -137,28 +140,56 @@ template <class T> XCB_HD cx<T> load_real_packed(const PassParams<T>& p, const T
   } else if (q < p.n_real) {
     r.x = x[q];
   }
-  ss += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+  ss += (double)(r.x * r.x + r.y * r.y);
   return r;
 }
 
-// final packed element m = (r[2m], r[2m+1]) -> cropped, scaled lag samples
-template <class T> XCB_HD void epilogue_store(const PassParams<T>& p, T* outp, int64_t m, T re, T im) {
+// final packed element m = (r[2m], r[2m+1]) -> cropped, scaled lag samples.
+// All indices fit 32 bits (L = 2M < 2^32).
+template <class T> XCB_HD void epilogue_store(const PassParams<T>& p, T* outp, uint32_t m, T re, T im) {
+  const uint32_t n = (uint32_t)p.n, L = (uint32_t)p.L;
+  const uint32_t i0 = (uint32_t)p.i0, K = (uint32_t)(p.i1 - p.i0);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    int64_t l = 2 * m + h;
-    int64_t i;
-    if (l < p.n) i = l + p.n - 1;
-    else if (l > p.L - p.n) i = l - p.L + p.n - 1;
+    uint32_t l = 2u * m + (uint32_t)h;
+    uint32_t i;
+    if (l < n) i = l + (n - 1u);
+    else if (l > L - n) i = l - (L - n + 1u);
     else continue;
-    if (i < p.i0 || i >= p.i1) continue;
+    uint32_t o = i - i0;            // wraps to a huge value when i < i0
+    if (o >= K) continue;
     T val = (h ? im : re) * p.escale;
     if (p.unbiased) {
-      int64_t k = i - (p.n - 1);
-      if (k < 0) k = -k;
-      val *= T((double)p.n / (double)(p.n - k));
+      uint32_t k = i >= n - 1u ? i - (n - 1u) : (n - 1u) - i;
+      val *= T((double)n / (double)(n - k));
     }
-    T* dst = outp + (i - p.i0);
+    T* dst = outp + o;
     *dst = p.accumulate ? (*dst + val) : val;
+  }
+}
+
+// v[r] <- (conj?)(v[r]) * W_M^(e0 + r*de), r = 0..R-1, with the twiddle advanced
+// by a running product instead of R table lookups (2 lookups per thread).
+template <int R, bool CONJ_IN, class T>
+XCB_HD void twiddle_chain(const PassParams<T>& p, uint32_t e0, uint32_t de, cx<T>* v) {
+  cx<T> w = tw_big(p, e0);
+  const cx<T> step = tw_big(p, de);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cx<T> x = v[r];
+    if (CONJ_IN) x.y = -x.y;
+    v[r] = cmul(x, w);
+    if (r + 1 < R) w = cmul(w, step);
+  }
+}
+
+// v[r] <- v[r] * w^r, r = 1..R-1 (stage-2 twiddles W_N^(r*j), w = W_N^j)
+template <int R, class T> XCB_HD void twiddle_powers(cx<T> w, cx<T>* v) {
+  cx<T> wr = w;
+#pragma unroll
+  for (int r = 1; r < R; ++r) {
+    v[r] = cmul(v[r], wr);
+    if (r + 1 < R) wr = cmul(wr, w);
   }
 }
 
@@ -234,11 +265,7 @@ template <class T, int R1, int R2> struct ColPass {
         for (int r = 0; r < R1; ++r) v[r] = src[(int64_t)(t.j + r * R2) * p.inner];
         if (p.load_mode == CL_CPLX_INV) {
           uint32_t col = (uint32_t)(t.col0 + t.c) * p.tw_scale;
-#pragma unroll
-          for (int r = 0; r < R1; ++r) {
-            cx<T> w = tw_big(p, col * (uint32_t)(t.j + r * R2));
-            v[r] = cmul(cconj(v[r]), w);
-          }
+          twiddle_chain<R1, true>(p, col * (uint32_t)t.j, col * (uint32_t)R2, v);
         }
       }
       fft_reg<R1>(v);
@@ -257,27 +284,26 @@ template <class T, int R1, int R2> struct ColPass {
       cx<T>* v = ctx.v;
 #pragma unroll
       for (int r = 0; r < R2; ++r) v[r] = smem[(t.j + r * R1) * C + t.c];
-#pragma unroll
-      for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ld_ro(p.tw_inner + r * t.j));
+      twiddle_powers<R2>(ld_ro(p.tw_inner + t.j), v);
       fft_reg<R2>(v);
       if (p.store_mode == CS_TW) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + t.batch * p.out_stride + t.base + t.c;
         uint32_t col = (uint32_t)(t.col0 + t.c) * p.tw_scale;
+        twiddle_chain<R2, false>(p, col * (uint32_t)t.j, col * (uint32_t)R1, v);
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-          int k = t.j + r * R1;
-          dst[(int64_t)k * p.inner] = cmul(v[r], tw_big(p, col * (uint32_t)k));
-        }
+        for (int r = 0; r < R2; ++r) dst[(int64_t)(t.j + r * R1) * p.inner] = v[r];
       } else if (p.store_mode == CS_CONJ) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + t.batch * p.out_stride + t.base + t.c;
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[(int64_t)(t.j + r * R1) * p.inner] = cconj(v[r]);
       } else {
         T* outp = p.ccf + p.jobs[t.batch].out_off;
+        const uint32_t m0 = (uint32_t)(t.base + t.c), inner = (uint32_t)p.inner;
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
-          int64_t m = t.base + (int64_t)(t.j + r * R1) * p.inner + t.c;
-          epilogue_store(p, outp, m, v[r].x, -v[r].y);
+          const int k = t.j + r * R1;
+          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+            epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
         }
       }
     }
@@ -318,12 +344,8 @@ template <class T, int R1, int R2> struct RowPass {
     return k;
   }
 
-  // phase 0: column -> row bookkeeping
-  static XCB_HD void phase_info(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
-    if (ctx.tid >= C) return;
-    RowInfo<T>* info = info_ptr(smem_raw);
-    int c = ctx.tid;
-    int64_t tile = ctx.bid % p.tiles_per_batch;
+  // column c of tile `tile` -> global row (pair product: rows ra / rb of pair slot c/2)
+  static XCB_HD RowInfo<T> row_info(const PassParams<T>& p, int64_t tile, int c) {
     RowInfo<T> ri;
     ri.row = -1; ri.store = 0; ri.pad = 0; ri.wrow.x = T(1); ri.wrow.y = T(0);
     if (p.load_mode == RL_PROLOGUE) {
@@ -346,47 +368,86 @@ template <class T, int R1, int R2> struct RowPass {
       int64_t row = tile * C + c;
       if (row < p.rows) { ri.row = row; ri.store = 1; }
     }
-    info[c] = ri;
+    return ri;
   }
+
+  // phase 0: column -> row bookkeeping
+  static XCB_HD void phase_info(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    if (ctx.tid >= C) return;
+    info_ptr(smem_raw)[ctx.tid] = row_info(p, ctx.bid % p.tiles_per_batch, ctx.tid);
+  }
+
+  // pair product of one element pair (k, M-k): A, B at (row ra, e); Am, Bm at
+  // (row rb, em).  Returns conj(V[k]) and conj(V[M-k]) scaled (the inverse runs
+  // as conj . FFT . conj).
+  static XCB_HD void pair_product(const cx<T>& A, const cx<T>& Am, const cx<T>& B, const cx<T>& Bm,
+                                  const cx<T>& wrow, const cx<T>& we, T scale, cx<T>& va, cx<T>& vb) {
+    const cx<T> Ap = cconj(Am), Bp = cconj(Bm);
+    const cx<T> Si = cadd(A, Ap), Di = csub(A, Ap);
+    const cx<T> Sj = cadd(B, Bp), Dj = csub(B, Bp);
+    const cx<T> P1 = cmulc(Si, Sj), P2 = cmulc(Di, Dj), P3 = cmulc(Di, Sj), P4 = cmulc(Si, Dj);
+    const cx<T> uw = cconj(cmul(wrow, we));        // conj(W_M^k), k = klow(row) + (M/N) e
+    const cx<T> uP4 = cmul(uw, P4);
+    const cx<T> s12 = cadd(P1, P2);
+    const cx<T> V = csub(cadd(s12, P3), uP4);      // V[k]
+    const cx<T> Vm = cadd(csub(s12, P3), uP4);     // conj(V[M-k])
+    va.x = V.x * scale;  va.y = -V.y * scale;
+    vb.x = Vm.x * scale; vb.y = Vm.y * scale;
+  }
+
+  // Thread <-> data mapping of the cooperative phases: every column c of the
+  // tile (= one global row) is owned by TJ consecutive threads which stride over
+  // its N elements (N / TJ = RMIN iterations, exact).  Row bookkeeping is read
+  // once per thread; global accesses of a warp are contiguous runs of TJ
+  // elements; shared accesses have pitch CP (conflict free).
+  static constexpr int TJ = G::TJ;
+  static constexpr int RMIN = N / TJ;             // = min(R1, R2)
+  static constexpr int UB = 8;
 
   // phase 1: global -> shared (transposed)
   static XCB_HD void phase_load(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
     cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
     const RowInfo<T>* info = info_ptr(smem_raw);
-    int64_t batch = ctx.bid / p.tiles_per_batch;
+    const int64_t batch = ctx.bid / p.tiles_per_batch;
     ctx.ss = 0.0;
     if (p.load_mode == RL_PROLOGUE) {
+      // pair slot lp is owned by 2*TJ threads
+      const int lp = ctx.tid / (2 * TJ), t = ctx.tid - lp * (2 * TJ);
       const Job jb = p.jobs[batch];
-      const cx<T>* zi = p.spec + jb.spec_i;
-      const cx<T>* zj = p.spec + jb.spec_j;
+      const RowInfo<T> ia = info[2 * lp];
+      const int64_t rb = info[2 * lp + 1].row;
       T scale = T(0.25);
       if (p.normalize) scale = T(0.25 / sqrt(p.sumsq[jb.sig_i] * p.sumsq[jb.sig_j]));
-      for (int idx = ctx.tid; idx < (C / 2) * N; idx += G::THREADS) {
-        int lp = idx / N, e = idx - lp * N;
-        const RowInfo<T> ia = info[2 * lp], ib = info[2 * lp + 1];
-        cx<T> va, vb;
-        va.x = va.y = vb.x = vb.y = T(0);
-        int em = N - 1 - e;
-        if (ia.row >= 0) {
-          if (ia.row == 0) em = (e == 0) ? 0 : N - e;
-          int64_t oa = ia.row * N + e, ob = ib.row * N + em;
-          cx<T> A = zi[oa], Ap = cconj(zi[ob]);
-          cx<T> B = zj[oa], Bp = cconj(zj[ob]);
-          cx<T> Si = cadd(A, Ap), Di = csub(A, Ap);
-          cx<T> Sj = cadd(B, Bp), Dj = csub(B, Bp);
-          cx<T> P1 = cmulc(Si, Sj), P2 = cmulc(Di, Dj), P3 = cmulc(Di, Sj), P4 = cmulc(Si, Dj);
-          // u = conj(W_M^k), k = klow(row) + (M/N) e
-          cx<T> u = cconj(cmul(ia.wrow, ld_ro(p.tw_inner + e)));
-          cx<T> uP4 = cmul(u, P4);
-          cx<T> s12 = cadd(P1, P2);
-          cx<T> V = csub(cadd(s12, P3), uP4);             // V[k]
-          cx<T> Vm = cadd(csub(s12, P3), uP4);            // conj(V[M-k])
-          // shared memory holds conj(V) (inverse via conj . FFT . conj)
-          va.x = V.x * scale;  va.y = -V.y * scale;
-          vb.x = Vm.x * scale; vb.y = Vm.y * scale;
+      const bool ok = ia.row >= 0;
+      const cx<T>* zi_a = p.spec + jb.spec_i + (ok ? ia.row : 0) * N;
+      const cx<T>* zj_a = p.spec + jb.spec_j + (ok ? ia.row : 0) * N;
+      const cx<T>* zi_b = p.spec + jb.spec_i + (ok ? rb : 0) * N;
+      const cx<T>* zj_b = p.spec + jb.spec_j + (ok ? rb : 0) * N;
+      const bool row0 = ia.row == 0;
+      constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
+      constexpr int PB = 2;
+      for (int it0 = 0; it0 < ITER; it0 += PB) {
+        cx<T> A[PB], Am[PB], B[PB], Bm[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int e = t + (it0 + u) * 2 * TJ;
+          if (ok && e < N) {
+            const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+            A[u] = zi_a[e]; Am[u] = zi_b[em]; B[u] = zj_a[e]; Bm[u] = zj_b[em];
+          }
         }
-        smem[e * CP + 2 * lp] = va;
-        smem[em * CP + 2 * lp + 1] = vb;
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+          const int e = t + (it0 + u) * 2 * TJ;
+          if (e < N) {
+            const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+            cx<T> va, vb;
+            va.x = va.y = vb.x = vb.y = T(0);
+            if (ok) pair_product(A[u], Am[u], B[u], Bm[u], ia.wrow, ld_ro(p.tw_inner + e), scale, va, vb);
+            smem[e * CP + 2 * lp] = va;
+            smem[em * CP + 2 * lp + 1] = vb;
+          }
+        }
       }
     } else if (p.load_mode == RL_REAL) {
       const T* x = reinterpret_cast<const T*>(p.in) + batch * p.in_stride;
@@ -399,13 +460,20 @@ template <class T, int R1, int R2> struct RowPass {
       }
       if (p.sumsq_partial) red_ptr(smem_raw)[ctx.tid] = ctx.ss;
     } else {
-      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + batch * p.in_stride;
-      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
-        int c = idx / N, e = idx - c * N;
-        cx<T> v; v.x = v.y = T(0);
-        int64_t row = info[c].row;
-        if (row >= 0) v = src[row * N + e];
-        smem[e * CP + c] = v;
+      const int c = ctx.tid / TJ, t = ctx.tid - c * TJ;
+      const int64_t row = info[c].row;
+      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + batch * p.in_stride + (row >= 0 ? row : 0) * N + t;
+      cx<T>* dst = smem + t * CP + c;
+      for (int it0 = 0; it0 < RMIN; it0 += UB) {
+        cx<T> buf[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+          buf[u].x = buf[u].y = T(0);
+          if (it0 + u < RMIN && row >= 0) buf[u] = src[(it0 + u) * TJ];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u)
+          if (it0 + u < RMIN) dst[(it0 + u) * TJ * CP] = buf[u];
       }
     }
   }
@@ -436,8 +504,7 @@ template <class T, int R1, int R2> struct RowPass {
       cx<T>* v = ctx.v;
 #pragma unroll
       for (int r = 0; r < R2; ++r) v[r] = smem[(j + r * R1) * CP + c];
-#pragma unroll
-      for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ld_ro(p.tw_inner + r * j));
+      twiddle_powers<R2>(ld_ro(p.tw_inner + j), v);
       fft_reg<R2>(v);
 #pragma unroll
       for (int r = 0; r < R2; ++r) smem[(j + r * R1) * CP + c] = v[r];
@@ -445,8 +512,10 @@ template <class T, int R1, int R2> struct RowPass {
   }
 
   static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
+    phase_store(p, ctx, smem_raw, info_ptr(smem_raw));
+  }
+  static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw, const RowInfo<T>* info) {
     const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
-    const RowInfo<T>* info = info_ptr(smem_raw);
     int64_t batch = ctx.bid / p.tiles_per_batch;
     if (p.store_mode == RS_EPI) {
       T* outp = p.ccf + p.jobs[batch].out_off;
@@ -455,18 +524,21 @@ template <class T, int R1, int R2> struct RowPass {
         const RowInfo<T> ri = info[c];
         if (ri.row < 0 || !ri.store) continue;
         cx<T> v = smem[e * CP + c];
-        epilogue_store(p, outp, ri.row * N + e, v.x, -v.y);
+        epilogue_store(p, outp, (uint32_t)(ri.row * N + e), v.x, -v.y);
       }
     } else {
-      cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride;
-      const bool cj = p.store_mode == RS_CONJ;
-      for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
-        int c = idx / N, e = idx - c * N;
-        const RowInfo<T> ri = info[c];
-        if (ri.row < 0 || !ri.store) continue;
-        cx<T> v = smem[e * CP + c];
-        if (cj) v.y = -v.y;
-        dst[ri.row * N + e] = v;
+      const int c = ctx.tid / TJ, t = ctx.tid - c * TJ;
+      const RowInfo<T> ri = info[c];
+      if (ri.row >= 0 && ri.store) {
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + ri.row * N + t;
+        const cx<T>* src = smem + t * CP + c;
+        const T sgn = p.store_mode == RS_CONJ ? T(-1) : T(1);
+#pragma unroll
+        for (int it = 0; it < RMIN; ++it) {
+          cx<T> v = src[it * TJ * CP];
+          v.y *= sgn;
+          dst[it * TJ] = v;
+        }
       }
     }
     if (p.sumsq_partial && p.load_mode == RL_REAL)

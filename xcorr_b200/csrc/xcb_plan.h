@@ -56,9 +56,17 @@ inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
     for (int i = 0; i < p; ++i) idx[i] = 0;
     while (true) {
       double m = 1;
-      for (int i = 0; i < p; ++i) m *= kMenu[idx[i]].N;
+      int mx = 0;
+      bool good_last = false;     // a length <= 256 and multiple of 16 can be the contiguous (row) axis
+      for (int i = 0; i < p; ++i) {
+        const int N = kMenu[idx[i]].N;
+        m *= N;
+        if (N > mx) mx = N;
+        if (N <= 256 && N % 16 == 0) good_last = true;
+      }
       if (m >= (double)n_min && m < 2147483648.0) {
-        double cost = m * (p + 0.5);
+        // primary: HBM traffic; ties: row axis that fits two CTAs per SM, then balanced lengths
+        double cost = m * (p + 0.5) * (1.0 + (good_last || p == 1 ? 0.0 : 1e-3) + 1e-6 * mx);
         if (cost < best) { best = cost; bn = p; for (int i = 0; i < p; ++i) bd[i] = kMenu[idx[i]].N; }
       }
       int k = p - 1;
@@ -69,12 +77,19 @@ inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
     }
   }
   if (bn == 0) return false;
-  // Axis order: the size with the most factors of two goes last (its length is
-  // the inner stride of the pass before it -> 128-byte aligned column tiles);
-  // the rest in decreasing order.
+  // Axis order: last = the length <= 256 with the most factors of two (row
+  // pass: staging for two CTAs per SM; its length is also the inner stride of
+  // the pass before it -> 128-byte aligned column tiles); else the most
+  // factors of two; the rest in decreasing order.
   std::sort(bd, bd + bn, [](int a, int b) { return a > b; });
-  int last = 0;
-  for (int i = 1; i < bn; ++i) if (pow2_exponent(bd[i]) > pow2_exponent(bd[last])) last = i;
+  int last = -1;
+  for (int i = 0; i < bn; ++i)
+    if (bd[i] <= 256 && (last < 0 || pow2_exponent(bd[i]) > pow2_exponent(bd[last]))) last = i;
+  if (last < 0 || pow2_exponent(bd[last]) < 4) {
+    int alt = 0;
+    for (int i = 1; i < bn; ++i) if (pow2_exponent(bd[i]) > pow2_exponent(bd[alt])) alt = i;
+    if (last < 0 || pow2_exponent(bd[alt]) >= 4) last = alt;
+  }
   int lv = bd[last];
   for (int i = last; i + 1 < bn; ++i) bd[i] = bd[i + 1];
   bd[bn - 1] = lv;
@@ -239,6 +254,22 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   for (int r = 0; r < kMaxDims; ++r) { p.region_lo[r] = g.region_lo[r]; p.region_hi[r] = g.region_hi[r]; }
   for (int r = 0; r <= kMaxDims; ++r) p.pair_start[r] = g.pair_start[r];
   p.n_pairs_rows = g.n_pairs_rows;
+  // rows k of the last column pass (element m = k*S[1] + col) that can hold a kept lag
+  p.keep_lo[0] = p.keep_lo[1] = 0;
+  p.keep_hi[0] = p.keep_hi[1] = 0;
+  if (g.nd > 1) {
+    const int64_t n = g.n, L = g.L, inner0 = g.S[1];
+    // lags >= 0: i = l + n-1, l in [0, n)        -> l in [max(0, i0-(n-1)), min(n, i1-(n-1)))
+    int64_t la = std::max<int64_t>(0, f.i0 - (n - 1)), lb = std::min<int64_t>(n, f.i1 - (n - 1));
+    if (lb > la) { p.keep_lo[0] = (int32_t)((la / 2) / inner0); p.keep_hi[0] = (int32_t)(((lb - 1) / 2) / inner0 + 1); }
+    // lags < 0: i = l - L + n-1, i in [0, n-1)   -> l = i + L - (n-1)
+    int64_t ia = std::max<int64_t>(0, f.i0), ib = std::min<int64_t>(n - 1, f.i1);
+    if (ib > ia) {
+      int64_t l0 = ia + L - (n - 1), l1 = ib - 1 + L - (n - 1);
+      p.keep_lo[1] = (int32_t)((l0 / 2) / inner0);
+      p.keep_hi[1] = (int32_t)((l1 / 2) / inner0 + 1);
+    }
+  }
   if (a == g.nd - 1) {
     p.load_mode = RL_PROLOGUE;
     p.store_mode = (g.nd == 1) ? RS_EPI : RS_CONJ;

@@ -1,0 +1,346 @@
+// Persistent column-pass kernel with TMA-staged tiles (sm_100a).
+//
+// One CTA stays resident per SM slot and walks tiles blockIdx.x, +gridDim.x, ...
+// Each tile ([N rows] x [128 B] strided in HBM) is fetched by ONE elected thread
+// with cp.async.bulk.tensor.2d into a ring of shared-memory slots, completion
+// signalled on an mbarrier (complete_tx::bytes).  While the CTA computes tile i
+// the copies of tiles i+1.. are in flight, so HBM latency is hidden without
+// spending registers or LSU issue slots on loads, and out-of-range columns are
+// zero-filled by the TMA unit.  The two radix stages run in place in the slot:
+//
+//   wait(full[s]) -> stage-1 read -> bar -> radix-R1, write -> bar
+//   -> stage-2 read -> fence.proxy.async + bar -> re-arm slot s (TMA for tile
+//   i+NSLOT) -> radix-R2, twiddle, store to HBM straight from registers.
+//
+// Arithmetic (twiddle chains, butterflies, lag epilogue) is the same code as the
+// plain kernels in xcb_passes.h, which the CPU emulator tests cover.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "xcb_passes.h"
+
+namespace xcb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+template <class T, int R1, int R2> struct ColTma {
+  using G = Cfg<T, R1, R2>;
+  static constexpr int N = G::N, C = G::C, TJ = G::TJ, THREADS = G::THREADS;
+  static constexpr int SLOT_BYTES = N * C * 2 * (int)sizeof(T);
+  static constexpr int BOX_ROWS = N <= 256 ? N : N / 2;
+  static constexpr int NBOX = N / BOX_ROWS;
+  static constexpr int NSLOT = (3 * SLOT_BYTES + 64 + THREADS * 8) * 2 <= 220 * 1024 ? 3 : 2;
+  static constexpr int RED_OFF = NSLOT * SLOT_BYTES + 64;
+  static constexpr int SMEM = RED_OFF + THREADS * 8;
+  static_assert(N % BOX_ROWS == 0 && BOX_ROWS <= 256, "TMA box");
+};
+
+template <class T, int R1, int R2>
+__global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, 2)
+xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassParams<T> p) {
+  using K = ColTma<T, R1, R2>;
+  constexpr int N = K::N, C = K::C;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + K::NSLOT * K::SLOT_BYTES);
+
+  const int tid = threadIdx.x;
+  const int c = tid % C, j = tid / C;
+  const int64_t ntiles = (int64_t)p.n_batch * p.tiles_per_batch;
+  const int64_t stride_tiles = gridDim.x;
+  double* red = reinterpret_cast<double*>(smem_raw + K::RED_OFF);
+
+  auto issue = [&](int64_t tile, int s) {
+    const int64_t batch = tile / p.tiles_per_batch;
+    const int64_t rem = tile - batch * p.tiles_per_batch;
+    const int64_t o = rem / p.col_tiles;
+    const int64_t cb = rem - o * p.col_tiles;
+    const int32_t x0 = (int32_t)(cb * C * 2);                     // in units of T
+    const int32_t y0 = (int32_t)(o * N);                          // row within the signal
+    unsigned char* dst = smem_raw + s * K::SLOT_BYTES;
+    mbar_expect_tx(&full[s], (uint32_t)K::SLOT_BYTES);
+#pragma unroll
+    for (int b = 0; b < K::NBOX; ++b)
+      tma_load_3d(dst + b * (K::SLOT_BYTES / K::NBOX), &tmap, &full[s], x0, y0 + b * K::BOX_ROWS, (int32_t)batch);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < K::NSLOT; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < K::NSLOT; ++s) {
+      int64_t t0 = (int64_t)blockIdx.x + s * stride_tiles;
+      if (t0 < ntiles) issue(t0, s);
+    }
+  }
+
+  const cx<T> w_inner = ld_ro(p.tw_inner + (j < R1 ? j : 0));   // W_N^j, tile independent
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += stride_tiles, ++it) {
+    const int s = (int)(it % K::NSLOT);
+    const uint32_t parity = (it / K::NSLOT) & 1u;
+    cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw + s * K::SLOT_BYTES);
+
+    const int64_t batch = tile / p.tiles_per_batch;
+    const int64_t rem = tile - batch * p.tiles_per_batch;
+    const int64_t o = rem / p.col_tiles;
+    const int64_t col0 = (rem - o * p.col_tiles) * C;
+    const int64_t base = o * (int64_t)N * p.inner + col0;
+    const bool col_ok = (col0 + c) < p.inner;
+    const uint32_t colscale = (uint32_t)(col0 + c) * p.tw_scale;
+
+    cx<T> v[K::TJ];
+    mbar_wait(&full[s], parity);
+    if (j < R2) {
+#pragma unroll
+      for (int r = 0; r < R1; ++r) v[r] = sm[(j + r * R2) * C + c];
+    }
+    if (p.sumsq_partial) {          // real-input first pass: sum of squares of this tile (rows past n are zero)
+      T ssq = T(0);
+      if (j < R2) {
+#pragma unroll
+        for (int r = 0; r < R1; ++r) ssq += v[r].x * v[r].x + v[r].y * v[r].y;
+      }
+      red[tid] = (double)ssq;
+    }
+    __syncthreads();
+    if (p.sumsq_partial) block_sumsq<K::THREADS>(p.sumsq_partial + tile, red, tid);
+    if (j < R2) {
+      if (p.load_mode == CL_CPLX_INV) twiddle_chain<R1, true>(p, colscale * (uint32_t)j, colscale * (uint32_t)R2, v);
+      fft_reg<R1>(v);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) sm[(j * R1 + r) * C + c] = v[r];
+    }
+    __syncthreads();
+    if (j < R1) {
+#pragma unroll
+      for (int r = 0; r < R2; ++r) v[r] = sm[(j + r * R1) * C + c];
+    }
+    fence_proxy_async_smem();   // our generic-proxy accesses to this slot precede its next TMA fill
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t next = tile + K::NSLOT * stride_tiles;
+      if (next < ntiles) issue(next, s);
+    }
+    if (j < R1 && col_ok) {
+      twiddle_powers<R2>(w_inner, v);
+      fft_reg<R2>(v);
+      if (p.store_mode == CS_TW) {
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
+        twiddle_chain<R2, false>(p, colscale * (uint32_t)j, colscale * (uint32_t)R1, v);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) dst[(int64_t)(j + r * R1) * p.inner] = v[r];
+      } else if (p.store_mode == CS_CONJ) {
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) dst[(int64_t)(j + r * R1) * p.inner] = cconj(v[r]);
+      } else {
+        T* outp = p.ccf + p.jobs[batch].out_off;
+        const uint32_t m0 = (uint32_t)(base + c), inner = (uint32_t)p.inner;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const int k = j + r * R1;
+          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+            epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Persistent row pass with bulk-async staging
+// ---------------------------------------------------------------------------
+// A tile is C contiguous rows (forward last pass) or C/2 mirrored row pairs of
+// two spectra (pair product).  Warp 0 fetches the NEXT tile's rows with
+// cp.async.bulk (one instruction per row, completion on an mbarrier) into a
+// staging area while all warps transform the current tile in the padded
+// transposed buffer; staging -> buffer is a shared-memory pass (pair product
+// fused there), so no thread ever waits on an HBM load.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <class T, int R1, int R2> struct RowBulk {
+  using G = Cfg<T, R1, R2>;
+  static constexpr int N = G::N, C = G::C, CP = G::CP, THREADS = G::THREADS;
+  static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
+  static constexpr int FFT_BYTES = N * CP * 2 * (int)sizeof(T);
+  static constexpr int INFO_OFF = FFT_BYTES;                          // == RowPass::info_ptr offset
+  static constexpr int STAGE_OFF = (FFT_BYTES + 2 * C * 32 + 127) / 128 * 128;
+  static constexpr int STAGE_BYTES = 2 * C * ROW_BYTES;               // pair product: 4 x C/2 rows
+  static constexpr int BAR_OFF = STAGE_OFF + STAGE_BYTES;
+  static constexpr int SMEM = BAR_OFF + 64;
+  static constexpr bool kRowsAligned = (ROW_BYTES % 16) == 0;
+};
+
+template <class T, int R1, int R2>
+__global__ void __launch_bounds__(RowBulk<T, R1, R2>::THREADS, 2)
+xcb_row_pass_bulk(const __grid_constant__ PassParams<T> p) {
+  using K = RowBulk<T, R1, R2>;
+  using P = RowPass<T, R1, R2>;
+  constexpr int N = K::N, C = K::C, CP = K::CP, H = K::C / 2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cx<T>* fft = reinterpret_cast<cx<T>*>(smem_raw);
+  RowInfo<T>* info2 = reinterpret_cast<RowInfo<T>*>(smem_raw + K::INFO_OFF);    // [2][C]
+  cx<T>* stage = reinterpret_cast<cx<T>*>(smem_raw + K::STAGE_OFF);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + K::BAR_OFF);
+
+  const int tid = threadIdx.x;
+  const bool prologue = p.load_mode == RL_PROLOGUE;
+  const int64_t ntiles = (int64_t)p.n_batch * p.tiles_per_batch;
+  const int64_t stride_tiles = gridDim.x;
+
+  // warp 0: bookkeeping of `tile` into info2[slot], then the bulk copies
+  auto prefetch = [&](int64_t tile, int slot) {
+    const int64_t batch = tile / p.tiles_per_batch;
+    const int64_t tl = tile - batch * p.tiles_per_batch;
+    RowInfo<T>* inf = info2 + slot * C;
+    if (tid < C) inf[tid] = P::row_info(p, tl, tid);
+    __syncwarp();
+    if (prologue) {
+      const Job jb = p.jobs[batch];
+      const int kind = tid / H, lp = tid % H;           // 0: Zi(ra) 1: Zj(ra) 2: Zi(rb) 3: Zj(rb)
+      int64_t row = -1;
+      if (tid < 4 * H) row = inf[2 * lp + (kind >> 1)].row;
+      const bool valid = row >= 0;
+      const unsigned mask = __ballot_sync(0xffffffffu, valid);
+      if (tid == 0) mbar_expect_tx(full, (uint32_t)(__popc(mask) * K::ROW_BYTES));
+      __syncwarp();
+      if (valid) {
+        const cx<T>* src = p.spec + ((kind & 1) ? jb.spec_j : jb.spec_i) + row * N;
+        bulk_load(stage + (size_t)(kind * H + lp) * N, src, (uint32_t)K::ROW_BYTES, full);
+      }
+    } else if (tid == 0) {
+      int64_t nrows = p.rows - tl * C;
+      if (nrows > C) nrows = C;
+      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + batch * p.in_stride + tl * (int64_t)(C * N);
+      mbar_expect_tx(full, (uint32_t)(nrows * K::ROW_BYTES));
+      bulk_load(stage, src, (uint32_t)(nrows * K::ROW_BYTES), full);
+    }
+  };
+
+  if (tid == 0) { mbar_init(full, 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid < 32 && (int64_t)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
+
+  typename P::Ctx ctx;
+  ctx.tid = tid;
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += stride_tiles, ++it) {
+    const int slot = (int)(it & 1u);
+    const RowInfo<T>* info = info2 + slot * C;
+    ctx.bid = tile;
+    const int64_t batch = tile / p.tiles_per_batch;
+    __syncthreads();                       // info[slot] visible; previous tile's store phase has left `fft`
+    mbar_wait(full, it & 1u);
+    if (prologue) {
+      const Job jb = p.jobs[batch];
+      T scale = T(0.25);
+      if (p.normalize) scale = T(0.25 / sqrt(p.sumsq[jb.sig_i] * p.sumsq[jb.sig_j]));
+      constexpr int TJ = P::TJ;
+      const int lp = tid / (2 * TJ), t = tid - lp * (2 * TJ);    // pair slot owned by 2*TJ threads
+      const RowInfo<T> ia = info[2 * lp];
+      const bool ok = ia.row >= 0, row0 = ia.row == 0;
+      const cx<T>* sA = stage + (0 * H + lp) * N;
+      const cx<T>* sB = stage + (1 * H + lp) * N;
+      const cx<T>* sAm = stage + (2 * H + lp) * N;
+      const cx<T>* sBm = stage + (3 * H + lp) * N;
+      constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
+#pragma unroll
+      for (int i = 0; i < ITER; ++i) {
+        const int e = t + i * 2 * TJ;
+        if (e < N) {
+          const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+          cx<T> va, vb;
+          va.x = va.y = vb.x = vb.y = T(0);
+          if (ok) P::pair_product(sA[e], sAm[em], sB[e], sBm[em], ia.wrow, ld_ro(p.tw_inner + e), scale, va, vb);
+          fft[e * CP + 2 * lp] = va;
+          fft[em * CP + 2 * lp + 1] = vb;
+        }
+      }
+    } else {
+      constexpr int TJ = P::TJ;
+      const int c = tid / TJ, t = tid - c * TJ;
+      const bool ok = info[c].row >= 0;
+      const cx<T>* src = stage + c * N + t;
+      cx<T>* dst = fft + t * CP + c;
+#pragma unroll
+      for (int i = 0; i < P::RMIN; ++i) {
+        cx<T> v; v.x = v.y = T(0);
+        if (ok) v = src[i * TJ];
+        dst[i * TJ * CP] = v;
+      }
+    }
+    fence_proxy_async_smem();              // our reads of `stage` precede its next async fill
+    __syncthreads();
+    if (tid < 32) {
+      const int64_t next = tile + stride_tiles;
+      if (next < ntiles) prefetch(next, slot ^ 1);
+    }
+    P::phase_s1_read(p, ctx, smem_raw);
+    __syncthreads();
+    P::phase_s1_write(p, ctx, smem_raw);
+    __syncthreads();
+    P::phase_s2(p, ctx, smem_raw);
+    __syncthreads();
+    P::phase_store(p, ctx, smem_raw, info);
+  }
+}
+
+// Host: 3-D tensor map [batch][rows][row_elems] of T over the pass input, box =
+// [1][box_rows][128 bytes]; rows >= `rows` and columns >= row_elems read as
+// zero.  Implemented in xcb_api.cu (needs the driver entry point).
+int encode_col_tile_map(CUtensorMap* map, int dtype, const void* base, int64_t row_elems, int64_t rows,
+                        int64_t batches, int64_t row_pitch_bytes, int64_t batch_pitch_bytes, int box_rows);
+
+}  // namespace xcb
