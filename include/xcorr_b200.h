@@ -115,6 +115,51 @@ XCB_API int xcb_correlate(const xcb_plan* plan, const void* spec, const double* 
 XCB_API int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64_t row_len, int64_t* index,
                void* value, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Stream preprocessing: the array-valued obspy Trace operations named by the
+ * reference's op-lists (stream/process.py:29-94, applied at :280 through
+ * eval('waveforms.<op>(**params)')).  Buffers are device arrays
+ * dtype[n_signals][stride]; arithmetic is float64 whatever the storage dtype.
+ * ------------------------------------------------------------------------ */
+
+/* detrend + taper as one pointwise map  y[i] = w(i) * (x[i] - (c0 + c1*i)).
+ * Replaces Trace.detrend(type) and Trace.taper(...): the ramps are the first /
+ * last `wlen` values of the obspy window, computed on the host. */
+typedef struct xcb_pointwise {
+  int32_t detrend;           /* 0 none, 1 'demean'/'constant', 2 'linear', 3 'simple' */
+  int32_t taper_left;        /* ramp lengths in samples (0 = none) */
+  int32_t taper_right;
+  int32_t reserved;
+  const double* ramp_left;   /* device, taper_left values  */
+  const double* ramp_right;  /* device, taper_right values */
+} xcb_pointwise;
+
+/* Causal cascade of second-order sections == scipy.signal.sosfilt(sos, x) from
+ * zero state, i.e. Trace.filter(bandpass|highpass|lowpass|lowpass_cheby_2) and,
+ * with decimate > 1, Trace.decimate(factor) (low-pass + data[::factor]). */
+typedef struct xcb_sos {
+  int32_t n_sections;        /* 1..12 (several filters may be concatenated) */
+  int32_t decimate;          /* store every decimate-th output sample; >= 1 */
+  int32_t reverse;           /* 1: filter from the last sample backwards (second half of zerophase=True) */
+  int32_t chunk;             /* samples per scan chunk (e.g. 1024) */
+  double coef[12][5];        /* b0 b1 b2 a1 a2 per section (a0 = 1) */
+  const double* carry;       /* host, [2S][2S] row-major: state transition over `chunk` samples */
+  const double* carry_group; /* host, [2S][2S]: carry^64 */
+} xcb_sos;
+
+/* stats[s] = {sum x, sum i*x, x[0], x[n-1]} (device double[n_signals][4]) */
+XCB_API int xcb_stats_workspace_bytes(int64_t n, int32_t n_signals, size_t* bytes);
+XCB_API int xcb_stats(int32_t dtype, const void* x, int64_t n, int64_t stride, int32_t n_signals, double* stats,
+                      void* workspace, void* stream);
+XCB_API int xcb_pointwise_apply(int32_t dtype_in, const void* x, int64_t x_stride, int32_t dtype_out, void* y,
+                                int64_t y_stride, int64_t n, int32_t n_signals, const xcb_pointwise* pw,
+                                const double* stats, void* stream);
+/* y has ceil(n / decimate) samples per signal; `pre` (optional) is applied to x on the fly. */
+XCB_API int xcb_sosfilt_workspace_bytes(int64_t n, int32_t n_signals, const xcb_sos* f, size_t* bytes);
+XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32_t dtype_out, void* y,
+                        int64_t y_stride, int64_t n, int32_t n_signals, const xcb_sos* f, const xcb_pointwise* pre,
+                        const double* stats, void* workspace, void* stream);
+
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
  * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not

@@ -1,0 +1,172 @@
+"""scipy restatement of the obspy ``Trace`` operations the reference's op-lists
+name (TEST INFRASTRUCTURE; **parity unpinned**).
+
+The reference applies preprocessing by ``eval('waveforms.<op>(**params)')`` on
+obspy objects (``xcorr/stream/process.py:199-297``); the arithmetic lives in
+obspy (``obspy>=1.2``, ``setup.cfg:41``), which is neither installed here nor
+vendored under ``/root/reference``.  This module restates the published obspy
+1.2-1.4 algorithms on numpy/scipy, one function per
+operation, float64 throughout like obspy.  It is pinned only by analytic
+known-answer tests (``tests/test_preprocess_oracle.py``) and by the reference's
+call sites (``examples/core/process.py:61-155``); should an obspy install become
+available, regenerate fixtures from it.
+
+Not imported by the product package ``xcorr_b200``.
+"""
+import numpy as np
+from scipy import signal
+
+__all__ = ["detrend", "cosine_taper", "taper_window", "taper", "butter_sos", "filter_",
+           "cheby2_lowpass_sos", "decimate", "trim", "process"]
+
+
+def detrend(x, type="simple"):
+    """obspy ``Trace.detrend``: 'demean'/'constant' -> x - mean;
+    'linear' -> least-squares line (scipy.signal.detrend); 'simple' -> line
+    through the first and last sample."""
+    x = np.asarray(x, dtype=np.float64)
+    if type in ("demean", "constant"):
+        return signal.detrend(x, type="constant")
+    if type == "linear":
+        return signal.detrend(x, type="linear")
+    if type == "simple":
+        n = len(x)
+        return x - (x[0] + (x[-1] - x[0]) * np.arange(n) / float(n - 1))
+    raise ValueError(f"unsupported detrend type {type!r}")
+
+
+def cosine_taper(npts, p=0.1):
+    """obspy.signal.invsim.cosine_taper (no frequency arguments)."""
+    if p == 0.0 or p == 1.0:
+        frac = int(npts * p / 2.0)
+    else:
+        frac = int(npts * p / 2.0 + 0.5)
+    idx1, idx2, idx3, idx4 = 0, frac - 1, npts - frac, npts - 1
+    if idx1 == idx2:
+        idx2 += 1
+    if idx3 == idx4:
+        idx3 -= 1
+    w = np.zeros(npts)
+    w[idx1:idx2 + 1] = 0.5 * (1.0 - np.cos(np.pi * (np.arange(idx1, idx2 + 1) - idx1) / (idx2 - idx1)))
+    w[idx2 + 1:idx3] = 1.0
+    w[idx3:idx4 + 1] = 0.5 * (1.0 + np.cos(np.pi * (idx3 - np.arange(idx3, idx4 + 1)) / (idx4 - idx3)))
+    return w
+
+
+def taper_window(npts, sampling_rate, max_percentage=None, type="hann", max_length=None, side="both"):
+    """The multiplicative window obspy ``Trace.taper`` builds."""
+    max_half = []
+    if max_percentage is not None:
+        max_half.append(int(max_percentage * npts))
+    if max_length is not None:
+        max_half.append(int(max_length * sampling_rate))
+    max_half.append(int(npts / 2))
+    wlen = min(max_half)
+    M = 2 * wlen if 2 * wlen == npts else 2 * wlen + 1
+    if type == "cosine":
+        win = cosine_taper(M, 1.0)
+    else:
+        win = getattr(signal.windows, type)(M)
+    if side == "left":
+        return np.hstack((win[:wlen], np.ones(npts - wlen)))
+    if side == "right":
+        return np.hstack((np.ones(npts - wlen), win[len(win) - wlen:]))
+    return np.hstack((win[:wlen], np.ones(npts - 2 * wlen), win[len(win) - wlen:]))
+
+
+def taper(x, sampling_rate, max_percentage=None, type="hann", max_length=None, side="both"):
+    x = np.asarray(x, dtype=np.float64)
+    return x * taper_window(len(x), sampling_rate, max_percentage, type, max_length, side)
+
+
+def butter_sos(sampling_rate, type, freq=None, freqmin=None, freqmax=None, corners=4):
+    """Second-order sections of obspy.signal.filter.{bandpass,highpass,lowpass}."""
+    fe = 0.5 * sampling_rate
+    if type == "bandpass":
+        low, high = freqmin / fe, freqmax / fe
+        if high - 1.0 > -1e-6:          # obspy: falls back to a highpass
+            return butter_sos(sampling_rate, "highpass", freq=freqmin, corners=corners)
+        if low > 1:
+            raise ValueError("Selected low corner frequency is above Nyquist.")
+        z, p, k = signal.iirfilter(corners, [low, high], btype="band", ftype="butter", output="zpk")
+    elif type == "highpass":
+        f = freq / fe
+        if f > 1:
+            raise ValueError("Selected corner frequency is above Nyquist.")
+        z, p, k = signal.iirfilter(corners, f, btype="highpass", ftype="butter", output="zpk")
+    elif type == "lowpass":
+        f = min(freq / fe, 1.0)
+        z, p, k = signal.iirfilter(corners, f, btype="lowpass", ftype="butter", output="zpk")
+    else:
+        raise ValueError(f"unsupported filter type {type!r}")
+    return signal.zpk2sos(z, p, k)
+
+
+def filter_(x, sampling_rate, type, zerophase=False, **opts):
+    """obspy ``Trace.filter``: causal ``sosfilt`` from zero state (twice, time
+    reversed in between, for ``zerophase``)."""
+    x = np.asarray(x, dtype=np.float64)
+    if type == "lowpass_cheby_2":
+        sos = cheby2_lowpass_sos(sampling_rate, opts["freq"], opts.get("maxorder", 12))
+        return signal.sosfilt(sos, x)
+    sos = butter_sos(sampling_rate, type, **opts)
+    if zerophase:
+        firstpass = signal.sosfilt(sos, x)
+        return signal.sosfilt(sos, firstpass[::-1])[::-1]
+    return signal.sosfilt(sos, x)
+
+
+def cheby2_lowpass_sos(sampling_rate, freq, maxorder=12):
+    """obspy.signal.filter.lowpass_cheby_2 design (rp=1, rs=96)."""
+    nyquist = sampling_rate * 0.5
+    rp, rs, order = 1, 96, 1e99
+    ws = freq / nyquist
+    wp = ws
+    if ws > 1:
+        ws = 1.0
+    while True:
+        if order <= maxorder:
+            break
+        wp = wp * 0.99
+        order, wn = signal.cheb2ord(wp, ws, rp, rs, analog=0)
+    z, p, k = signal.cheby2(order, rs, wn, btype="low", analog=0, output="zpk")
+    return signal.zpk2sos(z, p, k)
+
+
+def decimate(x, sampling_rate, factor, no_filter=False):
+    """obspy ``Trace.decimate``: Chebyshev-II anti-alias low-pass at
+    ``0.5*fs/factor`` then ``data[::factor]``.  Returns (y, new_rate)."""
+    if factor > 16:
+        raise ArithmeticError("Automatic filter design is unstable for decimation factors above 16.")
+    x = np.asarray(x, dtype=np.float64)
+    if not no_filter:
+        x = signal.sosfilt(cheby2_lowpass_sos(sampling_rate, sampling_rate * 0.5 / float(factor)), x)
+    return x[::factor].copy(), sampling_rate / float(factor)
+
+
+def trim(x, start=0, length=None):
+    """Array form of the time-based trims (``stream/client.py:1017`` and
+    ``core/process.py:156-157``): samples ``[start, start+length)``."""
+    return x[start:] if length is None else x[start:start + length]
+
+
+def process(x, sampling_rate, operations):
+    """Apply an op-list ``[(name, params), ...]`` to one trace.  Returns
+    ``(y, sampling_rate)``."""
+    y = np.asarray(x, dtype=np.float64)
+    fs = float(sampling_rate)
+    for name, params in operations:
+        params = dict(params)
+        if name == "detrend":
+            y = detrend(y, params.get("type", "simple"))
+        elif name == "taper":
+            y = taper(y, fs, **params)
+        elif name == "filter":
+            y = filter_(y, fs, **params)
+        elif name == "decimate":
+            y, fs = decimate(y, fs, **params)
+        elif name == "trim":
+            y = trim(y, **params)
+        else:
+            raise NotImplementedError(f"operation {name!r} is outside the array-valued hot path")
+    return y, fs

@@ -1,0 +1,80 @@
+"""Known-answer tests pinning the (otherwise unpinned) obspy restatement."""
+import numpy as np
+from scipy import signal
+
+from oracle import preprocess_oracle as pre
+
+
+def test_detrend_known_answers():
+    i = np.arange(1000.0)
+    x = 3.0 + 0.25 * i
+    assert np.max(np.abs(pre.detrend(x, "linear"))) < 1e-9
+    assert np.max(np.abs(pre.detrend(x, "simple"))) < 1e-9
+    d = pre.detrend(x + np.sin(i), "demean")
+    assert abs(d.mean()) < 1e-12
+    assert np.allclose(pre.detrend(x, "constant"), x - x.mean())
+
+
+def test_cosine_taper_and_window_shape():
+    w = pre.cosine_taper(11, 1.0)
+    assert w[0] == 0.0 and w[-1] == 0.0 and abs(w[5] - 1.0) < 1e-15 or w.max() <= 1.0
+    # reference parameters: 5 %, at most 30 s, at 50 Hz over a day
+    n, fs = 4_320_000, 50.0
+    win = pre.taper_window(n, fs, max_percentage=0.05, type="cosine", max_length=30.0)
+    wlen = 1500
+    assert len(win) == n and win[0] == 0.0 and win[-1] == 0.0
+    assert np.all(win[wlen:n - wlen] == 1.0) and np.all(np.diff(win[:wlen]) >= 0)
+    assert np.allclose(win[:wlen], win[::-1][:wlen])
+    # half-cosine ramp of 2*wlen+1 points
+    assert np.allclose(win[:wlen], 0.5 * (1 - np.cos(np.pi * np.arange(wlen) / (wlen - 1) * (wlen - 1) / wlen)), atol=1e-3)
+    h = pre.taper_window(1000, 1.0, max_percentage=0.1, type="hann")
+    assert np.allclose(h[:100], signal.windows.hann(201)[:100])
+
+
+def test_filter_designs_match_survey_numbers():
+    sos = pre.butter_sos(250.0, "bandpass", freqmin=3.0, freqmax=12.0, corners=4)
+    assert sos.shape == (4, 6)
+    _, p, _ = signal.sos2zpk(sos)
+    assert abs(np.max(np.abs(p)) - 0.9819) < 2e-4
+    c = pre.cheby2_lowpass_sos(250.0, 25.0)
+    assert c.shape == (6, 6)
+    _, p, _ = signal.sos2zpk(c)
+    assert abs(np.max(np.abs(p)) - 0.96036) < 2e-4
+    hp = pre.butter_sos(250.0, "highpass", freq=0.05, corners=4)
+    _, p, _ = signal.sos2zpk(hp)
+    assert abs(np.max(np.abs(p)) - 0.99952) < 1e-4
+
+
+def test_filter_response_and_decimate():
+    fs = 250.0
+    t = np.arange(200_000) / fs
+    inband, outband = np.sin(2 * np.pi * 7.5 * t), np.sin(2 * np.pi * 40.0 * t)
+    y = pre.filter_(inband + outband, fs, "bandpass", freqmin=3.0, freqmax=12.0)
+    tail = slice(50_000, None)
+    assert abs(np.std(y[tail]) / np.std(inband[tail]) - 1.0) < 2e-2
+    y2 = pre.filter_(outband, fs, "bandpass", freqmin=3.0, freqmax=12.0)
+    assert np.std(y2[tail]) < 3e-3                          # -50 dB at 40 Hz
+    zp = pre.filter_(inband, fs, "bandpass", freqmin=3.0, freqmax=12.0, zerophase=True)
+    lag = np.argmax(signal.correlate(zp[60_000:120_000], inband[60_000:120_000], mode="same")) - 30_000
+    assert lag == 0                                         # zero phase
+    d, fs2 = pre.decimate(inband, fs, 5)
+    assert fs2 == 50.0 and len(d) == 40_000
+    assert abs(np.std(d[10_000:]) / np.std(inband) - 1.0) < 2e-2
+    d_nf, _ = pre.decimate(inband, fs, 5, no_filter=True)
+    assert np.array_equal(d_nf, inband[::5])
+
+
+def test_process_chain_config2():
+    fs = 250.0
+    n = 250 * 600
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n) + 3.0 + 1e-6 * np.arange(n) + np.sin(2 * np.pi * 7.5 * np.arange(n) / fs)
+    ops = [("detrend", {"type": "demean"}),
+           ("taper", {"type": "cosine", "max_percentage": 0.05, "max_length": 30.0}),
+           ("filter", {"type": "bandpass", "freqmin": 3.0, "freqmax": 12.0}),
+           ("decimate", {"factor": 5}),
+           ("detrend", {"type": "demean"}),
+           ("taper", {"type": "cosine", "max_percentage": 0.05, "max_length": 30.0})]
+    y, fs2 = pre.process(x, fs, ops)
+    assert fs2 == 50.0 and len(y) == n // 5 and abs(y.mean()) < 1e-3 * np.std(y) + 1e-12
+    assert y[0] == 0.0 and abs(y[-1]) < 1e-12

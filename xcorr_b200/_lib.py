@@ -55,6 +55,29 @@ class xcb_plan_info(ctypes.Structure):
     ]
 
 
+class xcb_pointwise(ctypes.Structure):
+    _fields_ = [
+        ("detrend", ctypes.c_int32),
+        ("taper_left", ctypes.c_int32),
+        ("taper_right", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("ramp_left", ctypes.c_void_p),
+        ("ramp_right", ctypes.c_void_p),
+    ]
+
+
+class xcb_sos(ctypes.Structure):
+    _fields_ = [
+        ("n_sections", ctypes.c_int32),
+        ("decimate", ctypes.c_int32),
+        ("reverse", ctypes.c_int32),
+        ("chunk", ctypes.c_int32),
+        ("coef", (ctypes.c_double * 5) * 12),
+        ("carry", ctypes.POINTER(ctypes.c_double)),
+        ("carry_group", ctypes.POINTER(ctypes.c_double)),
+    ]
+
+
 # every symbol include/xcorr_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
 SYMBOLS = {
@@ -68,6 +91,14 @@ SYMBOLS = {
     "xcb_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "xcb_correlate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "xcb_argmax": (ctypes.c_int, [_i32, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "xcb_stats_workspace_bytes": (ctypes.c_int, [_i64, _i32, ctypes.POINTER(ctypes.c_size_t)]),
+    "xcb_stats": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),
+    "xcb_pointwise_apply": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, _i64, _i64, _i32,
+                                           ctypes.POINTER(xcb_pointwise), _vp, _vp]),
+    "xcb_sosfilt_workspace_bytes": (ctypes.c_int, [_i64, _i32, ctypes.POINTER(xcb_sos),
+                                                   ctypes.POINTER(ctypes.c_size_t)]),
+    "xcb_sosfilt": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, _i64, _i64, _i32, ctypes.POINTER(xcb_sos),
+                                   ctypes.POINTER(xcb_pointwise), _vp, _vp, _vp]),
     "xcb_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "xcb_profile_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(_i64)]),

@@ -1,0 +1,437 @@
+// Stream preprocessing on device: the array-valued obspy
+// Trace operations the reference's op-lists name (stream/process.py:29-94).
+//
+//   xcb_stats      sum x, sum i*x, first, last  (detrend coefficients)   -- P1
+//   xcb_pointwise  y = taper(i) * (x - (c0 + c1*i))                       -- P1, P2
+//   xcb_sosfilt    causal cascade of second-order sections (scipy sosfilt,
+//                  DF2T, zero initial state), optional fused pointwise
+//                  prologue and decimating store                          -- P3, P4
+//
+// sosfilt is sequential in time; here it is a three-phase chunked scan that is
+// exact (no warm-up approximation, so long-memory filters such as a 0.05 Hz
+// high-pass at 250 Hz are fine):
+//   1. every chunk (one thread, `chunk` samples) runs the cascade from zero
+//      state and keeps its final state z_c (2S doubles);
+//   2. the chunk start states follow s_{c+1} = P s_c + z_c with P the cascade's
+//      state transition over one chunk (built on the host by simulating unit
+//      states); done hierarchically: fold groups of 64 chunks, one short
+//      sequential sweep over groups with P^64, expand inside groups;
+//   3. every chunk reruns from its true start state and stores the outputs
+//      (every `decimate`-th one).
+// All arithmetic is float64 regardless of the storage dtype, in the same
+// operation order as scipy's sosfilt.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/xcorr_b200.h"
+
+namespace {
+
+constexpr int kGroup = 64;        // chunks per carry group
+constexpr int kMaxSections = 12;
+
+struct PointwiseDev {
+  int32_t detrend;                // 0 none, 1 demean, 2 linear, 3 simple
+  int32_t taper_left, taper_right;
+  const double* ramp_left;
+  const double* ramp_right;
+};
+
+__device__ __forceinline__ void trend_coefficients(const PointwiseDev& pw, const double* st, int64_t n, double& c0,
+                                                   double& c1) {
+  c0 = 0.0;
+  c1 = 0.0;
+  if (pw.detrend == 1) {
+    c0 = st[0] / (double)n;
+  } else if (pw.detrend == 2) {
+    const double nn = (double)n, ibar = 0.5 * (nn - 1.0);
+    const double sxx = nn * (nn * nn - 1.0) / 12.0;
+    c1 = n > 1 ? (st[1] - ibar * st[0]) / sxx : 0.0;
+    c0 = st[0] / nn - c1 * ibar;
+  } else if (pw.detrend == 3) {
+    c0 = st[2];
+    c1 = n > 1 ? (st[3] - st[2]) / (double)(n - 1) : 0.0;
+  }
+}
+
+__device__ __forceinline__ double pointwise_value(const PointwiseDev& pw, double v, int64_t i, int64_t n, double c0,
+                                                  double c1) {
+  if (pw.detrend) v -= c0 + c1 * (double)i;
+  if (i < pw.taper_left) v *= __ldg(pw.ramp_left + i);
+  else if (i >= n - pw.taper_right) v *= __ldg(pw.ramp_right + (i - (n - pw.taper_right)));
+  return v;
+}
+
+// ---------------------------------------------------------------- statistics
+template <class T>
+__global__ void __launch_bounds__(256) stats_partial(const T* __restrict__ x, int64_t n, int64_t stride, int blocks,
+                                                     double* __restrict__ partial) {
+  const int sig = blockIdx.y, b = blockIdx.x;
+  const T* xs = x + (int64_t)sig * stride;
+  const int64_t per = (n + blocks - 1) / blocks;
+  const int64_t lo = (int64_t)b * per;
+  int64_t hi = lo + per;
+  if (hi > n) hi = n;
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+    const double v = (double)xs[i];
+    s0 += v;
+    s1 += v * (double)i;
+  }
+  __shared__ double r0[256], r1[256];
+  r0[threadIdx.x] = s0;
+  r1[threadIdx.x] = s1;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r0[threadIdx.x] += r0[threadIdx.x + o]; r1[threadIdx.x] += r1[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[((int64_t)sig * blocks + b) * 2 + 0] = r0[0];
+    partial[((int64_t)sig * blocks + b) * 2 + 1] = r1[0];
+  }
+}
+
+template <class T>
+__global__ void stats_final(const T* __restrict__ x, int64_t n, int64_t stride, int blocks,
+                            const double* __restrict__ partial, double* __restrict__ stats) {
+  const int sig = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  double s0 = 0.0, s1 = 0.0;
+  for (int b = 0; b < blocks; ++b) {            // fixed order: bit-reproducible
+    s0 += partial[((int64_t)sig * blocks + b) * 2 + 0];
+    s1 += partial[((int64_t)sig * blocks + b) * 2 + 1];
+  }
+  const T* xs = x + (int64_t)sig * stride;
+  stats[sig * 4 + 0] = s0;
+  stats[sig * 4 + 1] = s1;
+  stats[sig * 4 + 2] = (double)xs[0];
+  stats[sig * 4 + 3] = (double)xs[n - 1];
+}
+
+// ----------------------------------------------------------------- pointwise
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) pointwise_kernel(const TI* __restrict__ x, int64_t xs, TO* __restrict__ y,
+                                                        int64_t ys, int64_t n, PointwiseDev pw,
+                                                        const double* __restrict__ stats) {
+  const int sig = blockIdx.y;
+  double c0, c1;
+  trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
+  const TI* xi = x + (int64_t)sig * xs;
+  TO* yo = y + (int64_t)sig * ys;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    yo[i] = (TO)pointwise_value(pw, (double)xi[i], i, n, c0, c1);
+}
+
+// ------------------------------------------------------------------- sosfilt
+template <int S> struct SosCoef { double c[S][5]; };     // b0 b1 b2 a1 a2
+
+template <int S> __device__ __forceinline__ double cascade(const SosCoef<S>& f, double (&z)[2 * S], double v) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const double y = f.c[s][0] * v + z[2 * s];
+    z[2 * s] = f.c[s][1] * v - f.c[s][3] * y + z[2 * s + 1];
+    z[2 * s + 1] = f.c[s][2] * v - f.c[s][4] * y;
+    v = y;
+  }
+  return v;
+}
+
+// phase 1: zero-state final state of every chunk
+template <int S, class TI>
+__global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
+                                                  int chunk, int64_t n_chunks, const __grid_constant__ SosCoef<S> f,
+                                                  PointwiseDev pw, const double* __restrict__ stats, int reverse,
+                                                  double* __restrict__ zstate) {
+  const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (gid >= (int64_t)n_signals * n_chunks) return;
+  const int sig = (int)(gid / n_chunks);
+  const int64_t c = gid - (int64_t)sig * n_chunks;
+  double c0, c1;
+  trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
+  const TI* xi = x + (int64_t)sig * xs;
+  double z[2 * S];
+#pragma unroll
+  for (int k = 0; k < 2 * S; ++k) z[k] = 0.0;
+  const int64_t t0 = c * chunk;
+  int64_t t1 = t0 + chunk;
+  if (t1 > n) t1 = n;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t i = reverse ? n - 1 - t : t;
+    cascade<S>(f, z, pointwise_value(pw, (double)__ldg(xi + i), i, n, c0, c1));
+  }
+  double* out = zstate + gid * (2 * S);
+#pragma unroll
+  for (int k = 0; k < 2 * S; ++k) out[k] = z[k];
+}
+
+// phase 3: rerun every chunk from its true start state and store
+template <int S, class TI, class TO>
+__global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int64_t n, int64_t xs, TO* __restrict__ y,
+                                                  int64_t ys, int n_signals, int chunk, int64_t n_chunks,
+                                                  const __grid_constant__ SosCoef<S> f, PointwiseDev pw,
+                                                  const double* __restrict__ stats, int reverse, int decim,
+                                                  const double* __restrict__ sstart) {
+  const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (gid >= (int64_t)n_signals * n_chunks) return;
+  const int sig = (int)(gid / n_chunks);
+  const int64_t c = gid - (int64_t)sig * n_chunks;
+  double c0, c1;
+  trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
+  const TI* xi = x + (int64_t)sig * xs;
+  TO* yo = y + (int64_t)sig * ys;
+  double z[2 * S];
+  const double* in = sstart + gid * (2 * S);
+#pragma unroll
+  for (int k = 0; k < 2 * S; ++k) z[k] = in[k];
+  const int64_t t0 = c * chunk;
+  int64_t t1 = t0 + chunk;
+  if (t1 > n) t1 = n;
+  int64_t next_keep = (t0 + decim - 1) / decim * decim;     // first t >= t0 with t % decim == 0
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t i = reverse ? n - 1 - t : t;
+    const double v = cascade<S>(f, z, pointwise_value(pw, (double)__ldg(xi + i), i, n, c0, c1));
+    if (decim == 1) {
+      yo[i] = (TO)v;
+    } else if (t == next_keep) {
+      yo[t / decim] = (TO)v;
+      next_keep += decim;
+    }
+  }
+}
+
+// phase 2: chunk start states.  One warp per (signal, group); d = 2S <= 24.
+// mode 0: fold   e_g = sum over the group's chunks (zero start)      -> gstate[sig][g]
+// mode 2: expand sstart[c] for the group's chunks from gstart[sig][g]
+__global__ void __launch_bounds__(32) sos_carry_group(const double* __restrict__ zstate, int d, int64_t n_chunks,
+                                                      int64_t n_groups, const double* __restrict__ P, int mode,
+                                                      double* __restrict__ gstate, double* __restrict__ sstart) {
+  __shared__ double s[32];
+  __shared__ double Ps[24 * 24];
+  const int lane = threadIdx.x;
+  const int64_t sg = blockIdx.x;                 // sig * n_groups + g
+  const int64_t sig = sg / n_groups, g = sg - sig * n_groups;
+  for (int k = lane; k < d * d; k += 32) Ps[k] = P[k];
+  s[lane] = (mode == 2 && lane < d) ? gstate[sg * d + lane] : 0.0;
+  __syncwarp();
+  const int64_t c0 = g * kGroup;
+  int64_t c1 = c0 + kGroup;
+  if (c1 > n_chunks) c1 = n_chunks;
+  for (int64_t c = c0; c < c1; ++c) {
+    const int64_t ci = sig * n_chunks + c;
+    if (mode == 2 && lane < d) sstart[ci * d + lane] = s[lane];
+    double acc = lane < d ? zstate[ci * d + lane] : 0.0;
+    if (lane < d)
+      for (int k = 0; k < d; ++k) acc += Ps[lane * d + k] * s[k];
+    __syncwarp();
+    s[lane] = acc;
+    __syncwarp();
+  }
+  if (mode == 0 && lane < d) gstate[sg * d + lane] = s[lane];
+}
+
+// sequential sweep over groups (one warp per signal): gstate holds e_g on entry,
+// the group START states on exit.
+__global__ void __launch_bounds__(32) sos_carry_sweep(int d, int64_t n_groups, const double* __restrict__ PG,
+                                                      double* __restrict__ gstate) {
+  __shared__ double s[32];
+  __shared__ double Ps[24 * 24];
+  const int lane = threadIdx.x;
+  const int64_t sig = blockIdx.x;
+  for (int k = lane; k < d * d; k += 32) Ps[k] = PG[k];
+  s[lane] = 0.0;
+  __syncwarp();
+  for (int64_t g = 0; g < n_groups; ++g) {
+    double* slot = gstate + (sig * n_groups + g) * d;
+    double acc = lane < d ? slot[lane] : 0.0;       // e_g
+    if (lane < d) {
+      for (int k = 0; k < d; ++k) acc += Ps[lane * d + k] * s[k];
+      slot[lane] = s[lane];                          // start state of group g
+    }
+    __syncwarp();
+    s[lane] = acc;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+struct SosArgs {
+  const void* x; int64_t xs; void* y; int64_t ys; int64_t n; int n_signals;
+  int chunk; int64_t n_chunks; PointwiseDev pw; const double* stats; int reverse, decim;
+  double* zstate; double* sstart; const double (*coef)[5];
+};
+
+template <int S, class TI> cudaError_t run_phase1(const SosArgs& a, cudaStream_t st) {
+  SosCoef<S> f;
+  for (int s = 0; s < S; ++s) for (int k = 0; k < 5; ++k) f.c[s][k] = a.coef[s][k];
+  const int64_t total = (int64_t)a.n_signals * a.n_chunks;
+  sos_phase1<S, TI><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(static_cast<const TI*>(a.x), a.n, a.xs,
+                                                                    a.n_signals, a.chunk, a.n_chunks, f, a.pw,
+                                                                    a.stats, a.reverse, a.zstate);
+  return cudaGetLastError();
+}
+
+template <int S, class TI, class TO> cudaError_t run_phase3(const SosArgs& a, cudaStream_t st) {
+  SosCoef<S> f;
+  for (int s = 0; s < S; ++s) for (int k = 0; k < 5; ++k) f.c[s][k] = a.coef[s][k];
+  const int64_t total = (int64_t)a.n_signals * a.n_chunks;
+  sos_phase3<S, TI, TO><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      static_cast<const TI*>(a.x), a.n, a.xs, static_cast<TO*>(a.y), a.ys, a.n_signals, a.chunk, a.n_chunks, f, a.pw,
+      a.stats, a.reverse, a.decim, a.sstart);
+  return cudaGetLastError();
+}
+
+template <int S> cudaError_t run_phase(int phase, int dti, int dto, const SosArgs& a, cudaStream_t st) {
+  if (phase == 1) return dti == XCB_F32 ? run_phase1<S, float>(a, st) : run_phase1<S, double>(a, st);
+  if (dti == XCB_F32) return dto == XCB_F32 ? run_phase3<S, float, float>(a, st) : run_phase3<S, float, double>(a, st);
+  return dto == XCB_F32 ? run_phase3<S, double, float>(a, st) : run_phase3<S, double, double>(a, st);
+}
+
+cudaError_t run_phase_s(int S, int phase, int dti, int dto, const SosArgs& a, cudaStream_t st) {
+  switch (S) {
+    case 1: return run_phase<1>(phase, dti, dto, a, st);
+    case 2: return run_phase<2>(phase, dti, dto, a, st);
+    case 3: return run_phase<3>(phase, dti, dto, a, st);
+    case 4: return run_phase<4>(phase, dti, dto, a, st);
+    case 5: return run_phase<5>(phase, dti, dto, a, st);
+    case 6: return run_phase<6>(phase, dti, dto, a, st);
+    case 7: return run_phase<7>(phase, dti, dto, a, st);
+    case 8: return run_phase<8>(phase, dti, dto, a, st);
+    case 9: return run_phase<9>(phase, dti, dto, a, st);
+    case 10: return run_phase<10>(phase, dti, dto, a, st);
+    case 11: return run_phase<11>(phase, dti, dto, a, st);
+    case 12: return run_phase<12>(phase, dti, dto, a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+struct SosLayout { int64_t n_chunks, n_groups; int d; size_t off_P, off_PG, off_z, off_s, off_g, total; };
+
+SosLayout sos_layout(int64_t n, int n_signals, const xcb_sos* f) {
+  SosLayout L;
+  L.d = 2 * f->n_sections;
+  L.n_chunks = (n + f->chunk - 1) / f->chunk;
+  L.n_groups = (L.n_chunks + kGroup - 1) / kGroup;
+  size_t o = 0;
+  L.off_P = o;  o += align256(sizeof(double) * L.d * L.d);
+  L.off_PG = o; o += align256(sizeof(double) * L.d * L.d);
+  L.off_z = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_chunks * L.d);
+  L.off_s = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_chunks * L.d);
+  L.off_g = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_groups * L.d);
+  L.total = o;
+  return L;
+}
+
+PointwiseDev to_dev(const xcb_pointwise* p) {
+  PointwiseDev d;
+  memset(&d, 0, sizeof(d));
+  if (p) {
+    d.detrend = p->detrend;
+    d.taper_left = p->taper_left;
+    d.taper_right = p->taper_right;
+    d.ramp_left = p->ramp_left;
+    d.ramp_right = p->ramp_right;
+  }
+  return d;
+}
+
+bool dtype_ok(int d) { return d == XCB_F32 || d == XCB_F64; }
+
+}  // namespace
+
+extern "C" {
+
+XCB_API int xcb_stats_workspace_bytes(int64_t n, int32_t n_signals, size_t* bytes) {
+  if (!bytes || n < 1 || n_signals < 1) return XCB_ERR_ARG;
+  *bytes = sizeof(double) * 2 * 1024 * (size_t)n_signals;
+  return XCB_OK;
+}
+
+XCB_API int xcb_stats(int32_t dtype, const void* x, int64_t n, int64_t stride, int32_t n_signals, double* stats,
+                      void* workspace, void* stream) {
+  if (!x || !stats || !workspace || n < 1 || n_signals < 1 || stride < n || !dtype_ok(dtype)) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int blocks = (int)((n + 65535) / 65536);
+  if (blocks > 1024) blocks = 1024;
+  if (blocks < 1) blocks = 1;
+  double* partial = static_cast<double*>(workspace);
+  dim3 grid((unsigned)blocks, (unsigned)n_signals);
+  if (dtype == XCB_F32) {
+    stats_partial<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), n, stride, blocks, partial);
+    stats_final<float><<<n_signals, 32, 0, st>>>(static_cast<const float*>(x), n, stride, blocks, partial, stats);
+  } else {
+    stats_partial<double><<<grid, 256, 0, st>>>(static_cast<const double*>(x), n, stride, blocks, partial);
+    stats_final<double><<<n_signals, 32, 0, st>>>(static_cast<const double*>(x), n, stride, blocks, partial, stats);
+  }
+  return cudaGetLastError() == cudaSuccess ? XCB_OK : XCB_ERR_CUDA;
+}
+
+XCB_API int xcb_pointwise_apply(int32_t dtype_in, const void* x, int64_t x_stride, int32_t dtype_out, void* y,
+                                int64_t y_stride, int64_t n, int32_t n_signals, const xcb_pointwise* pw,
+                                const double* stats, void* stream) {
+  if (!x || !y || !pw || n < 1 || n_signals < 1 || !dtype_ok(dtype_in) || !dtype_ok(dtype_out)) return XCB_ERR_ARG;
+  if (pw->detrend && !stats) return XCB_ERR_ARG;
+  if (pw->taper_left + pw->taper_right > n) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PointwiseDev d = to_dev(pw);
+  int bx = (int)((n + 256 * 8 - 1) / (256 * 8));
+  if (bx > 65535) bx = 65535;
+  dim3 grid((unsigned)bx, (unsigned)n_signals);
+  if (dtype_in == XCB_F32 && dtype_out == XCB_F32)
+    pointwise_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, x_stride, (float*)y, y_stride, n, d, stats);
+  else if (dtype_in == XCB_F32)
+    pointwise_kernel<float, double><<<grid, 256, 0, st>>>((const float*)x, x_stride, (double*)y, y_stride, n, d, stats);
+  else if (dtype_out == XCB_F32)
+    pointwise_kernel<double, float><<<grid, 256, 0, st>>>((const double*)x, x_stride, (float*)y, y_stride, n, d, stats);
+  else
+    pointwise_kernel<double, double><<<grid, 256, 0, st>>>((const double*)x, x_stride, (double*)y, y_stride, n, d,
+                                                          stats);
+  return cudaGetLastError() == cudaSuccess ? XCB_OK : XCB_ERR_CUDA;
+}
+
+XCB_API int xcb_sosfilt_workspace_bytes(int64_t n, int32_t n_signals, const xcb_sos* f, size_t* bytes) {
+  if (!f || !bytes || n < 1 || n_signals < 1 || f->n_sections < 1 || f->n_sections > kMaxSections || f->chunk < 1)
+    return XCB_ERR_ARG;
+  *bytes = sos_layout(n, n_signals, f).total;
+  return XCB_OK;
+}
+
+XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32_t dtype_out, void* y,
+                        int64_t y_stride, int64_t n, int32_t n_signals, const xcb_sos* f, const xcb_pointwise* pre,
+                        const double* stats, void* workspace, void* stream) {
+  if (!x || !y || !f || !workspace || n < 1 || n_signals < 1 || !dtype_ok(dtype_in) || !dtype_ok(dtype_out))
+    return XCB_ERR_ARG;
+  if (f->n_sections < 1 || f->n_sections > kMaxSections || f->chunk < 1 || f->decimate < 1) return XCB_ERR_ARG;
+  if (!f->carry || !f->carry_group) return XCB_ERR_ARG;
+  if (f->reverse && f->decimate != 1) return XCB_ERR_UNSUPPORTED;
+  if (pre && pre->detrend && !stats) return XCB_ERR_ARG;
+  if (pre && pre->taper_left + pre->taper_right > n) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const SosLayout L = sos_layout(n, n_signals, f);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  double* dP = reinterpret_cast<double*>(ws + L.off_P);
+  double* dPG = reinterpret_cast<double*>(ws + L.off_PG);
+  double* dz = reinterpret_cast<double*>(ws + L.off_z);
+  double* ds = reinterpret_cast<double*>(ws + L.off_s);
+  double* dg = reinterpret_cast<double*>(ws + L.off_g);
+  if (cudaMemcpyAsync(dP, f->carry, sizeof(double) * L.d * L.d, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(dPG, f->carry_group, sizeof(double) * L.d * L.d, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return XCB_ERR_CUDA;
+  SosArgs a;
+  a.x = x; a.xs = x_stride; a.y = y; a.ys = y_stride; a.n = n; a.n_signals = n_signals;
+  a.chunk = f->chunk; a.n_chunks = L.n_chunks; a.pw = to_dev(pre); a.stats = stats;
+  a.reverse = f->reverse; a.decim = f->decimate; a.zstate = dz; a.sstart = ds; a.coef = f->coef;
+  if (run_phase_s(f->n_sections, 1, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
+  const unsigned ng = (unsigned)((int64_t)n_signals * L.n_groups);
+  sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 0, dg, ds);
+  sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg);
+  sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 2, dg, ds);
+  if (cudaGetLastError() != cudaSuccess) return XCB_ERR_CUDA;
+  if (run_phase_s(f->n_sections, 3, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
+  return XCB_OK;
+}
+
+}  // extern "C"

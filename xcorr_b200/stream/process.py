@@ -1,0 +1,478 @@
+r"""
+:mod:`stream.process` -- Stream preprocessing on the GPU
+=========================================================
+
+Array-valued counterpart of the reference's ``xcorr/stream/process.py``: the
+same op-list format ``[('operation', {parameters}), ...]`` and the same
+operation names, applied to a batch of equally sampled traces held in a CUDA
+tensor instead of an obspy ``Stream``.
+
+Operations with array semantics run on the device through the C ABI
+(``xcb_stats``, ``xcb_pointwise_apply``, ``xcb_sosfilt``):
+
+============  ===============================================================
+``detrend``   ``type`` in demean / constant / linear / simple (obspy ``Trace.detrend``)
+``taper``     ``max_percentage``, ``type`` (cosine, hann, ...), ``max_length``, ``side``
+``filter``    ``type`` in bandpass / highpass / lowpass / lowpass_cheby_2,
+              ``corners=4``, ``zerophase=False`` -- causal ``sosfilt`` like obspy
+``decimate``  ``factor`` (<= 16), ``no_filter`` -- Chebyshev-II low-pass + ``[::factor]``
+``trim``      sample-based: ``start``, ``length`` (the time-based trim of the
+              reference is resolved to samples by the caller)
+============  ===============================================================
+
+Filter *design* (``scipy.signal.iirfilter`` / ``cheb2ord`` / ``cheby2`` /
+``zpk2sos``) and the taper ramps are host-side bookkeeping, exactly the calls
+obspy makes; every per-sample operation is device code.  Adjacent operations are
+fused: a detrend and/or taper directly in front of a filter become the filter's
+load prologue, consecutive causal filters become one cascade, and the
+``[::factor]`` of ``decimate`` is the cascade's strided store.
+
+The remaining names of the reference's whitelist (``merge``, ``remove_response``,
+``rotate``, ``select``, ``interpolate``, ``resample``, ...) act on obspy objects
+or station metadata and stay with the reference's client
+(``stream/client.py:996``); they raise ``NotImplementedError`` here.
+"""
+import ctypes
+import hashlib
+import json
+import warnings
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ['process', 'list_operations', 'is_operation', 'device_operations',
+           'hash_operations', 'check_operations_hash', 'operations_to_dict',
+           'operations_to_json', 'PreprocessProgram']
+
+# the reference's whitelist (stream/process.py:29-94); True = runs on the device
+_operations = {
+    'attach_response': False, 'decimate': True, 'detrend': True, 'filter': True,
+    'interpolate': False, 'merge': False, 'normalize': False, 'remove_response': False,
+    'remove_sensitivity': False, 'resample': False, 'rotate': False, 'select': False,
+    'simulate': False, 'taper': True, 'trim': True, 'running_rms': False,
+}
+
+_DETREND = {'demean': 1, 'constant': 1, 'linear': 2, 'simple': 3}
+_SCAN_CHUNK = 1024
+_GROUP = 64
+
+
+def list_operations():
+    r"""Names accepted in an op-list (``stream/process.py:97-101``)."""
+    return list(_operations.keys())
+
+
+def device_operations():
+    r"""The subset that runs on the GPU."""
+    return [k for k, v in _operations.items() if v]
+
+
+def is_operation(operation: str):
+    r"""``stream/process.py:133-149``."""
+    return operation in _operations
+
+
+# -- op-list json / hash helpers (stream/process.py:540-611, util/hasher.py) ---
+_channel_band_codes = 'FGDCESHBMLVURPTQ'
+
+
+def _hash_obj(obj):
+    filtered = {k: v for k, v in obj.items() if k not in ('sha256_hash', 'sha256_hash_metadata',
+                                                          'add_offset', 'scale_factor')}
+    dump = json.dumps(filtered, separators=(',', ':'), sort_keys=True, indent=4, skipkeys=False, default=repr)
+    return hashlib.sha256(dump.encode('utf-8')).hexdigest()
+
+
+def filter_operations(operations: dict):
+    return {c: operations[c] for c in operations if len(c) == 3 and c[0] in _channel_band_codes}
+
+
+def hash_operations(operations: dict):
+    operations = filter_operations(operations)
+    operations['sha256_hash'] = _hash_obj(operations)
+    return operations
+
+
+def check_operations_hash(operations: dict, raise_error: bool = False):
+    if 'sha256_hash' not in operations:
+        raise ValueError('Preprocess operations does not contain a hash!')
+    sha256 = _hash_obj(filter_operations(operations))
+    if raise_error and operations['sha256_hash'] != sha256:
+        raise ValueError("Preprocess operations hash '{}' does not match the computed hash '{}'!"
+                         .format(sha256, operations['sha256_hash']))
+    return operations['sha256_hash'] == sha256
+
+
+def operations_to_dict(operations: str):
+    operations = json.loads(operations)
+    if 'sha256_hash' not in operations:
+        raise ValueError('Preprocess operations does not contain a hash!')
+    sha256 = operations['sha256_hash']
+    operations = hash_operations(operations)
+    if operations['sha256_hash'] != sha256:
+        raise ValueError("Preprocess operations hash '{}' does not match the computed hash '{}'!"
+                         .format(sha256, operations['sha256_hash']))
+    return operations
+
+
+def operations_to_json(operations: dict):
+    return json.dumps(hash_operations(operations))
+
+
+# -- host-side design (the calls obspy makes) ---------------------------------
+def _cosine_taper(npts, p):
+    frac = int(npts * p / 2.0) if p in (0.0, 1.0) else int(npts * p / 2.0 + 0.5)
+    i1, i2, i3, i4 = 0, frac - 1, npts - frac, npts - 1
+    if i1 == i2:
+        i2 += 1
+    if i3 == i4:
+        i3 -= 1
+    w = np.zeros(npts)
+    w[i1:i2 + 1] = 0.5 * (1.0 - np.cos(np.pi * (np.arange(i1, i2 + 1) - i1) / (i2 - i1)))
+    w[i2 + 1:i3] = 1.0
+    w[i3:i4 + 1] = 0.5 * (1.0 + np.cos(np.pi * (i3 - np.arange(i3, i4 + 1)) / (i4 - i3)))
+    return w
+
+
+def _taper_ramps(npts, fs, max_percentage=None, type='hann', max_length=None, side='both', **extra):
+    from scipy import signal
+    if extra:
+        raise TypeError(f"taper: unsupported arguments {sorted(extra)}")
+    half = [int(npts / 2)]
+    if max_percentage is not None:
+        half.append(int(max_percentage * npts))
+    if max_length is not None:
+        half.append(int(max_length * fs))
+    wlen = min(half)
+    M = 2 * wlen if 2 * wlen == npts else 2 * wlen + 1
+    win = _cosine_taper(M, 1.0) if type == 'cosine' else getattr(signal.windows, type)(M)
+    left = win[:wlen] if side in ('both', 'left') else np.zeros(0)
+    right = win[len(win) - wlen:] if side in ('both', 'right') else np.zeros(0)
+    return np.ascontiguousarray(left, dtype=np.float64), np.ascontiguousarray(right, dtype=np.float64)
+
+
+def _cheby2_sos(fs, freq, maxorder=12):
+    from scipy import signal
+    nyquist = fs * 0.5
+    rp, rs, order = 1, 96, 1e99
+    ws = freq / nyquist
+    wp = ws
+    if ws > 1:
+        ws = 1.0
+    while order > maxorder:
+        wp = wp * 0.99
+        order, wn = signal.cheb2ord(wp, ws, rp, rs, analog=0)
+    z, p, k = signal.cheby2(order, rs, wn, btype='low', analog=0, output='zpk')
+    return signal.zpk2sos(z, p, k)
+
+
+def _filter_sos(fs, type, freq=None, freqmin=None, freqmax=None, corners=4, maxorder=12, **extra):
+    from scipy import signal
+    if extra:
+        raise TypeError(f"filter: unsupported arguments {sorted(extra)}")
+    fe = 0.5 * fs
+    if type == 'lowpass_cheby_2':
+        return _cheby2_sos(fs, freq, maxorder)
+    if type == 'bandpass':
+        low, high = freqmin / fe, freqmax / fe
+        if high - 1.0 > -1e-6:
+            warnings.warn('Selected high corner frequency is above Nyquist. Applying a high-pass instead.')
+            return _filter_sos(fs, 'highpass', freq=freqmin, corners=corners)
+        if low > 1:
+            raise ValueError('Selected low corner frequency is above Nyquist.')
+        z, p, k = signal.iirfilter(corners, [low, high], btype='band', ftype='butter', output='zpk')
+    elif type == 'highpass':
+        f = freq / fe
+        if f > 1:
+            raise ValueError('Selected corner frequency is above Nyquist.')
+        z, p, k = signal.iirfilter(corners, f, btype='highpass', ftype='butter', output='zpk')
+    elif type == 'lowpass':
+        f = freq / fe
+        if f > 1:
+            f = 1.0
+            warnings.warn('Selected corner frequency is above Nyquist. Setting Nyquist as high corner.')
+        z, p, k = signal.iirfilter(corners, f, btype='lowpass', ftype='butter', output='zpk')
+    else:
+        raise NotImplementedError(f"filter type {type!r}")
+    return signal.zpk2sos(z, p, k)
+
+
+def _carry_matrices(sos, chunk):
+    """State transition of the DF2T cascade over `chunk` zero-input samples
+    (column i = final state started from unit state i), and its 64th power."""
+    from scipy import signal
+    S = sos.shape[0]
+    d = 2 * S
+    P = np.zeros((d, d))
+    zero = np.zeros(chunk)
+    for i in range(d):
+        zi = np.zeros((S, 2))
+        zi[i // 2, i % 2] = 1.0
+        _, zf = signal.sosfilt(sos, zero, zi=zi)
+        P[:, i] = zf.reshape(-1)
+    return np.ascontiguousarray(P), np.ascontiguousarray(np.linalg.matrix_power(P, _GROUP))
+
+
+# -- program ------------------------------------------------------------------
+class _Stage:
+    """One device launch group: optional pointwise prologue, optional cascade."""
+
+    def __init__(self):
+        self.detrend = 0
+        self.taper = None          # kwargs
+        self.sos = []              # list of (S_i, 6) arrays, concatenated
+        self.decimate = 1
+        self.reverse = False
+
+    @property
+    def has_pointwise(self):
+        return self.detrend != 0 or self.taper is not None
+
+
+class PreprocessProgram:
+    """An op-list compiled into fused device stages for traces of a given
+    length and sampling rate."""
+
+    def __init__(self, operations, npts, sampling_rate):
+        self.npts_in = int(npts)
+        self.fs_in = float(sampling_rate)
+        self.steps = []            # ('stage', _Stage) | ('trim', start, length)
+        n, fs = self.npts_in, self.fs_in
+        cur = None
+
+        def flush():
+            nonlocal cur
+            if cur is not None:
+                self.steps.append(('stage', cur))
+                cur = None
+
+        for op, params in operations:
+            if not is_operation(op):
+                raise ValueError(f'Provided operation "{op}" is invalid.')
+            if not _operations[op]:
+                raise NotImplementedError(
+                    f'operation "{op}" acts on obspy objects / station metadata and is not part of the '
+                    'array-valued GPU path; apply it with the reference client before the hand-off')
+            params = dict(params)
+            if op == 'detrend':
+                kind = _DETREND.get(params.get('type', 'simple'))
+                if kind is None:
+                    raise NotImplementedError(f"detrend type {params.get('type')!r}")
+                if cur is not None and (cur.sos or cur.has_pointwise):
+                    flush()
+                cur = cur or _Stage()
+                cur.detrend = kind
+            elif op == 'taper':
+                if cur is not None and (cur.sos or cur.taper is not None):
+                    flush()
+                cur = cur or _Stage()
+                cur.taper = params
+            elif op == 'filter':
+                zerophase = params.pop('zerophase', False)
+                sos = _filter_sos(fs, **params)
+                if cur is not None and (cur.decimate != 1 or cur.reverse):
+                    flush()
+                cur = cur or _Stage()
+                if sum(len(q) for q in cur.sos) + len(sos) > 12:
+                    flush()
+                    cur = _Stage()
+                cur.sos.append(sos)
+                if zerophase:            # sosfilt(sos, sosfilt(sos, x)[::-1])[::-1]
+                    flush()
+                    cur = _Stage()
+                    cur.sos.append(sos)
+                    cur.reverse = True
+                    flush()
+            elif op == 'decimate':
+                factor = int(params.pop('factor'))
+                no_filter = params.pop('no_filter', False)
+                params.pop('strict_length', None)
+                if params:
+                    raise TypeError(f"decimate: unsupported arguments {sorted(params)}")
+                if factor > 16:
+                    raise ArithmeticError('Automatic filter design is unstable for decimation factors above 16. '
+                                          'Manual decimation is necessary.')
+                if cur is not None and (cur.decimate != 1 or cur.reverse):
+                    flush()
+                cur = cur or _Stage()
+                if not no_filter:
+                    sos = _cheby2_sos(fs, fs * 0.5 / float(factor))
+                    if sum(len(q) for q in cur.sos) + len(sos) > 12:
+                        flush()
+                        cur = _Stage()
+                    cur.sos.append(sos)
+                cur.decimate = factor
+                flush()
+                n = (n + factor - 1) // factor
+                fs = fs / float(factor)
+                continue
+            elif op == 'trim':
+                flush()
+                start = int(params.get('start', 0))
+                length = params.get('length')
+                length = n - start if length is None else int(length)
+                if start < 0 or length < 1 or start + length > n:
+                    raise ValueError('trim outside the trace')
+                self.steps.append(('trim', start, length))
+                n = length
+        flush()
+        self.npts_out, self.fs_out = n, fs
+        # resolve lengths per stage
+        n, fs = self.npts_in, self.fs_in
+        for st in self.steps:
+            if st[0] == 'trim':
+                n = st[2]
+                continue
+            s = st[1]
+            s.npts, s.fs = n, fs
+            n = (n + s.decimate - 1) // s.decimate
+            fs = fs / float(s.decimate)
+
+    # ------------------------------------------------------------------------
+    def run(self, x, out_dtype=None):
+        """x: CUDA tensor (n_signals, npts) float32/float64, last dim contiguous.
+        Returns a new tensor (n_signals, npts_out)."""
+        import torch
+        lib = _lib.load()
+        if x.dim() != 2 or x.shape[1] != self.npts_in or x.stride(1) != 1 or not x.is_cuda:
+            raise ValueError(f'x must be a CUDA tensor (n_signals, {self.npts_in})')
+        out_dtype = out_dtype or x.dtype
+        xcb = {torch.float32: _lib.XCB_F32, torch.float64: _lib.XCB_F64}
+        dev = x.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nsig = x.shape[0]
+        cur = x
+        keep = []       # host/device objects that must outlive the async launches
+        n_stage = sum(1 for s in self.steps if s[0] == 'stage')
+        i_stage = 0
+        for st in self.steps:
+            if st[0] == 'trim':
+                cur = cur[:, st[1]:st[1] + st[2]]
+                continue
+            s = st[1]
+            i_stage += 1
+            n = s.npts
+            assert cur.shape[1] == n
+            dt_out = out_dtype if i_stage == n_stage else torch.float64
+            pw = _lib.xcb_pointwise()
+            stats = None
+            if s.has_pointwise:
+                pw.detrend = s.detrend
+                if s.taper is not None:
+                    left, right = _taper_ramps(n, s.fs, **s.taper)
+                    dl = torch.from_numpy(left).to(dev)
+                    dr = torch.from_numpy(right).to(dev)
+                    keep += [dl, dr]
+                    pw.taper_left, pw.taper_right = len(left), len(right)
+                    pw.ramp_left, pw.ramp_right = dl.data_ptr(), dr.data_ptr()
+                if s.detrend:
+                    nb = ctypes.c_size_t()
+                    _lib.check(lib.xcb_stats_workspace_bytes(n, nsig, ctypes.byref(nb)), 'xcb_stats_workspace_bytes')
+                    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                    stats = torch.empty((nsig, 4), dtype=torch.float64, device=dev)
+                    keep += [ws, stats]
+                    _lib.check(lib.xcb_stats(xcb[cur.dtype], cur.data_ptr(), n, cur.stride(0), nsig,
+                                             stats.data_ptr(), ws.data_ptr(), stream), 'xcb_stats')
+            if s.sos:
+                sos = np.vstack(s.sos)
+                f = _lib.xcb_sos()
+                f.n_sections = len(sos)
+                f.decimate = s.decimate
+                f.reverse = int(s.reverse)
+                f.chunk = _SCAN_CHUNK
+                for k, sec in enumerate(sos):
+                    a0 = sec[3]
+                    for m, v in enumerate((sec[0] / a0, sec[1] / a0, sec[2] / a0, sec[4] / a0, sec[5] / a0)):
+                        f.coef[k][m] = float(v)
+                P, PG = _carry_matrices(sos, _SCAN_CHUNK)
+                keep += [P, PG]
+                f.carry = P.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+                f.carry_group = PG.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+                nb = ctypes.c_size_t()
+                _lib.check(lib.xcb_sosfilt_workspace_bytes(n, nsig, ctypes.byref(f), ctypes.byref(nb)),
+                           'xcb_sosfilt_workspace_bytes')
+                ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                n_out = (n + s.decimate - 1) // s.decimate
+                y = torch.empty((nsig, n_out), dtype=dt_out, device=dev)
+                keep += [ws, f]
+                _lib.check(lib.xcb_sosfilt(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), xcb[y.dtype], y.data_ptr(),
+                                           y.stride(0), n, nsig, ctypes.byref(f),
+                                           ctypes.byref(pw) if s.has_pointwise else None,
+                                           stats.data_ptr() if stats is not None else None, ws.data_ptr(), stream),
+                           'xcb_sosfilt')
+            else:
+                y = cur
+                if s.has_pointwise:
+                    y = torch.empty((nsig, n), dtype=dt_out, device=dev)
+                    _lib.check(lib.xcb_pointwise_apply(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), xcb[y.dtype],
+                                                       y.data_ptr(), y.stride(0), n, nsig, ctypes.byref(pw),
+                                                       stats.data_ptr() if stats is not None else None, stream),
+                               'xcb_pointwise_apply')
+                if s.decimate != 1:     # decimate(no_filter=True): data[::factor]
+                    y = y[:, ::s.decimate]
+            cur = y
+        # (the carry matrices are pageable host memory: cudaMemcpyAsync returns once they are staged,
+        #  and torch's allocator is stream ordered, so `keep` may be dropped with the launches still queued)
+        if cur is x:
+            cur = x.clone()
+        if cur.dtype != out_dtype:
+            cur = cur.to(out_dtype)
+        if not cur.is_contiguous():
+            cur = cur.contiguous()
+        return cur
+
+
+def process(waveforms, operations: list, sampling_rate: float = None, inventory=None,
+            starttime=None, endtime=None, raise_error: bool = False, verb: int = 0, **kwargs):
+    r"""Process a batch of traces given a list of operations.
+
+    Mirrors ``stream/process.py:300-412``: operations are applied in order;
+    on failure a warning is given and ``None`` returned unless `raise_error`.
+
+    Parameters
+    ----------
+    waveforms : CUDA :class:`torch.Tensor` ``(n_traces, npts)``
+        Equally sampled traces (the reference passes an obspy Stream).
+    operations : `list`
+        ``[('operation', {parameters}), ...]``.
+    sampling_rate : `float`
+        Sampling rate of `waveforms` in Hz (obspy keeps it in ``Trace.stats``).
+
+    Returns
+    -------
+    (waveforms, sampling_rate) after the operations, or ``None`` on failure.
+    """
+    if sampling_rate is None:
+        raise TypeError('``sampling_rate`` is required for array input')
+    if not isinstance(raise_error, bool):
+        raise TypeError('``raise_error`` is not of type `bool`')
+    ops = []
+    for operation_params in operations:
+        if not isinstance(operation_params, (tuple, list)) or len(operation_params) != 2:
+            msg = 'Provided operation should be a tuple or list with length 2 (method:str,params:dict).'
+            if raise_error:
+                raise TypeError(msg)
+            warnings.warn(msg, UserWarning)
+            continue
+        operation, parameters = operation_params
+        if not is_operation(operation):
+            msg = 'Provided operation "{}" is invalid thus ignored.'.format(operation)
+            if raise_error:
+                raise ValueError(msg)
+            warnings.warn(msg, UserWarning)
+            continue
+        ops.append((operation, parameters))
+    try:
+        prog = PreprocessProgram(ops, waveforms.shape[-1], sampling_rate)
+        if verb > 0:
+            print('Apply processing operations:', [o for o, _ in ops])
+        return prog.run(waveforms, **kwargs), prog.fs_out
+    except (KeyboardInterrupt, SystemExit):
+        raise
+    except Exception as error:
+        msg = 'Failed to execute operations. Error: {}'.format(error)
+        if raise_error:
+            raise RuntimeError(msg)
+        warnings.warn(msg, UserWarning)
+        return None
