@@ -79,10 +79,15 @@ def test_pointwise_ops(env, ops):
 def test_filters_and_decimation(env, ops):
     x = raw_traces(2, 250 * 800 + 3, 250.0, 2)
     got, ref = run(env, x, 250.0, ops)
-    assert np.max(np.abs(got - ref)) <= 1e-11 * np.max(np.abs(ref)), np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+    err = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
+    print("relative error", ops[0], err)
+    # a 0.05 Hz corner at 250 Hz (pole radius 0.99952) amplifies rounding by ~1/(1-|p|)^2 = 4e6:
+    # two float64 evaluation orders of the same recurrence differ at the 1e-10 level there
+    long_memory = any(p.get("freq") == 0.05 for _, p in ops)
+    assert err <= (1e-9 if long_memory else 1e-12), err
 
 
-@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-6)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
 def test_config2_chain_then_cc(env, dtype, tol):
     """BASELINE config 2 chain (250 Hz -> 50 Hz) followed by cc(): the
     preprocessed traces and the resulting CCF both match the CPU restatement."""
@@ -93,6 +98,7 @@ def test_config2_chain_then_cc(env, dtype, tol):
     x = src + np.sin(2 * np.pi * 7.5 * t / fs) + 1e-6 * t + 3.0
     got, ref = run(env, x, fs, CFG2_OPS, dtype)
     assert got.shape[1] == n_raw // 5
+    print('trace error', dtype.__name__, np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
     assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref))
     n = got.shape[1]
     plan = xb.CorrelationPlan(n, 3, xb.all_pairs(3), dtype=torch.float32 if dtype == np.float32 else torch.float64)
@@ -100,7 +106,9 @@ def test_config2_chain_then_cc(env, dtype, tol):
     for q, (i, j) in enumerate(xb.all_pairs(3)):
         r = orc.cc(ref[i], ref[j], unbiased=False)
         assert np.argmax(ccf[q]) == np.argmax(r)
-        assert np.max(np.abs(ccf[q] - r)) <= (1e-12 if dtype == np.float64 else 1e-5) * np.max(np.abs(r)) * 10
+        e = np.max(np.abs(ccf[q] - r)) / np.max(np.abs(r))
+        print('ccf error', dtype.__name__, e)
+        assert e <= (1e-12 if dtype == np.float64 else 1e-5)
 
 
 def test_oplist_error_behaviour(env):

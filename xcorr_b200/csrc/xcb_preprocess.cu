@@ -127,12 +127,17 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const TI* __restrict__ x
 // ------------------------------------------------------------------- sosfilt
 template <int S> struct SosCoef { double c[S][5]; };     // b0 b1 b2 a1 a2
 
+// One sample through the cascade.  Every product and sum is rounded separately
+// (__dmul_rn / __dadd_rn are never contracted into FMAs) in the order of
+// scipy's _sosfilt loop, so a chunk started from the same state reproduces
+// scipy.signal.sosfilt bit for bit:
+//   y  = b0*x + z0;   z0 = (b1*x - a1*y) + z1;   z1 = b2*x - a2*y
 template <int S> __device__ __forceinline__ double cascade(const SosCoef<S>& f, double (&z)[2 * S], double v) {
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    const double y = f.c[s][0] * v + z[2 * s];
-    z[2 * s] = f.c[s][1] * v - f.c[s][3] * y + z[2 * s + 1];
-    z[2 * s + 1] = f.c[s][2] * v - f.c[s][4] * y;
+    const double y = __dadd_rn(__dmul_rn(f.c[s][0], v), z[2 * s]);
+    z[2 * s] = __dadd_rn(__dsub_rn(__dmul_rn(f.c[s][1], v), __dmul_rn(f.c[s][3], y)), z[2 * s + 1]);
+    z[2 * s + 1] = __dsub_rn(__dmul_rn(f.c[s][2], v), __dmul_rn(f.c[s][4], y));
     v = y;
   }
   return v;

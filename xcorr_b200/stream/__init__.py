@@ -1,3 +1,3 @@
-"""Mirror of the reference's ``xcorr.stream`` namespace for the hot path."""
-from . import process as _process_module  # noqa: F401
-from .process import process, PreprocessProgram  # noqa: F401
+"""Mirror of the reference's ``xcorr.stream`` namespace for the hot path:
+``xcorr_b200.stream.process.process(waveforms, operations, ...)``."""
+from . import process  # noqa: F401
