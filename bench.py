@@ -337,7 +337,7 @@ def run_gpu(args):
             cb = cpu_reference(n, steps=1, warmup=0)
             out["cpu_baseline"] = {"value": cb["value"], "unit": "pair-days/s", "cores": cb["cores"],
                                    "kind": "port", "sample": cb["sample"]}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -363,10 +363,29 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "pair-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+def _claim_stdout():
+    """stdout must carry exactly one JSON line: anything a library prints on fd 1
+    (e.g. NCCL's version banner) is diverted to stderr; emit() writes the line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
 
 
 def main():
+    global _REAL_STDOUT
+    _REAL_STDOUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
