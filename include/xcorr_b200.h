@@ -61,7 +61,7 @@ typedef struct xcb_desc {
   int32_t win_stride;
   int32_t normalize;       /* util/cc.py:76-77 */
   int32_t unbiased;        /* intended util/cc.py:79 == signal/unbias.py:85 weights n/(n-|k|) */
-  int32_t stack;           /* 1: ccf[pair][lag] accumulates over windows instead of ccf[pair][window][lag] */
+  int32_t stack;           /* 1: ccf[pair][lag] += sum over the windows (cross-spectra summed before ONE inverse per pair) */
   const int32_t* pairs;    /* host, [n_pairs][2] receiver indices (i, j): Rxy[k] = sum_m x_i[m+k] x_j[m] */
   int64_t lag_index_min;   /* lag.attrs['index_min'] (core/init.py:191-208, util/time.py:94-108) */
   int64_t lag_index_max;   /* exclusive; both 0 -> full 2n-1 lags */
@@ -73,7 +73,7 @@ typedef struct xcb_plan_info {
   int64_t spectrum_elems;  /* M complex elements per signal in `spec` */
   int64_t n_lags;          /* K = lag_index_max - lag_index_min */
   int64_t n_signals;       /* n_receivers * n_windows */
-  int64_t n_jobs;          /* n_pairs * n_windows */
+  int64_t n_jobs;          /* inverse transforms per call: n_pairs * n_windows (n_pairs when stacking) */
   int64_t jobs_in_flight;
   size_t workspace_bytes;
   int32_t nd;
@@ -143,8 +143,8 @@ typedef struct xcb_sos {
   int32_t reverse;           /* 1: filter from the last sample backwards (second half of zerophase=True) */
   int32_t chunk;             /* samples per scan chunk (e.g. 1024) */
   double coef[12][5];        /* b0 b1 b2 a1 a2 per section (a0 = 1) */
-  const double* carry;       /* host, [2S][2S] row-major: state transition over `chunk` samples */
-  const double* carry_group; /* host, [2S][2S]: carry^64 */
+  const double* carry;       /* device, [2S][2S] row-major: state transition over `chunk` samples */
+  const double* carry_group; /* device, [2S][2S]: carry^256 (one carry group = 256 chunks) */
 } xcb_sos;
 
 /* stats[s] = {sum x, sum i*x, x[0], x[n-1]} (device double[n_signals][4]) */

@@ -40,7 +40,7 @@ def choose_dims(n):
 
 
 def emu_cc(x, pairs, dims=None, i0=None, i1=None, normalize=True, unbiased=False,
-           want_spec=False):
+           want_spec=False, n_stack=1):
     """x: (S, n) float32/float64.  Returns (ccf[P, K], sumsq[S], spec or None)."""
     x = np.ascontiguousarray(x)
     S, n = x.shape
@@ -61,6 +61,6 @@ def emu_cc(x, pairs, dims=None, i0=None, i1=None, normalize=True, unbiased=False
                       ctypes.c_int64(i0), ctypes.c_int64(i1), int(normalize), int(unbiased),
                       out.ctypes.data_as(ctypes.c_void_p),
                       sumsq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                      spec.ctypes.data_as(ctypes.c_void_p) if want_spec else None)
+                      spec.ctypes.data_as(ctypes.c_void_p) if want_spec else None, int(n_stack))
     assert rc == 0, rc
     return out, sumsq, spec

@@ -53,7 +53,7 @@ template <class T> static bool run_pass(const PassParams<T>& p, bool row) {
 template <class T>
 static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_stride, int n_signals,
                     const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased,
-                    T* out, double* sumsq_out, T* spec_out) {
+                    T* out, double* sumsq_out, T* spec_out, int n_stack) {
   PlanGeom g;
   int d[kMaxDims], k = nd;
   if (nd == 0) { if (!plan_choose_dims(n, d, &k)) return -1; }
@@ -83,14 +83,18 @@ static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_st
   const int64_t K = i1 - i0;
   std::vector<Job> jobs(n_pairs);
   for (int q = 0; q < n_pairs; ++q) {
-    jobs[q].sig_i = pairs[2 * q]; jobs[q].sig_j = pairs[2 * q + 1];
-    jobs[q].spec_i = (int64_t)pairs[2 * q] * g.M; jobs[q].spec_j = (int64_t)pairs[2 * q + 1] * g.M;
+    // signals are [receiver][window] when stacking (n_stack windows per receiver)
+    jobs[q].sig_i = pairs[2 * q] * n_stack; jobs[q].sig_j = pairs[2 * q + 1] * n_stack;
+    jobs[q].spec_i = (int64_t)jobs[q].sig_i * g.M; jobs[q].spec_j = (int64_t)jobs[q].sig_j * g.M;
     jobs[q].out_off = (int64_t)q * K;
   }
   std::vector<cx<T>> work((size_t)n_pairs * g.M);
+  std::vector<double> rnorm(n_signals);
+  for (int s = 0; s < n_signals; ++s) rnorm[s] = 1.0 / sqrt(sumsq[s]);
   CorrFlags f; f.i0 = i0; f.i1 = i1; f.normalize = normalize; f.unbiased = unbiased; f.accumulate = 0;
+  f.n_stack = n_stack; f.stack_sig_stride = 1; f.stack_spec_stride = g.M;
   for (int a = g.nd - 1; a >= 0; --a) {
-    PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec.data(), sumsq.data(), jobs.data(), n_pairs, work.data(), out, f);
+    PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec.data(), rnorm.data(), jobs.data(), n_pairs, work.data(), out, f);
     if (!run_pass(p, a == g.nd - 1)) return -4;
   }
   return 0;
@@ -103,11 +107,12 @@ int emu_choose_dims(int64_t n, int* dims, int* nd) { return plan_choose_dims(n, 
 // dtype: 0 = f32, 1 = f64.  x: [n_signals][x_stride]; pairs: [n_pairs][2]; out: [n_pairs][i1-i0]
 int emu_cc(int dtype, int64_t n, const int* dims, int nd, const void* x, int64_t x_stride, int n_signals,
            const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased, void* out,
-           double* sumsq_out, void* spec_out) {
+           double* sumsq_out, void* spec_out, int n_stack) {
+  if (n_stack < 1) n_stack = 1;
   if (dtype == 0)
     return emu_cc_t<float>(n, dims, nd, (const float*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
-                           unbiased, (float*)out, sumsq_out, (float*)spec_out);
+                           unbiased, (float*)out, sumsq_out, (float*)spec_out, n_stack);
   return emu_cc_t<double>(n, dims, nd, (const double*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
-                          unbiased, (double*)out, sumsq_out, (double*)spec_out);
+                          unbiased, (double*)out, sumsq_out, (double*)spec_out, n_stack);
 }
 }

@@ -101,3 +101,16 @@ def test_planner_named_shapes_are_exact():
     d = choose_dims(900_000)
     assert 900_000 <= int(np.prod(d)) <= 1.03 * 900_000
     assert choose_dims(5) == (64,)
+
+
+def test_spectral_stacking_sums_windows():
+    """n_stack windows per receiver: the cross-spectra are summed before one
+    inverse transform == sum of the per-window CCFs (each normalised by its own norms)."""
+    n, R, W = 3000, 3, 4
+    rec = np.stack([orc.synthetic_receivers(R, n, seed=50 + w, delay=17) for w in range(W)], axis=1)   # [R, W, n]
+    pairs = [(0, 1), (1, 2), (0, 2)]
+    out, _, _ = emu_cc(rec.reshape(R * W, n), pairs, n_stack=W)
+    for q, (i, j) in enumerate(pairs):
+        ref = sum(orc.cc(rec[i, w], rec[j, w], unbiased=False) for w in range(W))
+        assert np.max(np.abs(out[q] - ref)) <= 1e-13 * np.max(np.abs(ref))
+        assert np.argmax(out[q]) == np.argmax(ref)

@@ -127,6 +127,12 @@ __global__ void __launch_bounds__(256) xcb_sumsq_finish(const double* __restrict
   block_sumsq<256>(sumsq + blockIdx.x, red, threadIdx.x);
 }
 
+// rnorm[s] = 1 / ||x_s||  (zero norm -> inf, so the product becomes NaN like util/cc.py:77)
+__global__ void xcb_rnorm(const double* __restrict__ sumsq, int64_t n, double* __restrict__ rnorm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rnorm[i] = 1.0 / sqrt(sumsq[i]);
+}
+
 // First index of the row maximum (np.argmax): two stages, ties -> lowest index.
 template <class T>
 __global__ void __launch_bounds__(256) xcb_argmax_partial(const T* __restrict__ rows, int64_t row_len, int chunks,
@@ -199,7 +205,8 @@ struct xcb_plan {
   int64_t K = 0, i0 = 0, i1 = 0;
   int64_t n_signals = 0, n_jobs = 0, jobs_in_flight = 0;
   int64_t tiles0 = 0;               // CTAs per signal of the first forward pass
-  size_t work_bytes = 0, partial_bytes = 0;
+  int64_t win_stride = 1;           // signals between consecutive windows of a receiver
+  size_t work_bytes = 0, partial_bytes = 0, rnorm_bytes = 0;
   void* d_hi = nullptr;
   void* d_lo = nullptr;
   void* d_inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
@@ -287,7 +294,8 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   if (pl->i0 < 0 || pl->i1 > 2 * d->n - 1 || pl->i0 >= pl->i1) { delete pl; return XCB_ERR_ARG; }
   pl->K = pl->i1 - pl->i0;
   pl->n_signals = (int64_t)d->n_receivers * d->n_windows;
-  pl->n_jobs = (int64_t)d->n_pairs * d->n_windows;
+  // stacking sums the cross-spectra over windows inside the pair-product pass: one job per pair
+  pl->n_jobs = d->stack ? (int64_t)d->n_pairs : (int64_t)d->n_pairs * d->n_windows;
 
   { cudaError_t e = cudaGetDevice(&pl->device); if (e != cudaSuccess) { delete pl; return cuda_fail(e, "cudaGetDevice"); } }
   for (int a = 0; a < nd; ++a) {
@@ -303,9 +311,11 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   // holds two jobs that write the same output row)
   const int64_t rs = (d->recv_stride == 0 && d->win_stride == 0) ? d->n_windows : d->recv_stride;
   const int64_t ws = (d->recv_stride == 0 && d->win_stride == 0) ? 1 : d->win_stride;
+  pl->win_stride = ws;
   if (pl->n_jobs > 0) {
     std::vector<Job> jobs((size_t)pl->n_jobs);
-    for (int64_t w = 0; w < d->n_windows; ++w)
+    const int64_t nw = d->stack ? 1 : d->n_windows;
+    for (int64_t w = 0; w < nw; ++w)
       for (int64_t q = 0; q < d->n_pairs; ++q) {
         Job& j = jobs[(size_t)(w * d->n_pairs + q)];
         int64_t si = pl->pairs[2 * q] * rs + w * ws, sj = pl->pairs[2 * q + 1] * rs + w * ws;
@@ -325,11 +335,11 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   if (nd > 1) pl->tiles0 = (pl->g.M / pl->g.S[0]) * ((pl->g.S[1] + C - 1) / C);
   else pl->tiles0 = (pl->g.M / dims[0] + C - 1) / C;
   pl->partial_bytes = align_up((size_t)pl->n_signals * pl->tiles0 * sizeof(double), 256);
+  pl->rnorm_bytes = align_up((size_t)pl->n_signals * sizeof(double), 256);
   const size_t per_job = (size_t)pl->g.M * (pl->dtype == XCB_F32 ? 8 : 16);
   size_t cap = d->max_work_bytes > 0 ? (size_t)d->max_work_bytes : ((size_t)4 << 30);
   int64_t fl = (int64_t)(cap / per_job);
   if (fl < 1) fl = 1;
-  if (d->stack && fl > d->n_pairs) fl = d->n_pairs > 0 ? d->n_pairs : 1;   // one window per launch
   if (fl > pl->n_jobs) fl = pl->n_jobs > 0 ? pl->n_jobs : 1;
   pl->jobs_in_flight = fl;
   pl->work_bytes = align_up((size_t)fl * per_job, 256);
@@ -347,7 +357,7 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
   info->n_signals = pl->n_signals;
   info->n_jobs = pl->n_jobs;
   info->jobs_in_flight = pl->jobs_in_flight;
-  info->workspace_bytes = pl->partial_bytes + pl->work_bytes;
+  info->workspace_bytes = pl->partial_bytes + pl->rnorm_bytes + pl->work_bytes;
   info->nd = pl->g.nd;
   for (int a = 0; a < kMaxDims; ++a) info->dims[a] = pl->g.dims[a];
   info->dtype = pl->dtype;
@@ -394,17 +404,25 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
                        cudaStream_t st) {
   DevTables<T> tb = dev_tables<T>(pl);
   const PlanGeom& g = pl->g;
-  cx<T>* work = reinterpret_cast<cx<T>*>(static_cast<unsigned char*>(ws) + pl->partial_bytes);
+  double* rnorm = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + pl->partial_bytes);
+  cx<T>* work = reinterpret_cast<cx<T>*>(static_cast<unsigned char*>(ws) + pl->partial_bytes + pl->rnorm_bytes);
+  xcb_rnorm<<<(unsigned)((pl->n_signals + 255) / 256), 256, 0, st>>>(sumsq, pl->n_signals, rnorm);
+  XCB_CUDA(cudaGetLastError());
   CorrFlags f;
   f.i0 = pl->i0;
   f.i1 = pl->i1;
   f.normalize = pl->desc.normalize;
   f.unbiased = pl->desc.unbiased;
   f.accumulate = pl->desc.stack;
+  if (pl->desc.stack) {
+    f.n_stack = pl->desc.n_windows;
+    f.stack_sig_stride = (int)pl->win_stride;
+    f.stack_spec_stride = pl->win_stride * g.M;
+  }
   for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
     int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
     for (int a = g.nd - 1; a >= 0; --a) {
-      PassParams<T> p = make_inverse_pass<T>(g, tb, a, static_cast<const cx<T>*>(spec), sumsq, pl->d_jobs + j0, nj,
+      PassParams<T> p = make_inverse_pass<T>(g, tb, a, static_cast<const cx<T>*>(spec), rnorm, pl->d_jobs + j0, nj,
                                              work, static_cast<T*>(ccf), f);
       int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
       if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;

@@ -134,7 +134,7 @@ template <class T> bool bulk_eligible(const PassParams<T>& p) {
   if (enabled < 0) { const char* e = getenv("XCB_BULK"); enabled = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower than the plain kernel
   if (!enabled) return false;
   if (p.store_mode == RS_EPI) return false;
-  if (p.load_mode == RL_PROLOGUE) return reinterpret_cast<uintptr_t>(p.spec) % 16 == 0;
+  if (p.load_mode == RL_PROLOGUE) return p.n_stack == 1 && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0;
   if (p.load_mode == RL_CPLX)
     return reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && (p.in_stride * (int64_t)sizeof(cx<T>)) % 16 == 0;
   return false;

@@ -76,8 +76,14 @@ template <class T> struct PassParams {
   int64_t pair_start[kMaxDims + 1];                  // first pair id of region g (pair 0 = row 0)
   int64_t n_pairs_rows;      // total row pairs
   const Job* jobs;           // [n_batch]
-  const double* sumsq;       // per signal
+  const double* rnorm;       // per signal: 1/||x|| (= rsqrt of the sum of squares)
   const cx<T>* spec;         // spectrum buffer base
+  // spectral stacking: the product is summed over n_stack windows before the
+  // inverse transform; window w of a job adds w*stack_spec_stride elements to
+  // its spectrum offsets and w*stack_sig_stride to its signal indices
+  int32_t n_stack;
+  int32_t stack_sig_stride;
+  int64_t stack_spec_stride;
   // ---- lag epilogue (inverse last pass) ----
   int64_t n;                 // samples per window
   int64_t L;                 // 2M
@@ -416,24 +422,39 @@ template <class T, int R1, int R2> struct RowPass {
       const Job jb = p.jobs[batch];
       const RowInfo<T> ia = info[2 * lp];
       const int64_t rb = info[2 * lp + 1].row;
-      T scale = T(0.25);
-      if (p.normalize) scale = T(0.25 / sqrt(p.sumsq[jb.sig_i] * p.sumsq[jb.sig_j]));
       const bool ok = ia.row >= 0;
-      const cx<T>* zi_a = p.spec + jb.spec_i + (ok ? ia.row : 0) * N;
-      const cx<T>* zj_a = p.spec + jb.spec_j + (ok ? ia.row : 0) * N;
-      const cx<T>* zi_b = p.spec + jb.spec_i + (ok ? rb : 0) * N;
-      const cx<T>* zj_b = p.spec + jb.spec_j + (ok ? rb : 0) * N;
+      const int64_t off_a = (ok ? ia.row : 0) * N, off_b = (ok ? rb : 0) * N;
       const bool row0 = ia.row == 0;
       constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
       constexpr int PB = 2;
       for (int it0 = 0; it0 < ITER; it0 += PB) {
-        cx<T> A[PB], Am[PB], B[PB], Bm[PB];
+        cx<T> va[PB], vb[PB];
 #pragma unroll
-        for (int u = 0; u < PB; ++u) {
-          const int e = t + (it0 + u) * 2 * TJ;
-          if (ok && e < N) {
-            const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-            A[u] = zi_a[e]; Am[u] = zi_b[em]; B[u] = zj_a[e]; Bm[u] = zj_b[em];
+        for (int u = 0; u < PB; ++u) va[u].x = va[u].y = vb[u].x = vb[u].y = T(0);
+        for (int w = 0; w < p.n_stack; ++w) {
+          const cx<T>* zi = p.spec + jb.spec_i + w * p.stack_spec_stride;
+          const cx<T>* zj = p.spec + jb.spec_j + w * p.stack_spec_stride;
+          T scale = T(0.25);
+          if (p.normalize)
+            scale = T(0.25 * p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+          cx<T> A[PB], Am[PB], B[PB], Bm[PB];
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            const int e = t + (it0 + u) * 2 * TJ;
+            if (ok && e < N) {
+              const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+              A[u] = zi[off_a + e]; Am[u] = zi[off_b + em]; B[u] = zj[off_a + e]; Bm[u] = zj[off_b + em];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < PB; ++u) {
+            const int e = t + (it0 + u) * 2 * TJ;
+            if (ok && e < N) {
+              cx<T> pa, pb;
+              pair_product(A[u], Am[u], B[u], Bm[u], ia.wrow, ld_ro(p.tw_inner + e), scale, pa, pb);
+              va[u] = cadd(va[u], pa);
+              vb[u] = cadd(vb[u], pb);
+            }
           }
         }
 #pragma unroll
@@ -441,11 +462,8 @@ template <class T, int R1, int R2> struct RowPass {
           const int e = t + (it0 + u) * 2 * TJ;
           if (e < N) {
             const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-            cx<T> va, vb;
-            va.x = va.y = vb.x = vb.y = T(0);
-            if (ok) pair_product(A[u], Am[u], B[u], Bm[u], ia.wrow, ld_ro(p.tw_inner + e), scale, va, vb);
-            smem[e * CP + 2 * lp] = va;
-            smem[em * CP + 2 * lp + 1] = vb;
+            smem[e * CP + 2 * lp] = va[u];
+            smem[em * CP + 2 * lp + 1] = vb[u];
           }
         }
       }

@@ -226,12 +226,14 @@ inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb
 struct CorrFlags {
   int64_t i0 = 0, i1 = 0;
   int normalize = 1, unbiased = 0, accumulate = 0;
+  int n_stack = 1, stack_sig_stride = 0;       // spectral stacking over windows
+  int64_t stack_spec_stride = 0;
 };
 
 // inverse pass a (run a = nd-1 down to 0) over `n_jobs` jobs using work[n_jobs][M]
 template <class T>
 inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb, int a, const cx<T>* spec,
-                                       const double* sumsq, const Job* jobs, int n_jobs, cx<T>* work,
+                                       const double* rnorm, const Job* jobs, int n_jobs, cx<T>* work,
                                        T* ccf, const CorrFlags& f) {
   PassParams<T> p;
   pass_common(p, g, tb, a);
@@ -241,8 +243,11 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   p.out = work;
   p.in_stride = p.out_stride = g.M;
   p.jobs = jobs;
-  p.sumsq = sumsq;
+  p.rnorm = rnorm;
   p.spec = spec;
+  p.n_stack = f.n_stack;
+  p.stack_sig_stride = f.stack_sig_stride;
+  p.stack_spec_stride = f.stack_spec_stride;
   p.normalize = f.normalize;
   p.ccf = ccf;
   p.i0 = f.i0;

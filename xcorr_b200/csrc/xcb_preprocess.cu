@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr int kGroup = 64;        // chunks per carry group
+constexpr int kGroup = 256;       // chunks per carry group
 constexpr int kMaxSections = 12;
 
 struct PointwiseDev {
@@ -94,20 +94,26 @@ __global__ void __launch_bounds__(256) stats_partial(const T* __restrict__ x, in
 }
 
 template <class T>
-__global__ void stats_final(const T* __restrict__ x, int64_t n, int64_t stride, int blocks,
-                            const double* __restrict__ partial, double* __restrict__ stats) {
-  const int sig = blockIdx.x;
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) stats_final(const T* __restrict__ x, int64_t n, int64_t stride, int blocks,
+                                                  const double* __restrict__ partial, double* __restrict__ stats) {
+  const int sig = blockIdx.x, lane = threadIdx.x;
   double s0 = 0.0, s1 = 0.0;
-  for (int b = 0; b < blocks; ++b) {            // fixed order: bit-reproducible
+  for (int b = lane; b < blocks; b += 32) {      // fixed association: bit-reproducible
     s0 += partial[((int64_t)sig * blocks + b) * 2 + 0];
     s1 += partial[((int64_t)sig * blocks + b) * 2 + 1];
   }
-  const T* xs = x + (int64_t)sig * stride;
-  stats[sig * 4 + 0] = s0;
-  stats[sig * 4 + 1] = s1;
-  stats[sig * 4 + 2] = (double)xs[0];
-  stats[sig * 4 + 3] = (double)xs[n - 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_down_sync(0xffffffffu, s0, o);
+    s1 += __shfl_down_sync(0xffffffffu, s1, o);
+  }
+  if (lane == 0) {
+    const T* xs = x + (int64_t)sig * stride;
+    stats[sig * 4 + 0] = s0;
+    stats[sig * 4 + 1] = s1;
+    stats[sig * 4 + 2] = (double)xs[0];
+    stats[sig * 4 + 3] = (double)xs[n - 1];
+  }
 }
 
 // ----------------------------------------------------------------- pointwise
@@ -127,48 +133,99 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const TI* __restrict__ x
 // ------------------------------------------------------------------- sosfilt
 template <int S> struct SosCoef { double c[S][5]; };     // b0 b1 b2 a1 a2
 
-// One sample through the cascade.  Every product and sum is rounded separately
-// (__dmul_rn / __dadd_rn are never contracted into FMAs) in the order of
-// scipy's _sosfilt loop, so a chunk started from the same state reproduces
-// scipy.signal.sosfilt bit for bit:
-//   y  = b0*x + z0;   z0 = (b1*x - a1*y) + z1;   z1 = b2*x - a2*y
-template <int S> __device__ __forceinline__ double cascade(const SosCoef<S>& f, double (&z)[2 * S], double v) {
+// One sample through the cascade (scipy _sosfilt recurrence, DF2T):
+//   y = b0*x + z0;   z0 = b1*x - a1*y + z1;   z1 = b2*x - a2*y
+// with fused multiply-adds (5 per section).  Against scipy's separately rounded
+// products this differs at the 1e-14 level of the output (measured; a bit-exact
+// non-fused variant gave the same parity at twice the FP64 work).
+template <int S> struct SosRegs { double c[S][5]; };
+
+// Coefficients go from the kernel-parameter bank into ordinary registers through
+// an opaque generic load.  Left to itself the compiler keeps them in the 63-entry
+// uniform register file and spills/fills that file on every sample (measured: 176
+// instructions per sample instead of ~60, ALU pipe 82 % busy with moves).
+template <int S> __device__ __forceinline__ void load_coefficients(const SosCoef<S>& f, SosRegs<S>& r) {
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      double v;
+      asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(&f.c[s][k]));
+      r.c[s][k] = v;
+    }
+}
+
+template <int S> __device__ __forceinline__ double cascade(const SosRegs<S>& f, double (&z)[2 * S], double v) {
 #pragma unroll
   for (int s = 0; s < S; ++s) {
-    const double y = __dadd_rn(__dmul_rn(f.c[s][0], v), z[2 * s]);
-    z[2 * s] = __dadd_rn(__dsub_rn(__dmul_rn(f.c[s][1], v), __dmul_rn(f.c[s][3], y)), z[2 * s + 1]);
-    z[2 * s + 1] = __dsub_rn(__dmul_rn(f.c[s][2], v), __dmul_rn(f.c[s][4], y));
+    const double y = fma(f.c[s][0], v, z[2 * s]);
+    z[2 * s] = fma(-f.c[s][3], y, fma(f.c[s][1], v, z[2 * s + 1]));
+    z[2 * s + 1] = fma(-f.c[s][4], y, f.c[s][2] * v);
     v = y;
   }
   return v;
 }
 
-// phase 1: zero-state final state of every chunk
+constexpr int kIlp = 1;   // chunks per thread
+constexpr int kBatch = 8; // samples fetched ahead per thread: the loads leave the serial recurrence's critical path
+
+// phase 1: zero-state final state of every chunk (thread q owns chunks kIlp*q ... kIlp*q + kIlp-1)
 template <int S, class TI>
 __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
                                                   int chunk, int64_t n_chunks, const __grid_constant__ SosCoef<S> f,
                                                   PointwiseDev pw, const double* __restrict__ stats, int reverse,
                                                   double* __restrict__ zstate) {
+  const int64_t per_sig = (n_chunks + kIlp - 1) / kIlp;
   const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (gid >= (int64_t)n_signals * n_chunks) return;
-  const int sig = (int)(gid / n_chunks);
-  const int64_t c = gid - (int64_t)sig * n_chunks;
+  if (gid >= (int64_t)n_signals * per_sig) return;
+  const int sig = (int)(gid / per_sig);
+  const int64_t cb = (gid - (int64_t)sig * per_sig) * kIlp;
   double c0, c1;
   trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
   const TI* xi = x + (int64_t)sig * xs;
-  double z[2 * S];
+  SosRegs<S> fr;
+  load_coefficients<S>(f, fr);
+  double z[kIlp][2 * S];
 #pragma unroll
-  for (int k = 0; k < 2 * S; ++k) z[k] = 0.0;
-  const int64_t t0 = c * chunk;
-  int64_t t1 = t0 + chunk;
-  if (t1 > n) t1 = n;
-  for (int64_t t = t0; t < t1; ++t) {
-    const int64_t i = reverse ? n - 1 - t : t;
-    cascade<S>(f, z, pointwise_value(pw, (double)__ldg(xi + i), i, n, c0, c1));
+  for (int u = 0; u < kIlp; ++u)
+#pragma unroll
+    for (int k = 0; k < 2 * S; ++k) z[u][k] = 0.0;
+  TI buf[kIlp][kBatch], nxt[kIlp][kBatch];
+  auto fetch = [&](TI (&dst)[kIlp][kBatch], int j0) {
+#pragma unroll
+    for (int u = 0; u < kIlp; ++u)
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t t = (cb + u) * chunk + j0 + b;
+        dst[u][b] = (j0 + b < chunk && t < n) ? __ldg(xi + (reverse ? n - 1 - t : t)) : TI(0);
+      }
+  };
+  fetch(buf, 0);
+  for (int j0 = 0; j0 < chunk; j0 += kBatch) {
+    fetch(nxt, j0 + kBatch);
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b)
+#pragma unroll
+      for (int u = 0; u < kIlp; ++u) {
+        const int64_t t = (cb + u) * chunk + j0 + b;
+        if (j0 + b < chunk && t < n) {
+          const int64_t i = reverse ? n - 1 - t : t;
+          cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < kIlp; ++u)
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) buf[u][b] = nxt[u][b];
   }
-  double* out = zstate + gid * (2 * S);
 #pragma unroll
-  for (int k = 0; k < 2 * S; ++k) out[k] = z[k];
+  for (int u = 0; u < kIlp; ++u) {
+    if (cb + u < n_chunks) {
+      double* out = zstate + ((int64_t)sig * n_chunks + cb + u) * (2 * S);
+#pragma unroll
+      for (int k = 0; k < 2 * S; ++k) out[k] = z[u][k];
+    }
+  }
 }
 
 // phase 3: rerun every chunk from its true start state and store
@@ -178,85 +235,148 @@ __global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int6
                                                   const __grid_constant__ SosCoef<S> f, PointwiseDev pw,
                                                   const double* __restrict__ stats, int reverse, int decim,
                                                   const double* __restrict__ sstart) {
+  const int64_t per_sig = (n_chunks + kIlp - 1) / kIlp;
   const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (gid >= (int64_t)n_signals * n_chunks) return;
-  const int sig = (int)(gid / n_chunks);
-  const int64_t c = gid - (int64_t)sig * n_chunks;
+  if (gid >= (int64_t)n_signals * per_sig) return;
+  const int sig = (int)(gid / per_sig);
+  const int64_t cb = (gid - (int64_t)sig * per_sig) * kIlp;
   double c0, c1;
   trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
   const TI* xi = x + (int64_t)sig * xs;
   TO* yo = y + (int64_t)sig * ys;
-  double z[2 * S];
-  const double* in = sstart + gid * (2 * S);
+  SosRegs<S> fr;
+  load_coefficients<S>(f, fr);
+  double z[kIlp][2 * S];
+  int64_t next_keep[kIlp];
 #pragma unroll
-  for (int k = 0; k < 2 * S; ++k) z[k] = in[k];
-  const int64_t t0 = c * chunk;
-  int64_t t1 = t0 + chunk;
-  if (t1 > n) t1 = n;
-  int64_t next_keep = (t0 + decim - 1) / decim * decim;     // first t >= t0 with t % decim == 0
-  for (int64_t t = t0; t < t1; ++t) {
-    const int64_t i = reverse ? n - 1 - t : t;
-    const double v = cascade<S>(f, z, pointwise_value(pw, (double)__ldg(xi + i), i, n, c0, c1));
-    if (decim == 1) {
-      yo[i] = (TO)v;
-    } else if (t == next_keep) {
-      yo[t / decim] = (TO)v;
-      next_keep += decim;
-    }
+  for (int u = 0; u < kIlp; ++u) {
+    const int64_t c = cb + u < n_chunks ? cb + u : n_chunks - 1;
+    const double* in = sstart + ((int64_t)sig * n_chunks + c) * (2 * S);
+#pragma unroll
+    for (int k = 0; k < 2 * S; ++k) z[u][k] = in[k];
+    next_keep[u] = ((cb + u) * (int64_t)chunk + decim - 1) / decim * decim;   // first t >= t0 with t % decim == 0
+  }
+  TI buf[kIlp][kBatch], nxt[kIlp][kBatch];
+  auto fetch = [&](TI (&dst)[kIlp][kBatch], int j0) {
+#pragma unroll
+    for (int u = 0; u < kIlp; ++u)
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) {
+        const int64_t t = (cb + u) * chunk + j0 + b;
+        dst[u][b] = (j0 + b < chunk && t < n) ? __ldg(xi + (reverse ? n - 1 - t : t)) : TI(0);
+      }
+  };
+  fetch(buf, 0);
+  for (int j0 = 0; j0 < chunk; j0 += kBatch) {
+    fetch(nxt, j0 + kBatch);
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b)
+#pragma unroll
+      for (int u = 0; u < kIlp; ++u) {
+        const int64_t t = (cb + u) * chunk + j0 + b;
+        if (j0 + b < chunk && t < n) {
+          const int64_t i = reverse ? n - 1 - t : t;
+          const double v = cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
+          if (decim == 1) {
+            yo[i] = (TO)v;
+          } else if (t == next_keep[u]) {
+            yo[t / decim] = (TO)v;
+            next_keep[u] += decim;
+          }
+        }
+      }
+#pragma unroll
+    for (int u = 0; u < kIlp; ++u)
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) buf[u][b] = nxt[u][b];
   }
 }
 
-// phase 2: chunk start states.  One warp per (signal, group); d = 2S <= 24.
-// mode 0: fold   e_g = sum over the group's chunks (zero start)      -> gstate[sig][g]
-// mode 2: expand sstart[c] for the group's chunks from gstart[sig][g]
+// phase 2: chunk start states, s_{c+1} = P s_c + z_c (d = 2S <= 24).  Lane r owns
+// row r of the transition matrix (registers) and component r of the state; the
+// state is broadcast with shuffles, the row product runs as four independent
+// partial sums, and the next z is prefetched.
+__device__ __forceinline__ double carry_step(const double (&prow)[24], double s, double add, int d) {
+  double a0 = add, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 24; k += 4) {
+    const double s0 = __shfl_sync(0xffffffffu, s, k), s1 = __shfl_sync(0xffffffffu, s, k + 1);
+    const double s2 = __shfl_sync(0xffffffffu, s, k + 2), s3 = __shfl_sync(0xffffffffu, s, k + 3);
+    a0 = fma(prow[k], s0, a0);          // rows are zero padded beyond d
+    a1 = fma(prow[k + 1], s1, a1);
+    a2 = fma(prow[k + 2], s2, a2);
+    a3 = fma(prow[k + 3], s3, a3);
+  }
+  (void)d;
+  return (a0 + a1) + (a2 + a3);
+}
+
+// One warp per (signal, group).
+// mode 0: fold   e_g = state after the group's chunks from a zero start -> gstate[sig][g]
+// mode 2: expand sstart[c] for the group's chunks from gstate[sig][g] (group start state)
 __global__ void __launch_bounds__(32) sos_carry_group(const double* __restrict__ zstate, int d, int64_t n_chunks,
                                                       int64_t n_groups, const double* __restrict__ P, int mode,
                                                       double* __restrict__ gstate, double* __restrict__ sstart) {
-  __shared__ double s[32];
-  __shared__ double Ps[24 * 24];
   const int lane = threadIdx.x;
   const int64_t sg = blockIdx.x;                 // sig * n_groups + g
   const int64_t sig = sg / n_groups, g = sg - sig * n_groups;
-  for (int k = lane; k < d * d; k += 32) Ps[k] = P[k];
-  s[lane] = (mode == 2 && lane < d) ? gstate[sg * d + lane] : 0.0;
-  __syncwarp();
+  double prow[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) prow[k] = (lane < d && k < d) ? P[lane * d + k] : 0.0;
+  double s = (mode == 2 && lane < d) ? gstate[sg * d + lane] : 0.0;
   const int64_t c0 = g * kGroup;
   int64_t c1 = c0 + kGroup;
   if (c1 > n_chunks) c1 = n_chunks;
-  for (int64_t c = c0; c < c1; ++c) {
-    const int64_t ci = sig * n_chunks + c;
-    if (mode == 2 && lane < d) sstart[ci * d + lane] = s[lane];
-    double acc = lane < d ? zstate[ci * d + lane] : 0.0;
-    if (lane < d)
-      for (int k = 0; k < d; ++k) acc += Ps[lane * d + k] * s[k];
-    __syncwarp();
-    s[lane] = acc;
-    __syncwarp();
+  const double* zb = zstate + (sig * n_chunks) * d;
+  double* sb = sstart + (sig * n_chunks) * d;
+  // z is fetched kPf steps ahead: a step is ~100 cycles of arithmetic, DRAM latency several hundred
+  constexpr int kPf = 8;
+  double cur[kPf], nxt[kPf];
+#pragma unroll
+  for (int u = 0; u < kPf; ++u) cur[u] = (lane < d && c0 + u < c1) ? zb[(c0 + u) * d + lane] : 0.0;
+  for (int64_t cb = c0; cb < c1; cb += kPf) {
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) nxt[u] = (lane < d && cb + kPf + u < c1) ? zb[(cb + kPf + u) * d + lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) {
+      if (cb + u < c1) {
+        if (mode == 2 && lane < d) sb[(cb + u) * d + lane] = s;
+        s = carry_step(prow, s, cur[u], d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) cur[u] = nxt[u];
   }
-  if (mode == 0 && lane < d) gstate[sg * d + lane] = s[lane];
+  if (mode == 0 && lane < d) gstate[sg * d + lane] = s;
 }
 
 // sequential sweep over groups (one warp per signal): gstate holds e_g on entry,
-// the group START states on exit.
+// the group START states on exit; PG = P^kGroup.
 __global__ void __launch_bounds__(32) sos_carry_sweep(int d, int64_t n_groups, const double* __restrict__ PG,
                                                       double* __restrict__ gstate) {
-  __shared__ double s[32];
-  __shared__ double Ps[24 * 24];
   const int lane = threadIdx.x;
   const int64_t sig = blockIdx.x;
-  for (int k = lane; k < d * d; k += 32) Ps[k] = PG[k];
-  s[lane] = 0.0;
-  __syncwarp();
-  for (int64_t g = 0; g < n_groups; ++g) {
-    double* slot = gstate + (sig * n_groups + g) * d;
-    double acc = lane < d ? slot[lane] : 0.0;       // e_g
-    if (lane < d) {
-      for (int k = 0; k < d; ++k) acc += Ps[lane * d + k] * s[k];
-      slot[lane] = s[lane];                          // start state of group g
+  double prow[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) prow[k] = (lane < d && k < d) ? PG[lane * d + k] : 0.0;
+  double s = 0.0;
+  double* base = gstate + sig * n_groups * d;
+  constexpr int kPf = 8;
+  double cur[kPf], nxt[kPf];
+#pragma unroll
+  for (int u = 0; u < kPf; ++u) cur[u] = (lane < d && u < n_groups) ? base[u * d + lane] : 0.0;
+  for (int64_t gb = 0; gb < n_groups; gb += kPf) {
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) nxt[u] = (lane < d && gb + kPf + u < n_groups) ? base[(gb + kPf + u) * d + lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) {
+      if (gb + u < n_groups) {
+        if (lane < d) base[(gb + u) * d + lane] = s;        // start state of group gb+u (its e was read already)
+        s = carry_step(prow, s, cur[u], d);
+      }
     }
-    __syncwarp();
-    s[lane] = acc;
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) cur[u] = nxt[u];
   }
 }
 
@@ -270,7 +390,7 @@ struct SosArgs {
 template <int S, class TI> cudaError_t run_phase1(const SosArgs& a, cudaStream_t st) {
   SosCoef<S> f;
   for (int s = 0; s < S; ++s) for (int k = 0; k < 5; ++k) f.c[s][k] = a.coef[s][k];
-  const int64_t total = (int64_t)a.n_signals * a.n_chunks;
+  const int64_t total = (int64_t)a.n_signals * ((a.n_chunks + kIlp - 1) / kIlp);
   sos_phase1<S, TI><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(static_cast<const TI*>(a.x), a.n, a.xs,
                                                                     a.n_signals, a.chunk, a.n_chunks, f, a.pw,
                                                                     a.stats, a.reverse, a.zstate);
@@ -280,7 +400,7 @@ template <int S, class TI> cudaError_t run_phase1(const SosArgs& a, cudaStream_t
 template <int S, class TI, class TO> cudaError_t run_phase3(const SosArgs& a, cudaStream_t st) {
   SosCoef<S> f;
   for (int s = 0; s < S; ++s) for (int k = 0; k < 5; ++k) f.c[s][k] = a.coef[s][k];
-  const int64_t total = (int64_t)a.n_signals * a.n_chunks;
+  const int64_t total = (int64_t)a.n_signals * ((a.n_chunks + kIlp - 1) / kIlp);
   sos_phase3<S, TI, TO><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
       static_cast<const TI*>(a.x), a.n, a.xs, static_cast<TO*>(a.y), a.ys, a.n_signals, a.chunk, a.n_chunks, f, a.pw,
       a.stats, a.reverse, a.decim, a.sstart);
@@ -422,9 +542,9 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   double* dz = reinterpret_cast<double*>(ws + L.off_z);
   double* ds = reinterpret_cast<double*>(ws + L.off_s);
   double* dg = reinterpret_cast<double*>(ws + L.off_g);
-  if (cudaMemcpyAsync(dP, f->carry, sizeof(double) * L.d * L.d, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-      cudaMemcpyAsync(dPG, f->carry_group, sizeof(double) * L.d * L.d, cudaMemcpyHostToDevice, st) != cudaSuccess)
-    return XCB_ERR_CUDA;
+  // the carry matrices are device resident (uploaded once by the caller): no host copy, no implicit sync
+  dP = const_cast<double*>(f->carry);
+  dPG = const_cast<double*>(f->carry_group);
   SosArgs a;
   a.x = x; a.xs = x_stride; a.y = y; a.ys = y_stride; a.n = n; a.n_signals = n_signals;
   a.chunk = f->chunk; a.n_chunks = L.n_chunks; a.pw = to_dev(pre); a.stats = stats;

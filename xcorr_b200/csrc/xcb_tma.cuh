@@ -286,7 +286,7 @@ xcb_row_pass_bulk(const __grid_constant__ PassParams<T> p) {
     if (prologue) {
       const Job jb = p.jobs[batch];
       T scale = T(0.25);
-      if (p.normalize) scale = T(0.25 / sqrt(p.sumsq[jb.sig_i] * p.sumsq[jb.sig_j]));
+      if (p.normalize) scale = T(0.25 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
       constexpr int TJ = P::TJ;
       const int lp = tid / (2 * TJ), t = tid - lp * (2 * TJ);    // pair slot owned by 2*TJ threads
       const RowInfo<T> ia = info[2 * lp];

@@ -54,8 +54,8 @@ _operations = {
 }
 
 _DETREND = {'demean': 1, 'constant': 1, 'linear': 2, 'simple': 3}
-_SCAN_CHUNK = 1024
-_GROUP = 64
+_SCAN_CHUNK = 512
+_GROUP = 256
 
 
 def list_operations():
@@ -330,50 +330,17 @@ class PreprocessProgram:
             fs = fs / float(s.decimate)
 
     # ------------------------------------------------------------------------
-    def run(self, x, out_dtype=None):
-        """x: CUDA tensor (n_signals, npts) float32/float64, last dim contiguous.
-        Returns a new tensor (n_signals, npts_out)."""
-        import torch
-        lib = _lib.load()
-        if x.dim() != 2 or x.shape[1] != self.npts_in or x.stride(1) != 1 or not x.is_cuda:
-            raise ValueError(f'x must be a CUDA tensor (n_signals, {self.npts_in})')
-        out_dtype = out_dtype or x.dtype
-        xcb = {torch.float32: _lib.XCB_F32, torch.float64: _lib.XCB_F64}
-        dev = x.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        nsig = x.shape[0]
-        cur = x
-        keep = []       # host/device objects that must outlive the async launches
-        n_stage = sum(1 for s in self.steps if s[0] == 'stage')
-        i_stage = 0
+    def _host_design(self):
+        """Per-stage host products (taper ramps, section coefficients, carry
+        matrices): computed once, they depend only on the op-list and lengths."""
+        if getattr(self, '_designed', False):
+            return
         for st in self.steps:
-            if st[0] == 'trim':
-                cur = cur[:, st[1]:st[1] + st[2]]
+            if st[0] != 'stage':
                 continue
             s = st[1]
-            i_stage += 1
-            n = s.npts
-            assert cur.shape[1] == n
-            dt_out = out_dtype if i_stage == n_stage else torch.float64
-            pw = _lib.xcb_pointwise()
-            stats = None
-            if s.has_pointwise:
-                pw.detrend = s.detrend
-                if s.taper is not None:
-                    left, right = _taper_ramps(n, s.fs, **s.taper)
-                    dl = torch.from_numpy(left).to(dev)
-                    dr = torch.from_numpy(right).to(dev)
-                    keep += [dl, dr]
-                    pw.taper_left, pw.taper_right = len(left), len(right)
-                    pw.ramp_left, pw.ramp_right = dl.data_ptr(), dr.data_ptr()
-                if s.detrend:
-                    nb = ctypes.c_size_t()
-                    _lib.check(lib.xcb_stats_workspace_bytes(n, nsig, ctypes.byref(nb)), 'xcb_stats_workspace_bytes')
-                    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-                    stats = torch.empty((nsig, 4), dtype=torch.float64, device=dev)
-                    keep += [ws, stats]
-                    _lib.check(lib.xcb_stats(xcb[cur.dtype], cur.data_ptr(), n, cur.stride(0), nsig,
-                                             stats.data_ptr(), ws.data_ptr(), stream), 'xcb_stats')
+            s.ramps = _taper_ramps(s.npts, s.fs, **s.taper) if s.taper is not None else None
+            s.f = None
             if s.sos:
                 sos = np.vstack(s.sos)
                 f = _lib.xcb_sos()
@@ -385,35 +352,100 @@ class PreprocessProgram:
                     a0 = sec[3]
                     for m, v in enumerate((sec[0] / a0, sec[1] / a0, sec[2] / a0, sec[4] / a0, sec[5] / a0)):
                         f.coef[k][m] = float(v)
-                P, PG = _carry_matrices(sos, _SCAN_CHUNK)
-                keep += [P, PG]
-                f.carry = P.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
-                f.carry_group = PG.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+                s.P, s.PG = _carry_matrices(sos, _SCAN_CHUNK)
+                s.f = f
+        self._designed = True
+        self._dev_cache = {}
+
+    def _device_buffers(self, torch, lib, dev, nsig):
+        """Ramps, statistics and scan workspaces on `dev` for `nsig` traces (cached)."""
+        key = (str(dev), nsig)
+        if key in self._dev_cache:
+            return self._dev_cache[key]
+        bufs = []
+        for st in self.steps:
+            if st[0] != 'stage':
+                bufs.append(None)
+                continue
+            s = st[1]
+            b = {}
+            if s.ramps is not None:
+                b['left'] = torch.from_numpy(s.ramps[0]).to(dev)
+                b['right'] = torch.from_numpy(s.ramps[1]).to(dev)
+            if s.detrend:
                 nb = ctypes.c_size_t()
-                _lib.check(lib.xcb_sosfilt_workspace_bytes(n, nsig, ctypes.byref(f), ctypes.byref(nb)),
+                _lib.check(lib.xcb_stats_workspace_bytes(s.npts, nsig, ctypes.byref(nb)), 'xcb_stats_workspace_bytes')
+                b['stats_ws'] = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                b['stats'] = torch.empty((nsig, 4), dtype=torch.float64, device=dev)
+            if s.f is not None:
+                nb = ctypes.c_size_t()
+                _lib.check(lib.xcb_sosfilt_workspace_bytes(s.npts, nsig, ctypes.byref(s.f), ctypes.byref(nb)),
                            'xcb_sosfilt_workspace_bytes')
-                ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                b['sos_ws'] = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+                b['P'] = torch.from_numpy(s.P).to(dev)
+                b['PG'] = torch.from_numpy(s.PG).to(dev)
+            bufs.append(b)
+        self._dev_cache[key] = bufs
+        return bufs
+
+    def run(self, x, out_dtype=None):
+        """x: CUDA tensor (n_signals, npts) float32/float64, last dim contiguous.
+        Returns a new tensor (n_signals, npts_out).  All launches go to the
+        current stream; the cached workspaces make one program usable from one
+        stream at a time."""
+        import torch
+        lib = _lib.load()
+        if x.dim() != 2 or x.shape[1] != self.npts_in or x.stride(1) != 1 or not x.is_cuda:
+            raise ValueError(f'x must be a CUDA tensor (n_signals, {self.npts_in})')
+        out_dtype = out_dtype or x.dtype
+        xcb = {torch.float32: _lib.XCB_F32, torch.float64: _lib.XCB_F64}
+        dev = x.device
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        nsig = x.shape[0]
+        self._host_design()
+        bufs = self._device_buffers(torch, lib, dev, nsig)
+        cur = x
+        n_stage = sum(1 for s in self.steps if s[0] == 'stage')
+        i_stage = 0
+        for st, b in zip(self.steps, bufs):
+            if st[0] == 'trim':
+                cur = cur[:, st[1]:st[1] + st[2]]
+                continue
+            s = st[1]
+            i_stage += 1
+            n = s.npts
+            assert cur.shape[1] == n
+            dt_out = out_dtype if i_stage == n_stage else torch.float64
+            pw = _lib.xcb_pointwise()
+            stats_ptr = None
+            if s.has_pointwise:
+                pw.detrend = s.detrend
+                if s.ramps is not None:
+                    pw.taper_left, pw.taper_right = len(s.ramps[0]), len(s.ramps[1])
+                    pw.ramp_left, pw.ramp_right = b['left'].data_ptr(), b['right'].data_ptr()
+                if s.detrend:
+                    stats_ptr = b['stats'].data_ptr()
+                    _lib.check(lib.xcb_stats(xcb[cur.dtype], cur.data_ptr(), n, cur.stride(0), nsig, stats_ptr,
+                                             b['stats_ws'].data_ptr(), stream), 'xcb_stats')
+            if s.f is not None:
                 n_out = (n + s.decimate - 1) // s.decimate
                 y = torch.empty((nsig, n_out), dtype=dt_out, device=dev)
-                keep += [ws, f]
+                s.f.carry = ctypes.cast(b['P'].data_ptr(), ctypes.POINTER(ctypes.c_double))
+                s.f.carry_group = ctypes.cast(b['PG'].data_ptr(), ctypes.POINTER(ctypes.c_double))
                 _lib.check(lib.xcb_sosfilt(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), xcb[y.dtype], y.data_ptr(),
-                                           y.stride(0), n, nsig, ctypes.byref(f),
-                                           ctypes.byref(pw) if s.has_pointwise else None,
-                                           stats.data_ptr() if stats is not None else None, ws.data_ptr(), stream),
-                           'xcb_sosfilt')
+                                           y.stride(0), n, nsig, ctypes.byref(s.f),
+                                           ctypes.byref(pw) if s.has_pointwise else None, stats_ptr,
+                                           b['sos_ws'].data_ptr(), stream), 'xcb_sosfilt')
             else:
                 y = cur
                 if s.has_pointwise:
                     y = torch.empty((nsig, n), dtype=dt_out, device=dev)
                     _lib.check(lib.xcb_pointwise_apply(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), xcb[y.dtype],
                                                        y.data_ptr(), y.stride(0), n, nsig, ctypes.byref(pw),
-                                                       stats.data_ptr() if stats is not None else None, stream),
-                               'xcb_pointwise_apply')
+                                                       stats_ptr, stream), 'xcb_pointwise_apply')
                 if s.decimate != 1:     # decimate(no_filter=True): data[::factor]
                     y = y[:, ::s.decimate]
             cur = y
-        # (the carry matrices are pageable host memory: cudaMemcpyAsync returns once they are staged,
-        #  and torch's allocator is stream ordered, so `keep` may be dropped with the launches still queued)
         if cur is x:
             cur = x.clone()
         if cur.dtype != out_dtype:
