@@ -68,7 +68,9 @@ class CorrelationPlan:
         if not torch.cuda.is_available():
             raise _lib.XcbError("xcorr_b200 needs a CUDA device; there is no CPU fallback")
         self._lib = _lib.load()
-        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.xdtype = _xcb_dtype(dtype)
         self.dtype = _TORCH_DTYPE[self.xdtype]
         self.pairs = [(int(i), int(j)) for i, j in pairs]
