@@ -13,6 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import xcorr_b200 as xb  # noqa: E402
@@ -41,7 +42,9 @@ def timed(fn, steps, warmup):
 
 
 def b_alg(N, P, n, L, K, b, n_raw=0):
-    """SURVEY 8d bytes per pair-window: [N(F + R) + P I] / P."""
+    """SURVEY 8d bytes per pair-window: [N(F + R) + P I] / P, with the problem's
+    full-window transform length (not the plan's, which may use blocks)."""
+    L = 2 * int(np.prod(xb._lib.choose_transform(n)))
     F = n * b + 3 * L * b
     R = 2 * n_raw * b + n * b if n_raw else 0
     return (N * (F + R) + P * (4 * L * b + K * b)) / P
@@ -59,7 +62,7 @@ def run(name, steps, warmup):
         ms = timed(lambda: plan(x), steps, warmup)
         b = 8 if dt == torch.float64 else 4
         out.update(desc="1 pair, 24h@50Hz, lags (0, 9h)", dtype=str(dt), ms_per_step=ms, unit="pair-days/s",
-                   value=1 / (ms * 1e-3), passes=plan.dims,
+                   value=1 / (ms * 1e-3), passes=plan.dims, blocks=plan.n_blocks,
                    alg_bytes_per_unit=b_alg(2, 1, n, plan.fft_len, 1_620_000, b))
     elif name in ("cfg2", "cfg2_f64"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
@@ -77,7 +80,7 @@ def run(name, steps, warmup):
         ms_pre = timed(lambda: prog.run(raw), steps, warmup)
         out.update(desc="5 receivers / 10 pairs, 24h@250Hz raw -> detrend, taper, 3-12 Hz bandpass, decimate 5 -> cc at 50 Hz, lags (0, 9h)",
                    dtype=str(dt), ms_per_step=ms, ms_preprocess=ms_pre, unit="pair-days/s", value=len(pairs) / (ms * 1e-3),
-                   passes=plan.dims, alg_bytes_per_unit=b_alg(R, len(pairs), n, plan.fft_len, 1_620_000, b, n_raw))
+                   passes=plan.dims, blocks=plan.n_blocks, alg_bytes_per_unit=b_alg(R, len(pairs), n, plan.fft_len, 1_620_000, b, n_raw))
     elif name in ("cfg3_f64", "cfg3_full", "cfg3"):
         dt = torch.float64 if name == "cfg3_f64" else torch.float32
         b = 8 if dt == torch.float64 else 4
@@ -94,7 +97,7 @@ def run(name, steps, warmup):
             plan.correlate(out=ccf)
         ms = timed(step, steps, warmup)
         out.update(desc=f"16 receivers / 120 pairs, 24h@250Hz, K={K}", dtype=str(dt), ms_per_step=ms,
-                   unit="pair-days/s", value=len(pairs) / (ms * 1e-3), passes=plan.dims,
+                   unit="pair-days/s", value=len(pairs) / (ms * 1e-3), passes=plan.dims, blocks=plan.n_blocks,
                    alg_bytes_per_unit=b_alg(R, len(pairs), n, plan.fft_len, K, b))
     elif name in ("cfg4", "cfg4_f64"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
@@ -116,7 +119,7 @@ def run(name, steps, warmup):
         alg = (R * (n * b + 3 * L * b) + len(pairs) * (2 * L * b + (2 * L * b + K * b) / W)) / len(pairs)
         out.update(desc=f"4 receivers / 6 pairs, {W} windows of 1h@250Hz per step, stacked on device (spectral stacking)",
                    dtype=str(dt), ms_per_step=ms, unit="pair-hours/s", value=len(pairs) * W / (ms * 1e-3),
-                   passes=plan.dims, alg_bytes_per_unit=alg)
+                   passes=plan.dims, blocks=plan.n_blocks, alg_bytes_per_unit=alg)
     else:
         raise SystemExit(f"unknown config {name}")
     out["step_roofline_frac"] = out["alg_bytes_per_unit"] * out["value"] / 1e9 / peak

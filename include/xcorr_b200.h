@@ -65,12 +65,16 @@ typedef struct xcb_desc {
   const int32_t* pairs;    /* host, [n_pairs][2] receiver indices (i, j): Rxy[k] = sum_m x_i[m+k] x_j[m] */
   int64_t lag_index_min;   /* lag.attrs['index_min'] (core/init.py:191-208, util/time.py:94-108) */
   int64_t lag_index_max;   /* exclusive; both 0 -> full 2n-1 lags */
-  int64_t max_work_bytes;  /* cap for the inverse-transform scratch; 0 -> 4 GiB */
+  int64_t max_work_bytes;  /* cap for the inverse-transform scratch; 0 -> 16 GiB */
+  int32_t n_blocks;        /* 0: automatic; 1: one transform of the whole window; >1 (with nd, dims, block_len): block mode,
+                            * kept lags must be non-negative (lag_index_min >= n-1), see DESIGN.md section 3 */
+  int32_t reserved;
+  int64_t block_len;       /* samples per block when n_blocks > 1 */
 } xcb_desc;
 
 typedef struct xcb_plan_info {
   int64_t n, fft_len;      /* L = 2M >= 2n-1 */
-  int64_t spectrum_elems;  /* M complex elements per signal in `spec` */
+  int64_t spectrum_elems;  /* complex elements per signal in `spec` (M, or 2*n_blocks*M in block mode) */
   int64_t n_lags;          /* K = lag_index_max - lag_index_min */
   int64_t n_signals;       /* n_receivers * n_windows */
   int64_t n_jobs;          /* inverse transforms per call: n_pairs * n_windows (n_pairs when stacking) */
@@ -79,6 +83,8 @@ typedef struct xcb_plan_info {
   int32_t nd;
   int32_t dims[4];
   int32_t dtype;
+  int32_t n_blocks;        /* 1 = classic */
+  int64_t block_len;
 } xcb_plan_info;
 
 XCB_API const char* xcb_strerror(int status);

@@ -40,11 +40,12 @@ def choose_dims(n):
 
 
 def emu_cc(x, pairs, dims=None, i0=None, i1=None, normalize=True, unbiased=False,
-           want_spec=False, n_stack=1):
+           want_spec=False, n_stack=1, n_blocks=1, block_len=0):
     """x: (S, n) float32/float64.  Returns (ccf[P, K], sumsq[S], spec or None)."""
     x = np.ascontiguousarray(x)
     S, n = x.shape
     dtype = {np.dtype(np.float32): 0, np.dtype(np.float64): 1}[x.dtype]
+    auto_dims = dims is None
     if dims is None:
         dims = choose_dims(n)
     M = int(np.prod(dims))
@@ -55,12 +56,15 @@ def emu_cc(x, pairs, dims=None, i0=None, i1=None, normalize=True, unbiased=False
     sumsq = np.zeros(S)
     spec = np.zeros((S, M), dtype=np.complex64 if dtype == 0 else np.complex128) if want_spec else None
     d = (ctypes.c_int * 4)(*(list(dims) + [0] * (4 - len(dims))))
-    rc = lib().emu_cc(dtype, ctypes.c_int64(n), d, len(dims), x.ctypes.data_as(ctypes.c_void_p),
+    nd = 0 if (auto_dims and n_blocks < 0) else len(dims)
+    rc = lib().emu_cc(dtype, ctypes.c_int64(n), d, nd, x.ctypes.data_as(ctypes.c_void_p),
                       ctypes.c_int64(x.strides[0] // x.itemsize), S,
                       pairs.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(pairs),
                       ctypes.c_int64(i0), ctypes.c_int64(i1), int(normalize), int(unbiased),
                       out.ctypes.data_as(ctypes.c_void_p),
                       sumsq.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                      spec.ctypes.data_as(ctypes.c_void_p) if want_spec else None, int(n_stack))
-    assert rc == 0, rc
+                      spec.ctypes.data_as(ctypes.c_void_p) if want_spec else None, int(n_stack),
+                      int(n_blocks), ctypes.c_int64(block_len))
+    assert rc >= 1, rc           # returns the number of blocks used
+    emu_cc.last_blocks = rc
     return out, sumsq, spec

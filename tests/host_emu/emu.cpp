@@ -53,51 +53,56 @@ template <class T> static bool run_pass(const PassParams<T>& p, bool row) {
 template <class T>
 static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_stride, int n_signals,
                     const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased,
-                    T* out, double* sumsq_out, T* spec_out, int n_stack) {
+                    T* out, double* sumsq_out, T* spec_out, int n_stack, int n_blocks, int64_t block_len) {
   PlanGeom g;
   int d[kMaxDims], k = nd;
-  if (nd == 0) { if (!plan_choose_dims(n, d, &k)) return -1; }
-  else for (int a = 0; a < nd; ++a) d[a] = dims[a];
-  if (!plan_geom_init(g, n, d, k)) return -2;
+  const int64_t K = i1 - i0;
+  if (n_blocks < 0) {          // automatic block planning, as xcb_plan_create does
+    n_blocks = 1;
+    int bd[kMaxDims], bnd = 0, nb = 0;
+    int64_t bl = 0;
+    if (nd == 0 && i0 >= n - 1 && plan_choose_blocks(n, K, n_signals, n_pairs, bd, &bnd, &nb, &bl)) {
+      n_blocks = nb; block_len = bl; k = bnd;
+      for (int a = 0; a < bnd; ++a) d[a] = bd[a];
+    }
+  }
+  if (n_blocks <= 1) {
+    if (nd == 0) { if (!plan_choose_dims(n, d, &k)) return -1; }
+    else for (int a = 0; a < nd; ++a) d[a] = dims[a];
+    if (!plan_geom_init(g, n, d, k)) return -2;
+  } else {
+    if (nd > 0) for (int a = 0; a < nd; ++a) d[a] = dims[a];
+    if (!plan_geom_init(g, n, d, k, n_blocks, block_len, i0 - (n - 1), K)) return -2;
+  }
   HostTables<T> ht;
   build_tables(g, ht);
   DevTables<T> tb;
   tb.hi = ht.hi.data(); tb.lo = ht.lo.data();
   for (int a = 0; a < g.nd; ++a) tb.inner[a] = ht.inner[a].data();
 
-  std::vector<cx<T>> spec((size_t)n_signals * g.M);
-  std::vector<double> sumsq(n_signals, 0.0);
-  {
-    PassParams<T> p0 = make_forward_pass<T>(g, tb, 0, x, x_stride, spec.data(), g.M, n_signals, nullptr);
-    std::vector<double> partial((size_t)n_signals * p0.tiles_per_batch, 0.0);
-    for (int a = 0; a < g.nd; ++a) {
-      PassParams<T> p = make_forward_pass<T>(g, tb, a, x, x_stride, spec.data(), g.M, n_signals, partial.data());
-      if (!run_pass(p, a == g.nd - 1)) return -3;
-    }
+  auto runner = [&](const PassParams<T>& p, bool row, int) { return run_pass(p, row); };
+  const int per = spectra_per_signal(g);
+  const int64_t t0 = pass0_tiles(g, tile_cols<T>());
+  std::vector<cx<T>> spec((size_t)n_signals * per * g.M);
+  std::vector<double> partial((size_t)g.n_blocks * n_signals * t0, 0.0);
+  if (!run_forward<T>(g, tb, x, x_stride, n_signals, spec.data(), partial.data(), runner)) return -3;
+  std::vector<double> sumsq(n_signals, 0.0), rnorm(n_signals);
+  for (int b = 0; b < g.n_blocks; ++b)
     for (int s = 0; s < n_signals; ++s)
-      for (int64_t t = 0; t < p0.tiles_per_batch; ++t) sumsq[s] += partial[(size_t)s * p0.tiles_per_batch + t];
-  }
-  if (sumsq_out) memcpy(sumsq_out, sumsq.data(), sizeof(double) * n_signals);
-  if (spec_out) memcpy(spec_out, spec.data(), sizeof(cx<T>) * spec.size());
-
-  const int64_t K = i1 - i0;
-  std::vector<Job> jobs(n_pairs);
-  for (int q = 0; q < n_pairs; ++q) {
-    // signals are [receiver][window] when stacking (n_stack windows per receiver)
-    jobs[q].sig_i = pairs[2 * q] * n_stack; jobs[q].sig_j = pairs[2 * q + 1] * n_stack;
-    jobs[q].spec_i = (int64_t)jobs[q].sig_i * g.M; jobs[q].spec_j = (int64_t)jobs[q].sig_j * g.M;
-    jobs[q].out_off = (int64_t)q * K;
-  }
-  std::vector<cx<T>> work((size_t)n_pairs * g.M);
-  std::vector<double> rnorm(n_signals);
+      for (int64_t t = 0; t < t0; ++t) sumsq[s] += partial[((size_t)b * n_signals + s) * t0 + t];
   for (int s = 0; s < n_signals; ++s) rnorm[s] = 1.0 / sqrt(sumsq[s]);
+  if (sumsq_out) memcpy(sumsq_out, sumsq.data(), sizeof(double) * n_signals);
+  if (spec_out && per == 1) memcpy(spec_out, spec.data(), sizeof(cx<T>) * spec.size());
+
+  std::vector<Job> jobs(n_pairs);
+  // signals are [receiver][window] when stacking (n_stack windows per receiver)
+  for (int q = 0; q < n_pairs; ++q)
+    jobs[q] = make_job(g, (int64_t)pairs[2 * q] * n_stack, (int64_t)pairs[2 * q + 1] * n_stack, (int64_t)q * K);
+  std::vector<cx<T>> work((size_t)n_pairs * g.M);
   CorrFlags f; f.i0 = i0; f.i1 = i1; f.normalize = normalize; f.unbiased = unbiased; f.accumulate = 0;
   f.n_stack = n_stack; f.stack_sig_stride = 1; f.stack_spec_stride = g.M;
-  for (int a = g.nd - 1; a >= 0; --a) {
-    PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec.data(), rnorm.data(), jobs.data(), n_pairs, work.data(), out, f);
-    if (!run_pass(p, a == g.nd - 1)) return -4;
-  }
-  return 0;
+  if (!run_inverse<T>(g, tb, spec.data(), rnorm.data(), jobs.data(), n_pairs, work.data(), out, f, runner)) return -4;
+  return g.n_blocks;
 }
 
 extern "C" {
@@ -107,12 +112,12 @@ int emu_choose_dims(int64_t n, int* dims, int* nd) { return plan_choose_dims(n, 
 // dtype: 0 = f32, 1 = f64.  x: [n_signals][x_stride]; pairs: [n_pairs][2]; out: [n_pairs][i1-i0]
 int emu_cc(int dtype, int64_t n, const int* dims, int nd, const void* x, int64_t x_stride, int n_signals,
            const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased, void* out,
-           double* sumsq_out, void* spec_out, int n_stack) {
+           double* sumsq_out, void* spec_out, int n_stack, int n_blocks, int64_t block_len) {
   if (n_stack < 1) n_stack = 1;
   if (dtype == 0)
     return emu_cc_t<float>(n, dims, nd, (const float*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
-                           unbiased, (float*)out, sumsq_out, (float*)spec_out, n_stack);
+                           unbiased, (float*)out, sumsq_out, (float*)spec_out, n_stack, n_blocks, block_len);
   return emu_cc_t<double>(n, dims, nd, (const double*)x, x_stride, n_signals, pairs, n_pairs, i0, i1, normalize,
-                          unbiased, (double*)out, sumsq_out, (double*)spec_out, n_stack);
+                          unbiased, (double*)out, sumsq_out, (double*)spec_out, n_stack, n_blocks, block_len);
 }
 }

@@ -220,3 +220,44 @@ def test_day_at_250hz_full_size(xb, orc):
     mix = plan_n(x2).double()
     lin = 2.0 * base[0] + base[1]
     assert float((mix[0] - lin).abs().max()) <= 1e-5 * float(lin.abs().max())
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_block_mode_equals_classic_transform(xb, orc, dtype):
+    """Cropped non-negative lags: the planner cuts the second signal into blocks
+    and uses shorter transforms; results must equal the
+    single full-length transform and the oracle."""
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    n, R, W = 120_000, 6, 2
+    pairs = xb.all_pairs(R)
+    rec = np.stack([orc.synthetic_receivers(R, n, seed=400 + w, delay=61) for w in range(W)], axis=1)
+    x = torch.from_numpy(rec.astype(dtype)).cuda()
+    for lag0, K in ((0, 45_000), (1_000, 30_000)):
+        i0 = n - 1 + lag0
+        auto = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + K)
+        classic = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + K, n_blocks=1)
+        assert auto.n_blocks >= 2 and classic.n_blocks == 1
+        assert 2 * int(np.prod(auto.dims)) < 2 * n            # transforms shorter than the window pair
+        a, c = auto(x), classic(x)
+        idx_a, _ = auto.argmax(a)
+        idx_c, _ = classic.argmax(c)
+        assert torch.equal(idx_a, idx_c)
+        a, c = a.cpu().numpy(), c.cpu().numpy()
+        tol = TOL[np.dtype(dtype)]
+        for q, (i, j) in enumerate(pairs):
+            for w in range(W):
+                ref = orc.cc(rec[i, w], rec[j, w], unbiased=False)
+                peak = np.max(np.abs(ref))
+                assert np.max(np.abs(a[q, w] - ref[i0:i0 + K])) <= tol * peak
+                assert np.max(np.abs(c[q, w] - ref[i0:i0 + K])) <= tol * peak
+        assert np.allclose(auto.sumsq.cpu().numpy(), classic.sumsq.cpu().numpy(), rtol=1e-6)
+    # forced geometry + unbiased weights
+    forced = xb.CorrelationPlan(n, R, pairs[:3], n_windows=W, dtype=tdt, index_min=n - 1, index_max=n - 1 + 20_000,
+                                dims=(64, 64, 16 * 4) if False else (200, 200), n_blocks=2, block_len=60_000, unbiased=True)
+    got = forced(x).cpu().numpy()
+    for q, (i, j) in enumerate(pairs[:3]):
+        ref = orc.cc(rec[i, 1], rec[j, 1], unbiased=True)
+        assert np.max(np.abs(got[q, 1] - ref[n - 1:n - 1 + 20_000])) <= 20 * TOL[np.dtype(dtype)] * np.max(np.abs(ref[n - 1:n - 1 + 20_000]))
+    with pytest.raises(Exception):        # negative lags cannot use blocks
+        xb.CorrelationPlan(n, R, pairs, dtype=tdt, index_min=0, index_max=1000, dims=(200, 200), n_blocks=2, block_len=60_000)

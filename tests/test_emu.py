@@ -114,3 +114,47 @@ def test_spectral_stacking_sums_windows():
         ref = sum(orc.cc(rec[i, w], rec[j, w], unbiased=False) for w in range(W))
         assert np.max(np.abs(out[q] - ref)) <= 1e-13 * np.max(np.abs(ref))
         assert np.argmax(out[q]) == np.argmax(ref)
+
+
+@pytest.mark.parametrize("B,dims,n,K,lag0", [
+    (2, (64, 64), 6000, 1500, 0),          # F = 8192 >= 3000 + 1500
+    (3, (64, 80), 12000, 5000, 0),         # F = 10240 >= 4000 + 5000
+    (2, (64, 64, 64), 400_000, 100_000, 0),
+    (2, (64, 64), 6000, 1500, 700),        # first kept lag > 0
+    (4, (100,), 500, 60, 0),               # single-pass transform, F = 200 >= 125 + 60
+])
+def test_block_mode_matches_full_transform(B, dims, n, K, lag0):
+    """Cropped non-negative lags through B blocks of the second signal and
+    transforms of length ~n/B + K instead of 2n: same lags, same values."""
+    x = orc.synthetic_receivers(3, n, seed=n + B, delay=41)
+    pairs = [(0, 1), (2, 1), (0, 2)]
+    i0 = n - 1 + lag0
+    lb = -(-n // B)
+    out, ss, _ = emu_cc(x, pairs, dims=dims, i0=i0, i1=i0 + K, n_blocks=B, block_len=lb)
+    assert emu_cc.last_blocks == B
+    assert np.allclose(ss, np.sum(x ** 2, axis=1), rtol=1e-13)
+    for q, (i, j) in enumerate(pairs):
+        ref = orc.cc(x[i], x[j], unbiased=False)
+        peak = np.max(np.abs(ref))
+        assert np.max(np.abs(out[q] - ref[i0:i0 + K])) <= 1e-13 * peak, (q,)
+    # unbiased weights use the full window length
+    out_u, _, _ = emu_cc(x, pairs[:1], dims=dims, i0=i0, i1=i0 + K, n_blocks=B, block_len=lb, unbiased=True)
+    ref_u = orc.cc(x[0], x[1], unbiased=True)
+    assert np.max(np.abs(out_u[0] - ref_u[i0:i0 + K])) <= 1e-12 * np.max(np.abs(ref_u[i0:i0 + K]))
+
+
+def test_block_planner_picks_blocks_for_cropped_day():
+    # with many pairs per receiver the inverse transforms dominate and blocks pay off
+    R = 6
+    x = orc.synthetic_receivers(R, 40_000, seed=3, delay=41).astype(np.float32)
+    pairs = [(i, j) for i in range(R) for j in range(i + 1, R)]
+    out, _, _ = emu_cc(x, pairs, dims=None, i0=39_999, i1=39_999 + 15_000, n_blocks=-1)
+    assert emu_cc.last_blocks >= 2
+    for q in (0, 7, 14):
+        i, j = pairs[q]
+        ref = orc.cc(x[i].astype(np.float64), x[j].astype(np.float64), unbiased=False)
+        assert np.max(np.abs(out[q] - ref[39_999:39_999 + 15_000])) <= 1e-5 * np.max(np.abs(ref))
+        assert np.argmax(out[q]) == 41 * (j - i)
+    # a single pair of two receivers: the classic transform stays cheaper
+    emu_cc(x[:2], [(0, 1)], dims=None, i0=39_999, i1=39_999 + 15_000, n_blocks=-1)
+    assert emu_cc.last_blocks == 1

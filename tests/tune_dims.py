@@ -23,13 +23,32 @@ for combo in itertools.combinations_with_replacement(MENU, 3):
             cands.add(perm)
 if os.environ.get("XCB_DIMS"):
     cands = {tuple(int(v) for v in d.split(",")) for d in os.environ["XCB_DIMS"].split(";")}
+if os.environ.get("XCB_MRANGE"):                 # all factorisations with product in [lo, hi], row axis <= 256
+    lo, hi = (float(v) for v in os.environ["XCB_MRANGE"].split(","))
+    cands = set()
+    for combo in itertools.combinations_with_replacement(MENU, 3):
+        m = combo[0] * combo[1] * combo[2]
+        if lo <= m <= hi:
+            for perm in set(itertools.permutations(combo)):
+                if perm[2] <= 256 and perm[2] % 16 == 0 and perm[0] >= perm[1]:
+                    cands.add(perm)
+NB = int(os.environ.get("XCB_NBLOCKS", 1))       # block mode: dims give the short transform
+LB = int(os.environ.get("XCB_BLOCK_LEN", 0))
+KL = int(os.environ.get("XCB_LAGS", 3 * n // 8))
 dev = torch.device("cuda:0")
 x = make_inputs(torch, R, n, dev, dtype, seed=1)
 pairs = xb.all_pairs(R)[:P]
 rows = []
 for dims in sorted(cands):
     try:
-        plan = xb.CorrelationPlan(n, R, pairs, dtype=dtype, index_min=n - 1, index_max=n - 1 + 3 * n // 8, dims=dims)
+        lb = LB
+        if NB > 1 and not lb:
+            lb = -(-n // NB)
+            row = 2 * dims[1] * dims[2]
+            if n % row == 0 and -(-lb // row) * row + KL <= 2 * dims[0] * dims[1] * dims[2]:
+                lb = -(-lb // row) * row
+        plan = xb.CorrelationPlan(n, R, pairs, dtype=dtype, index_min=n - 1, index_max=n - 1 + KL, dims=dims,
+                                  n_blocks=NB, block_len=lb)
     except Exception as e:
         print(dims, "skip", e)
         continue
@@ -41,11 +60,11 @@ for dims in sorted(cands):
         ccf = plan(x)
     torch.cuda.synchronize()
     k = plan.profile_read()
-    fwd = sum(ms / c for name, ms, c in k if name.startswith("fwd"))
-    inv = sum(ms / c for name, ms, c in k if name.startswith("inv"))
+    fwd = sum(ms for name, ms, c in k if name.startswith("fwd")) / 3      # totals per iteration
+    inv = sum(ms for name, ms, c in k if name.startswith("inv")) / 3
     idx, _ = plan.argmax(ccf)
     ok = idx[0, 0].item() == 137
-    rows.append((fwd + inv * 120 / P, dims, fwd, inv, ok, [round(ms / c, 3) for _, ms, c in k]))
+    rows.append((fwd + inv * 120 / P, dims, fwd, inv, ok, [round(ms / 3, 3) for _, ms, c in k]))
     del plan, ccf
     torch.cuda.empty_cache()
 rows.sort()

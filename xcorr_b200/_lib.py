@@ -36,6 +36,9 @@ class xcb_desc(ctypes.Structure):
         ("lag_index_min", ctypes.c_int64),
         ("lag_index_max", ctypes.c_int64),
         ("max_work_bytes", ctypes.c_int64),
+        ("n_blocks", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("block_len", ctypes.c_int64),
     ]
 
 
@@ -52,6 +55,8 @@ class xcb_plan_info(ctypes.Structure):
         ("nd", ctypes.c_int32),
         ("dims", ctypes.c_int32 * 4),
         ("dtype", ctypes.c_int32),
+        ("n_blocks", ctypes.c_int32),
+        ("block_len", ctypes.c_int64),
     ]
 
 

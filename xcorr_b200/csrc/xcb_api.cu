@@ -117,11 +117,14 @@ extern "C" int xcb_choose_transform(int64_t n, int32_t dims[4], int32_t* nd) {
 // ---------------------------------------------------------------------------
 // sumsq[s] = sum of the per-tile partial sums, fixed order -> bit-reproducible
 __global__ void __launch_bounds__(256) xcb_sumsq_finish(const double* __restrict__ partial, int64_t tiles,
+                                                        int n_blocks, int64_t block_stride,
                                                         double* __restrict__ sumsq) {
   __shared__ double red[256];
-  const double* p = partial + (int64_t)blockIdx.x * tiles;
   double a = 0.0;
-  for (int64_t i = threadIdx.x; i < tiles; i += 256) a += p[i];
+  for (int b = 0; b < n_blocks; ++b) {       // block mode: the blocks partition the signal
+    const double* p = partial + b * block_stride + (int64_t)blockIdx.x * tiles;
+    for (int64_t i = threadIdx.x; i < tiles; i += 256) a += p[i];
+  }
   red[threadIdx.x] = a;
   __syncthreads();
   block_sumsq<256>(sumsq + blockIdx.x, red, threadIdx.x);
@@ -280,19 +283,44 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   for (int q = 0; q < 2 * d->n_pairs; ++q)
     if (pl->pairs[q] < 0 || pl->pairs[q] >= d->n_receivers) { delete pl; return XCB_ERR_ARG; }
 
-  int dims[kMaxDims] = {0, 0, 0, 0}, nd = d->nd;
-  if (nd == 0) {
-    if (!plan_choose_dims(d->n, dims, &nd)) { delete pl; return XCB_ERR_SIZE; }
-  } else {
-    for (int a = 0; a < nd; ++a) dims[a] = d->dims[a];
-  }
-  if (!plan_geom_init(pl->g, d->n, dims, nd)) { delete pl; return XCB_ERR_SIZE; }
-
   pl->i0 = d->lag_index_min;
   pl->i1 = d->lag_index_max;
   if (pl->i0 == 0 && pl->i1 == 0) pl->i1 = 2 * d->n - 1;
   if (pl->i0 < 0 || pl->i1 > 2 * d->n - 1 || pl->i0 >= pl->i1) { delete pl; return XCB_ERR_ARG; }
   pl->K = pl->i1 - pl->i0;
+
+  // transform: classic single transform of the window, or -- for cropped
+  // non-negative lags -- blocks with a shorter transform (xcb_plan.h, PlanGeom)
+  int dims[kMaxDims] = {0, 0, 0, 0}, nd = d->nd, n_blocks = d->n_blocks;
+  int64_t block_len = d->block_len;
+  const bool blocks_possible = pl->i0 >= d->n - 1 && !d->stack;
+  if (n_blocks > 1 && (!blocks_possible || nd == 0 || block_len < 1)) { delete pl; return XCB_ERR_ARG; }
+  if (n_blocks == 0) {
+    n_blocks = 1;
+    const char* env = getenv("XCB_BLOCKS");
+    if (nd == 0 && blocks_possible && !(env && env[0] == '0')) {
+      int bd[kMaxDims], bnd = 0, nb = 0;
+      int64_t bl = 0;
+      if (plan_choose_blocks(d->n, pl->K, d->n_receivers, d->n_pairs, bd, &bnd, &nb, &bl)) {
+        n_blocks = nb; block_len = bl; nd = bnd;
+        for (int a = 0; a < bnd; ++a) dims[a] = bd[a];
+      }
+    }
+  }
+  if (n_blocks <= 1) {
+    if (nd == 0) {
+      if (!plan_choose_dims(d->n, dims, &nd)) { delete pl; return XCB_ERR_SIZE; }
+    } else {
+      for (int a = 0; a < nd; ++a) dims[a] = d->dims[a];
+    }
+    if (!plan_geom_init(pl->g, d->n, dims, nd)) { delete pl; return XCB_ERR_SIZE; }
+  } else {
+    if (d->nd > 0) for (int a = 0; a < nd; ++a) dims[a] = d->dims[a];
+    if (!plan_geom_init(pl->g, d->n, dims, nd, n_blocks, block_len, pl->i0 - (d->n - 1), pl->K)) {
+      delete pl;
+      return XCB_ERR_SIZE;
+    }
+  }
   pl->n_signals = (int64_t)d->n_receivers * d->n_windows;
   // stacking sums the cross-spectra over windows inside the pair-product pass: one job per pair
   pl->n_jobs = d->stack ? (int64_t)d->n_pairs : (int64_t)d->n_pairs * d->n_windows;
@@ -317,13 +345,9 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
     const int64_t nw = d->stack ? 1 : d->n_windows;
     for (int64_t w = 0; w < nw; ++w)
       for (int64_t q = 0; q < d->n_pairs; ++q) {
-        Job& j = jobs[(size_t)(w * d->n_pairs + q)];
         int64_t si = pl->pairs[2 * q] * rs + w * ws, sj = pl->pairs[2 * q + 1] * rs + w * ws;
-        j.sig_i = (int32_t)si;
-        j.sig_j = (int32_t)sj;
-        j.spec_i = si * pl->g.M;
-        j.spec_j = sj * pl->g.M;
-        j.out_off = d->stack ? q * pl->K : (q * d->n_windows + w) * pl->K;
+        jobs[(size_t)(w * d->n_pairs + q)] =
+            make_job(pl->g, si, sj, d->stack ? q * pl->K : (q * d->n_windows + w) * pl->K);
       }
     cudaError_t e = cudaMalloc(&pl->d_jobs, jobs.size() * sizeof(Job));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_jobs, jobs.data(), jobs.size() * sizeof(Job), cudaMemcpyHostToDevice);
@@ -332,12 +356,11 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
 
   // workspace: [sumsq partials][inverse scratch]
   const int C = pl->dtype == XCB_F32 ? tile_cols<float>() : tile_cols<double>();
-  if (nd > 1) pl->tiles0 = (pl->g.M / pl->g.S[0]) * ((pl->g.S[1] + C - 1) / C);
-  else pl->tiles0 = (pl->g.M / dims[0] + C - 1) / C;
-  pl->partial_bytes = align_up((size_t)pl->n_signals * pl->tiles0 * sizeof(double), 256);
+  pl->tiles0 = pass0_tiles(pl->g, C);
+  pl->partial_bytes = align_up((size_t)pl->g.n_blocks * pl->n_signals * pl->tiles0 * sizeof(double), 256);
   pl->rnorm_bytes = align_up((size_t)pl->n_signals * sizeof(double), 256);
   const size_t per_job = (size_t)pl->g.M * (pl->dtype == XCB_F32 ? 8 : 16);
-  size_t cap = d->max_work_bytes > 0 ? (size_t)d->max_work_bytes : ((size_t)4 << 30);
+  size_t cap = d->max_work_bytes > 0 ? (size_t)d->max_work_bytes : ((size_t)16 << 30);
   int64_t fl = (int64_t)(cap / per_job);
   if (fl < 1) fl = 1;
   if (fl > pl->n_jobs) fl = pl->n_jobs > 0 ? pl->n_jobs : 1;
@@ -352,7 +375,9 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
   memset(info, 0, sizeof(*info));
   info->n = pl->g.n;
   info->fft_len = pl->g.L;
-  info->spectrum_elems = pl->g.M;
+  info->spectrum_elems = pl->g.M * spectra_per_signal(pl->g);
+  info->n_blocks = pl->g.n_blocks;
+  info->block_len = pl->g.block_len;
   info->n_lags = pl->K;
   info->n_signals = pl->n_signals;
   info->n_jobs = pl->n_jobs;
@@ -367,26 +392,37 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
 // ---------------------------------------------------------------------------
 // forward / correlate
 // ---------------------------------------------------------------------------
+// runs one pass on the device (the `run` callback of run_forward / run_inverse)
+template <class T> struct DeviceRunner {
+  const xcb_plan* pl;
+  cudaStream_t st;
+  int err = 0;        // cudaError_t of a failed launch, or -1 for an oversized grid
+  bool operator()(const PassParams<T>& p, bool row, int kind) {
+    const int a = kind % pl->g.nd;
+    const int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
+    if (nblocks >= 2147483647LL) { err = -1; return false; }
+    int e;
+    {
+      LaunchTimer tm(pl, kind, st);
+      e = row ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
+    }
+    if (e) { err = e; return false; }
+    return true;
+  }
+};
+
 template <class T>
 static int forward_t(const xcb_plan* pl, const void* x, int64_t x_stride, void* spec, double* sumsq, void* ws,
                      cudaStream_t st) {
   DevTables<T> tb = dev_tables<T>(pl);
   const PlanGeom& g = pl->g;
   double* partial = static_cast<double*>(ws);
-  // launches are split so that a grid never exceeds 2^31-1 CTAs
-  for (int a = 0; a < g.nd; ++a) {
-    PassParams<T> p = make_forward_pass<T>(g, tb, a, static_cast<const T*>(x), x_stride, static_cast<cx<T>*>(spec),
-                                           g.M, (int)pl->n_signals, a == 0 ? partial : nullptr);
-    int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
-    if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
-    int e;
-    {
-      LaunchTimer tm(pl, a, st);
-      e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
-    }
-    if (e) return cuda_fail((cudaError_t)e, "forward pass launch");
-  }
-  xcb_sumsq_finish<<<(unsigned)pl->n_signals, 256, 0, st>>>(partial, pl->tiles0, sumsq);
+  DeviceRunner<T> run{pl, st};
+  if (!run_forward<T>(g, tb, static_cast<const T*>(x), x_stride, (int)pl->n_signals, static_cast<cx<T>*>(spec),
+                      partial, run))
+    return run.err < 0 ? XCB_ERR_UNSUPPORTED : cuda_fail((cudaError_t)run.err, "forward pass launch");
+  xcb_sumsq_finish<<<(unsigned)pl->n_signals, 256, 0, st>>>(partial, pl->tiles0, g.n_blocks,
+                                                            pl->n_signals * pl->tiles0, sumsq);
   XCB_CUDA(cudaGetLastError());
   return XCB_OK;
 }
@@ -419,20 +455,12 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
     f.stack_sig_stride = (int)pl->win_stride;
     f.stack_spec_stride = pl->win_stride * g.M;
   }
+  DeviceRunner<T> run{pl, st};
   for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
     int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
-    for (int a = g.nd - 1; a >= 0; --a) {
-      PassParams<T> p = make_inverse_pass<T>(g, tb, a, static_cast<const cx<T>*>(spec), rnorm, pl->d_jobs + j0, nj,
-                                             work, static_cast<T*>(ccf), f);
-      int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
-      if (nblocks >= 2147483647LL) return XCB_ERR_UNSUPPORTED;
-      int e;
-      {
-        LaunchTimer tm(pl, g.nd + a, st);
-        e = (a == g.nd - 1) ? pl->launch[a]->row(&p, nblocks, st) : pl->launch[a]->col(&p, nblocks, st);
-      }
-      if (e) return cuda_fail((cudaError_t)e, "inverse pass launch");
-    }
+    if (!run_inverse<T>(g, tb, static_cast<const cx<T>*>(spec), rnorm, pl->d_jobs + j0, nj, work,
+                        static_cast<T*>(ccf), f, run))
+      return run.err < 0 ? XCB_ERR_UNSUPPORTED : cuda_fail((cudaError_t)run.err, "inverse pass launch");
   }
   return XCB_OK;
 }

@@ -143,8 +143,9 @@ template <class T> bool bulk_eligible(const PassParams<T>& p) {
 template <class T, int R1, int R2> int launch_row(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
   using K = RowBulk<T, R1, R2>;
-  const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+  PassParams<T> p = *static_cast<const PassParams<T>*>(params);
   if (K::kRowsAligned && bulk_eligible(p)) {
+    p.tile_major = 0;        // the persistent variant walks tiles job-major
     static int resident = 0;
     if (!resident) resident = resident_ctas((const void*)xcb_row_pass_bulk<T, R1, R2>, K::THREADS, K::SMEM);
     int64_t grid = nblocks < resident ? nblocks : resident;

@@ -95,6 +95,12 @@ template <class T> struct PassParams {
   // last inverse column pass: output rows k (element m = k*inner + col) that
   // can hold a kept lag: [keep_lo[0], keep_hi[0]) U [keep_lo[1], keep_hi[1])
   int32_t keep_lo[2], keep_hi[2];
+  // block mode: circular lag l of the (short) transform IS kept lag l (output index l)
+  int32_t epi_direct;
+  // row pass: 1 = consecutive CTAs take the SAME tile of consecutive jobs (tile
+  // major).  For the pair product all pairs of a frequency tile then run
+  // together and the spectra rows they share are served by L2 instead of HBM.
+  int32_t tile_major;
 };
 
 template <class T, int R1_, int R2_> struct Cfg {
@@ -158,11 +164,16 @@ template <class T> XCB_HD void epilogue_store(const PassParams<T>& p, T* outp, u
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint32_t l = 2u * m + (uint32_t)h;
-    uint32_t i;
-    if (l < n) i = l + (n - 1u);
-    else if (l > L - n) i = l - (L - n + 1u);
-    else continue;
-    uint32_t o = i - i0;            // wraps to a huge value when i < i0
+    uint32_t i, o;
+    if (p.epi_direct) {
+      o = l;
+      i = l + i0;
+    } else {
+      if (l < n) i = l + (n - 1u);
+      else if (l > L - n) i = l - (L - n + 1u);
+      else continue;
+      o = i - i0;                   // wraps to a huge value when i < i0
+    }
     if (o >= K) continue;
     T val = (h ? im : re) * p.escale;
     if (p.unbiased) {
@@ -350,6 +361,11 @@ template <class T, int R1, int R2> struct RowPass {
     return k;
   }
 
+  static XCB_HD void decode(const PassParams<T>& p, int64_t bid, int64_t& batch, int64_t& tile) {
+    if (p.tile_major) { tile = bid / p.n_batch; batch = bid - tile * p.n_batch; }
+    else { batch = bid / p.tiles_per_batch; tile = bid - batch * p.tiles_per_batch; }
+  }
+
   // column c of tile `tile` -> global row (pair product: rows ra / rb of pair slot c/2)
   static XCB_HD RowInfo<T> row_info(const PassParams<T>& p, int64_t tile, int c) {
     RowInfo<T> ri;
@@ -380,7 +396,9 @@ template <class T, int R1, int R2> struct RowPass {
   // phase 0: column -> row bookkeeping
   static XCB_HD void phase_info(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
     if (ctx.tid >= C) return;
-    info_ptr(smem_raw)[ctx.tid] = row_info(p, ctx.bid % p.tiles_per_batch, ctx.tid);
+    int64_t batch, tile;
+    decode(p, ctx.bid, batch, tile);
+    info_ptr(smem_raw)[ctx.tid] = row_info(p, tile, ctx.tid);
   }
 
   // pair product of one element pair (k, M-k): A, B at (row ra, e); Am, Bm at
@@ -414,7 +432,8 @@ template <class T, int R1, int R2> struct RowPass {
   static XCB_HD void phase_load(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
     cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
     const RowInfo<T>* info = info_ptr(smem_raw);
-    const int64_t batch = ctx.bid / p.tiles_per_batch;
+    int64_t batch, tile_;
+    decode(p, ctx.bid, batch, tile_);
     ctx.ss = 0.0;
     if (p.load_mode == RL_PROLOGUE) {
       // pair slot lp is owned by 2*TJ threads
@@ -534,7 +553,8 @@ template <class T, int R1, int R2> struct RowPass {
   }
   static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw, const RowInfo<T>* info) {
     const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
-    int64_t batch = ctx.bid / p.tiles_per_batch;
+    int64_t batch, tile_;
+    decode(p, ctx.bid, batch, tile_);
     if (p.store_mode == RS_EPI) {
       T* outp = p.ccf + p.jobs[batch].out_off;
       for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {

@@ -41,6 +41,13 @@ struct PlanGeom {
   int64_t region_lo[kMaxDims] = {0, 0, 0, 0}, region_hi[kMaxDims] = {0, 0, 0, 0};
   int64_t pair_start[kMaxDims + 1] = {0, 0, 0, 0, 0};
   int64_t n_pairs_rows = 0;
+  // Block mode (cropped, non-negative lags [lag0, lag0 + K)): the second signal
+  // of a pair is cut into n_blocks blocks of block_len samples, the first into
+  // overlapping segments of L samples starting at b*block_len + lag0; then
+  // r[lag0 + l] = sum_b (segment_b (*) block_b)[l] for l < K as long as
+  // L >= block_len + K, so the transforms have length L instead of 2n.
+  int n_blocks = 1;
+  int64_t block_len = 0, lag0 = 0;
 };
 
 inline int pow2_exponent(int v) { int e = 0; while (v % 2 == 0) { v /= 2; ++e; } return e; }
@@ -98,9 +105,13 @@ inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
   return true;
 }
 
-inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd) {
+inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd, int n_blocks = 1,
+                           int64_t block_len = 0, int64_t lag0 = 0, int64_t n_lags = 0) {
   if (n < 1 || nd < 1 || nd > kMaxDims) return false;
   g.n = n;
+  g.n_blocks = n_blocks < 1 ? 1 : n_blocks;
+  g.block_len = g.n_blocks > 1 ? block_len : 0;
+  g.lag0 = g.n_blocks > 1 ? lag0 : 0;
   g.nd = nd;
   int64_t M = 1;
   for (int a = 0; a < nd; ++a) {
@@ -108,7 +119,13 @@ inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd) {
     g.dims[a] = dims[a];
     M *= dims[a];
   }
-  if (M < n || M >= 2147483648LL) return false;
+  if (M >= 2147483648LL) return false;
+  if (g.n_blocks == 1) {
+    if (M < n) return false;
+  } else {
+    if (block_len < 1 || lag0 < 0 || n_lags < 1 || block_len * g.n_blocks < n) return false;
+    if (2 * M < block_len + n_lags) return false;
+  }
   g.M = M;
   g.L = 2 * M;
   g.S[nd] = 1;
@@ -197,7 +214,7 @@ template <class T> inline void pass_common(PassParams<T>& p, const PlanGeom& g, 
 template <class T>
 inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb, int a, const T* x,
                                        int64_t x_stride, cx<T>* spec, int64_t spec_stride, int n_signals,
-                                       double* sumsq_partial) {
+                                       double* sumsq_partial, int64_t n_real = -1) {
   PassParams<T> p;
   pass_common(p, g, tb, a);
   p.n_batch = n_signals;
@@ -206,7 +223,7 @@ inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb
   if (a == 0) {
     p.in = x;
     p.in_stride = x_stride;
-    p.n_real = g.n;
+    p.n_real = n_real >= 0 ? n_real : g.n;
     p.real_vec_ok = ((reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T))) == 0 && x_stride % 2 == 0) ? 1 : 0;
     p.sumsq_partial = sumsq_partial;
   } else {
@@ -262,7 +279,10 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   // rows k of the last column pass (element m = k*S[1] + col) that can hold a kept lag
   p.keep_lo[0] = p.keep_lo[1] = 0;
   p.keep_hi[0] = p.keep_hi[1] = 0;
-  if (g.nd > 1) {
+  p.epi_direct = g.n_blocks > 1 ? 1 : 0;
+  if (g.n_blocks > 1) {
+    if (g.nd > 1) p.keep_hi[0] = (int32_t)((((f.i1 - f.i0) + 1) / 2 - 1) / g.S[1] + 1);
+  } else if (g.nd > 1) {
     const int64_t n = g.n, L = g.L, inner0 = g.S[1];
     // lags >= 0: i = l + n-1, l in [0, n)        -> l in [max(0, i0-(n-1)), min(n, i1-(n-1)))
     int64_t la = std::max<int64_t>(0, f.i0 - (n - 1)), lb = std::min<int64_t>(n, f.i1 - (n - 1));
@@ -276,6 +296,7 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
     }
   }
   if (a == g.nd - 1) {
+    p.tile_major = 1;
     p.load_mode = RL_PROLOGUE;
     p.store_mode = (g.nd == 1) ? RS_EPI : RS_CONJ;
     p.tiles_per_batch = (g.n_pairs_rows + (C / 2) - 1) / (C / 2);
@@ -284,6 +305,122 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
     p.store_mode = (a == 0) ? CS_EPI : CS_CONJ;
   }
   return p;
+}
+
+// ---------------------------------------------------------------------------
+// Orchestration shared by the library (kernel launches) and the CPU emulator.
+// `run(params, is_row_pass, kind)` executes one pass; kinds 0..nd-1 are forward
+// passes, nd..2nd-1 inverse passes of the same axes.  Returns false on failure.
+// ---------------------------------------------------------------------------
+inline int64_t pass0_tiles(const PlanGeom& g, int C) {
+  return g.nd > 1 ? (g.M / g.S[0]) * ((g.S[1] + C - 1) / C) : (g.M / g.dims[0] + C - 1) / C;
+}
+
+// spectra per input signal: 1, or 2*n_blocks (segments then blocks) in block mode
+inline int spectra_per_signal(const PlanGeom& g) { return g.n_blocks > 1 ? 2 * g.n_blocks : 1; }
+
+// Forward transforms of n_signals signals x[s][x_stride].  `partial` receives the
+// per-tile sums of squares, [n_blocks][n_signals][pass0_tiles].
+template <class T, class Run>
+inline bool run_forward(const PlanGeom& g, const DevTables<T>& tb, const T* x, int64_t x_stride, int n_signals,
+                        cx<T>* spec, double* partial, Run&& run) {
+  const int C = tile_cols<T>();
+  if (g.n_blocks == 1) {
+    for (int a = 0; a < g.nd; ++a) {
+      PassParams<T> p = make_forward_pass<T>(g, tb, a, x, x_stride, spec, g.M, n_signals, a == 0 ? partial : nullptr);
+      if (!run(p, a == g.nd - 1, a)) return false;
+    }
+    return true;
+  }
+  const int B = g.n_blocks, per = 2 * B;
+  const int64_t t0 = pass0_tiles(g, C);
+  for (int role = 0; role < 2; ++role)
+    for (int b = 0; b < B; ++b) {
+      const int64_t start = (int64_t)b * g.block_len + (role == 0 ? g.lag0 : 0);
+      int64_t valid = g.n - start;
+      const int64_t want = role == 0 ? g.L : std::min<int64_t>(g.block_len, g.n - (int64_t)b * g.block_len);
+      if (valid > want) valid = want;
+      if (valid < 0) valid = 0;
+      PassParams<T> p = make_forward_pass<T>(g, tb, 0, x + start, x_stride, spec + (int64_t)(role * B + b) * g.M,
+                                             (int64_t)per * g.M, n_signals,
+                                             role == 1 ? partial + (int64_t)b * n_signals * t0 : nullptr, valid);
+      if (!run(p, g.nd == 1, 0)) return false;
+    }
+  for (int a = 1; a < g.nd; ++a) {
+    PassParams<T> p = make_forward_pass<T>(g, tb, a, x, x_stride, spec, g.M, n_signals * per, nullptr);
+    if (!run(p, a == g.nd - 1, a)) return false;
+  }
+  return true;
+}
+
+template <class T, class Run>
+inline bool run_inverse(const PlanGeom& g, const DevTables<T>& tb, const cx<T>* spec, const double* rnorm,
+                        const Job* jobs, int n_jobs, cx<T>* work, T* ccf, CorrFlags f, Run&& run) {
+  if (g.n_blocks > 1) {                 // the block sum is the stacking loop of the pair product
+    f.n_stack = g.n_blocks;
+    f.stack_sig_stride = 0;
+    f.stack_spec_stride = g.M;
+  }
+  for (int a = g.nd - 1; a >= 0; --a) {
+    PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec, rnorm, jobs, n_jobs, work, ccf, f);
+    if (!run(p, a == g.nd - 1, g.nd + a)) return false;
+  }
+  return true;
+}
+
+// Job of pair (signal si, signal sj) writing at out_off
+inline Job make_job(const PlanGeom& g, int64_t si, int64_t sj, int64_t out_off) {
+  Job j;
+  const int64_t per = spectra_per_signal(g);
+  j.sig_i = (int32_t)si;
+  j.sig_j = (int32_t)sj;
+  j.spec_i = si * per * g.M;                                   // segments of signal i
+  j.spec_j = (sj * per + (g.n_blocks > 1 ? g.n_blocks : 0)) * g.M;   // blocks of signal j
+  j.out_off = out_off;
+  return j;
+}
+
+// Block-mode planner: for kept lags [lag0, lag0 + K) with lag0 >= 0 choose the
+// number of blocks and the transform that minimise the HBM traffic model
+//   P * ((2B + 4) F + K) + N * 2B * 5.5 F      (F = transform length in reals)
+// against the classic  P * (6 L + K) + N * (n + 5 L).  Returns false when the
+// classic single transform is at least as good.
+inline bool plan_choose_blocks(int64_t n, int64_t n_lags, int n_recv, int n_pairs, int dims[kMaxDims], int* nd,
+                               int* n_blocks, int64_t* block_len) {
+  int cd[kMaxDims], cnd = 0;
+  if (!plan_choose_dims(n, cd, &cnd)) return false;
+  double Lc = 2.0;
+  for (int a = 0; a < cnd; ++a) Lc *= cd[a];
+  const double N = n_recv, P = n_pairs > 0 ? n_pairs : 1;
+  double best = P * (6.0 * Lc + n_lags) + N * (n + 5.0 * Lc);
+  bool found = false;
+  for (int B = 2; B <= 6; ++B) {
+    int bd[kMaxDims], bnd = 0;
+    int64_t lb = (n + B - 1) / B;
+    if (!plan_choose_dims((lb + n_lags + 1) / 2, bd, &bnd)) continue;
+    int64_t M = 1;
+    for (int a = 0; a < bnd; ++a) M *= bd[a];
+    // whole rows of the first pass (row = 2*S[1] reals) keep every piece TMA-legal
+    int64_t row = 2 * (M / bd[0]);
+    if (bnd > 1 && n % row == 0) {
+      int64_t lb_rows = (lb + row - 1) / row * row;
+      if (lb_rows + n_lags <= 2 * M) lb = lb_rows;
+    }
+    if (lb + n_lags > 2 * M) continue;
+    int Beff = (int)((n + lb - 1) / lb);
+    if (Beff < 2) continue;
+    const double F = 2.0 * M;
+    const double cost = P * ((2.0 * Beff + 4.0) * F + n_lags) + N * 2.0 * Beff * 5.5 * F;
+    if (cost < 0.95 * best) {
+      best = cost;
+      found = true;
+      for (int a = 0; a < bnd; ++a) dims[a] = bd[a];
+      *nd = bnd;
+      *n_blocks = Beff;
+      *block_len = lb;
+    }
+  }
+  return found;
 }
 
 }  // namespace xcb

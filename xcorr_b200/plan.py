@@ -64,7 +64,7 @@ class CorrelationPlan:
 
     def __init__(self, n, n_receivers, pairs, n_windows=1, dtype=torch.float32,
                  index_min=0, index_max=0, normalize=True, unbiased=False,
-                 stack=False, dims=None, max_work_bytes=0, device=None):
+                 stack=False, dims=None, max_work_bytes=0, device=None, n_blocks=0, block_len=0):
         if not torch.cuda.is_available():
             raise _lib.XcbError("xcorr_b200 needs a CUDA device; there is no CPU fallback")
         self._lib = _lib.load()
@@ -92,6 +92,8 @@ class CorrelationPlan:
         d.lag_index_min = int(index_min)
         d.lag_index_max = int(index_max)
         d.max_work_bytes = int(max_work_bytes)
+        d.n_blocks = int(n_blocks)
+        d.block_len = int(block_len)
         self._plan = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.xcb_plan_create(ctypes.byref(self._plan), ctypes.byref(d)), "xcb_plan_create")
@@ -105,6 +107,7 @@ class CorrelationPlan:
         self.n_jobs = int(info.n_jobs)
         self.jobs_in_flight = int(info.jobs_in_flight)
         self.dims = tuple(int(info.dims[a]) for a in range(info.nd))
+        self.n_blocks, self.block_len = int(info.n_blocks), int(info.block_len)
         self.n_receivers, self.n_windows = int(n_receivers), int(n_windows)
         self.stack = bool(stack)
         self.index_min = int(index_min)
