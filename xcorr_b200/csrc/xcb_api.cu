@@ -177,23 +177,42 @@ __global__ void __launch_bounds__(256) xcb_argmax_partial(const T* __restrict__ 
   }
 }
 
+// order of np.argmax candidates: a NaN beats any number, then larger value, then lower index
+template <class T> __device__ __forceinline__ bool argmax_better(bool hb, T vb, int64_t ib, bool ha, T va, int64_t ia) {
+  if (!hb) return false;
+  if (!ha) return true;
+  const bool nb = vb != vb, na = va != va;
+  if (nb != na) return nb;
+  if (nb) return ib < ia;
+  return vb > va || (vb == va && ib < ia);
+}
+
+// one warp per row over the per-chunk partial results
 template <class T>
-__global__ void xcb_argmax_final_rows(const T* __restrict__ pval, const int64_t* __restrict__ pidx, int chunks,
-                                      int64_t n_rows, int64_t* __restrict__ index, T* __restrict__ value) {
-  const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) xcb_argmax_final_rows(const T* __restrict__ pval, const int64_t* __restrict__ pidx,
+                                                            int chunks, int64_t n_rows, int64_t* __restrict__ index,
+                                                            T* __restrict__ value) {
+  const int64_t row = blockIdx.x;
   if (row >= n_rows) return;
-  bool have = false, isnan_ = false;
+  bool have = false;
   T best = T(0);
   int64_t bi = 0;
-  for (int c = 0; c < chunks; ++c) {        // chunks are in index order
-    int64_t i = pidx[row * chunks + c];
-    if (i < 0) continue;
-    T v = pval[row * chunks + c];
-    if (v != v) { if (!isnan_) { isnan_ = true; best = v; bi = i; have = true; } continue; }
-    if (!isnan_ && (!have || v > best)) { best = v; bi = i; have = true; }
+  for (int c = threadIdx.x; c < chunks; c += 32) {
+    const int64_t i = pidx[row * chunks + c];
+    const T v = pval[row * chunks + c];
+    if (argmax_better<T>(i >= 0, v, i, have, best, bi)) { have = true; best = v; bi = i; }
   }
-  index[row] = have ? bi : 0;
-  if (value) value[row] = best;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool ho = __shfl_down_sync(0xffffffffu, (int)have, o) != 0;
+    const T vo = __shfl_down_sync(0xffffffffu, best, o);
+    const int64_t io = __shfl_down_sync(0xffffffffu, bi, o);
+    if (argmax_better<T>(ho, vo, io, have, best, bi)) { have = true; best = vo; bi = io; }
+  }
+  if (threadIdx.x == 0) {
+    index[row] = have ? bi : 0;
+    if (value) value[row] = best;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -519,8 +538,7 @@ static int argmax_t(const void* rows, int64_t n_rows, int64_t row_len, int64_t* 
                                                pval + r0 * chunks, pidx + r0 * chunks);
   }
   XCB_CUDA(cudaGetLastError());
-  xcb_argmax_final_rows<T><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(pval, pidx, chunks, n_rows, index,
-                                                                          static_cast<T*>(value));
+  xcb_argmax_final_rows<T><<<(unsigned)n_rows, 32, 0, st>>>(pval, pidx, chunks, n_rows, index, static_cast<T*>(value));
   XCB_CUDA(cudaGetLastError());
   XCB_CUDA(cudaFreeAsync(pval, st));
   XCB_CUDA(cudaFreeAsync(pidx, st));

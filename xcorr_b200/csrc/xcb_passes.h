@@ -185,6 +185,21 @@ template <class T> XCB_HD void epilogue_store(const PassParams<T>& p, T* outp, u
   }
 }
 
+// Lean epilogue for the common block-mode case (lag l = output index l, no
+// weights, plain store): one aligned 2-sample store per complex element.
+template <class T> XCB_HD bool epilogue_fast_ok(const PassParams<T>& p) {
+  return p.epi_direct && !p.unbiased && !p.accumulate;
+}
+template <class T> XCB_HD void epilogue_store_fast(const PassParams<T>& p, T* outp, uint32_t m, T re, T im) {
+  const uint32_t K = (uint32_t)(p.i1 - p.i0), l = 2u * m;
+  if (l + 1u < K) {
+    cx<T> v; v.x = re * p.escale; v.y = im * p.escale;
+    *reinterpret_cast<cx<T>*>(outp + l) = v;           // l even, rows start 2*sizeof(T)-aligned (K even or job 0)
+  } else if (l < K) {
+    outp[l] = re * p.escale;
+  }
+}
+
 // v[r] <- (conj?)(v[r]) * W_M^(e0 + r*de), r = 0..R-1, with the twiddle advanced
 // by a running product instead of R table lookups (2 lookups per thread).
 template <int R, bool CONJ_IN, class T>
@@ -314,13 +329,22 @@ template <class T, int R1, int R2> struct ColPass {
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[(int64_t)(t.j + r * R1) * p.inner] = cconj(v[r]);
       } else {
-        T* outp = p.ccf + p.jobs[t.batch].out_off;
+        const int64_t out_off = p.jobs[t.batch].out_off;
+        T* outp = p.ccf + out_off;
         const uint32_t m0 = (uint32_t)(t.base + t.c), inner = (uint32_t)p.inner;
+        if (epilogue_fast_ok(p) && (out_off & 1) == 0) {
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-          const int k = t.j + r * R1;
-          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
-            epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          for (int r = 0; r < R2; ++r) {
+            const int k = t.j + r * R1;
+            if (k < p.keep_hi[0]) epilogue_store_fast(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R2; ++r) {
+            const int k = t.j + r * R1;
+            if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+              epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          }
         }
       }
     }

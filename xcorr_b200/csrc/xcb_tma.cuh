@@ -182,13 +182,22 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[(int64_t)(j + r * R1) * p.inner] = cconj(v[r]);
       } else {
-        T* outp = p.ccf + p.jobs[batch].out_off;
+        const int64_t out_off = p.jobs[batch].out_off;
+        T* outp = p.ccf + out_off;
         const uint32_t m0 = (uint32_t)(base + c), inner = (uint32_t)p.inner;
+        if (epilogue_fast_ok(p) && (out_off & 1) == 0) {
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-          const int k = j + r * R1;
-          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
-            epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          for (int r = 0; r < R2; ++r) {
+            const int k = j + r * R1;
+            if (k < p.keep_hi[0]) epilogue_store_fast(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < R2; ++r) {
+            const int k = j + r * R1;
+            if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+              epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
+          }
         }
       }
     }
