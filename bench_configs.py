@@ -120,6 +120,26 @@ def run(name, steps, warmup):
         out.update(desc=f"4 receivers / 6 pairs, {W} windows of 1h@250Hz per step, stacked on device (spectral stacking)",
                    dtype=str(dt), ms_per_step=ms, unit="pair-hours/s", value=len(pairs) * W / (ms * 1e-3),
                    passes=plan.dims, blocks=plan.n_blocks, alg_bytes_per_unit=alg)
+    elif name in ("cfg5", "cfg5_f64"):
+        from xcorr_b200.signal import Correlate2dPlan
+        dt = torch.float64 if name.endswith("f64") else torch.float32
+        b = 8 if dt == torch.float64 else 4
+        F, T, D = 1024, 128, 48
+        pairs = [(i, j) for i in range(D) for j in range(i, D)]          # lower triangle incl. diagonal
+        plan = Correlate2dPlan(F, T, D, pairs, dtype=dt, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(5)
+        days = torch.randn((D, F, T), generator=g, device=dev, dtype=dt) ** 2
+
+        def step():
+            cc2 = plan(days)
+            plan.argmax(cc2)
+        ms = timed(step, steps, warmup)
+        A = 2 * plan.plan.spectrum_elems * b                              # bytes of one padded spectrum
+        alg = (D * (F * T * b + 3 * A) + len(pairs) * 4 * A) / len(pairs)  # F = FTb + 3A, I = 4A
+        out.update(desc=f"{D} day spectrograms 1024x128 -> {len(pairs)} day pairs, cc2 + arg-max (timelapse kernel)",
+                   dtype=str(dt), ms_per_step=ms, unit="day-pairs/s", value=len(pairs) / (ms * 1e-3),
+                   passes=plan.plan.dims, blocks=plan.plan.n_blocks, alg_bytes_per_unit=alg)
     else:
         raise SystemExit(f"unknown config {name}")
     out["step_roofline_frac"] = out["alg_bytes_per_unit"] * out["value"] / 1e9 / peak
@@ -129,7 +149,7 @@ def run(name, steps, warmup):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="cfg1,cfg1_f32,cfg2,cfg2_f64,cfg3,cfg3_f64,cfg3_full,cfg4,cfg4_f64")
+    ap.add_argument("--configs", default="cfg1,cfg1_f32,cfg2,cfg2_f64,cfg3,cfg3_f64,cfg3_full,cfg4,cfg4_f64,cfg5,cfg5_f64")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()

@@ -1,0 +1,124 @@
+r"""
+:mod:`signal.correlate` -- 1-D / 2-D FFT correlation of arrays (timelapse kernel)
+===================================================================================
+
+``correlate2d`` of the reference (``signal/correlate.py:162-291``) pads two
+``F x T`` arrays to ``(2F-1) x (2T-1)``, multiplies ``fft2(f)`` by
+``conj(fft2(g))`` and returns ``fftshift(real(ifft2(.)))``; the timelapse script
+evaluates it for every day pair of CCF spectrograms
+(``scripts/timelapse.py:218-275``) and keeps the arg-max.
+
+Here the 2-D linear correlation runs on the 1-D kernels of the main path by
+embedding: write each array into rows of width ``W >= 2T-1`` (zeros to the
+right) and flatten.  The 1-D linear correlation of the flattened arrays at lag
+``dF*W + dT`` (``|dT| < T``) is exactly ``sum f[u+dF, v+dT] g[u, v]`` -- a
+shifted column either stays inside its row or lands on padding, never on a
+neighbouring row's data.  So every image is transformed ONCE (``N`` transforms
++ ``P`` products for ``P`` image pairs, the reference recomputes both
+spectra per pair), with ``n = F*W`` samples; for the named shape 1024 x 128,
+``W = 256`` gives ``n = 262144 = 64^3``.
+"""
+import numpy as np
+import torch
+
+from ..plan import CorrelationPlan
+
+__all__ = ['correlate1d', 'correlate2d', 'Correlate2dPlan']
+
+
+def _row_width(T):
+    """Smallest multiple of 16 that is >= 2T-1 (keeps rows 64-byte aligned)."""
+    return max(16, -(-(2 * T - 1) // 16) * 16)
+
+
+class Correlate2dPlan:
+    """All 2-D correlations of ``n_images`` arrays ``F x T`` over a pair list."""
+
+    def __init__(self, F, T, n_images, pairs, dtype=torch.float32, normalize=True, device=None):
+        self.F, self.T, self.W = int(F), int(T), _row_width(T)
+        self.n = self.F * self.W
+        self.pairs = [(int(i), int(j)) for i, j in pairs]
+        self.plan = CorrelationPlan(self.n, n_images, self.pairs, dtype=dtype, normalize=normalize,
+                                    device=device, n_blocks=1)
+        self.dtype, self.device = self.plan.dtype, self.plan.device
+        a = torch.arange(-(self.F - 1), self.F, device=self.device).view(-1, 1)
+        b = torch.arange(-(self.T - 1), self.T, device=self.device).view(1, -1)
+        # 1-D output index of shift (dF, dT): lag dF*W + dT sits at (n-1) + lag
+        self.index = ((self.n - 1) + a * self.W + b).reshape(-1)
+
+    def embed(self, images):
+        """(n_images, F, T) -> (n_images, F*W) zero-padded rows."""
+        x = torch.zeros((images.shape[0], self.F, self.W), dtype=self.dtype, device=self.device)
+        x[:, :, :self.T] = images.to(self.dtype)
+        return x.reshape(images.shape[0], self.n)
+
+    def forward(self, images):
+        self.plan.forward(self.embed(images))
+
+    def correlate(self):
+        """cc2 of every pair, shape (n_pairs, 2F-1, 2T-1)."""
+        ccf = self.plan.correlate()[:, 0]
+        return ccf.index_select(1, self.index).reshape(len(self.pairs), 2 * self.F - 1, 2 * self.T - 1)
+
+    def argmax(self, cc2):
+        """(value, dF, dT) of the maximum of each cc2 (first maximal index,
+        like ``np.argmax`` + ``np.unravel_index`` in ``scripts/timelapse.py:261-268``)."""
+        idx, val = self.plan.argmax(cc2.reshape(cc2.shape[0], -1))
+        nb = 2 * self.T - 1
+        return val, idx // nb - (self.F - 1), idx % nb - (self.T - 1)
+
+    def __call__(self, images):
+        self.forward(images)
+        return self.correlate()
+
+
+def _as_cuda(x, dtype=None):
+    t = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x)
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda() if not t.is_cuda else t
+
+
+def correlate2d(in1, in2, normalize: bool = True, dtype=None):
+    """
+    Two-dimensional cross-correlation of two arrays over their last two axes
+    (array core of ``signal/correlate.py:162-291``; labels and attributes are
+    the caller's).  Returns ``(..., 2F-1, 2T-1)``; index ``(a, b)`` is the shift
+    ``(a-(F-1), b-(T-1))``.  numpy in -> numpy out, CUDA tensor in -> tensor out.
+    """
+    was_numpy = not torch.is_tensor(in1)
+    a, b = _as_cuda(in1), _as_cuda(in2)
+    if a.shape != b.shape:
+        raise ValueError('in1 and in2 should have the same shape!')
+    if a.dtype not in (torch.float32, torch.float64):
+        a, b = a.double(), b.double()
+    if dtype is not None:
+        a, b = a.to(dtype), b.to(dtype)
+    lead = a.shape[:-2]
+    F, T = a.shape[-2:]
+    a2, b2 = a.reshape(-1, F, T), b.reshape(-1, F, T)
+    m = a2.shape[0]
+    plan = Correlate2dPlan(F, T, 2 * m, [(k, m + k) for k in range(m)], dtype=a.dtype, normalize=normalize)
+    cc = plan(torch.cat((a2, b2), dim=0)).reshape(*lead, 2 * F - 1, 2 * T - 1)
+    return cc.cpu().numpy() if was_numpy else cc
+
+
+def correlate1d(in1, in2, normalize: bool = True, dtype=None):
+    """
+    One-dimensional cross-correlation along the last axis (array core of
+    ``signal/correlate.py:32-160``): ``(..., 2n-1)``, zero lag at index ``n-1``.
+    """
+    was_numpy = not torch.is_tensor(in1)
+    a, b = _as_cuda(in1), _as_cuda(in2)
+    if a.shape != b.shape:
+        raise ValueError('in1 and in2 should have the same shape!')
+    if a.dtype not in (torch.float32, torch.float64):
+        a, b = a.double(), b.double()
+    if dtype is not None:
+        a, b = a.to(dtype), b.to(dtype)
+    lead, n = a.shape[:-1], a.shape[-1]
+    a2, b2 = a.reshape(-1, n), b.reshape(-1, n)
+    m = a2.shape[0]
+    plan = CorrelationPlan(n, 2 * m, [(k, m + k) for k in range(m)], dtype=a.dtype, normalize=normalize, n_blocks=1)
+    cc = plan(torch.cat((a2, b2), dim=0).contiguous())[:, 0].reshape(*lead, 2 * n - 1)
+    return cc.cpu().numpy() if was_numpy else cc
