@@ -66,8 +66,8 @@ typedef struct xcb_desc {
   int64_t lag_index_min;   /* lag.attrs['index_min'] (core/init.py:191-208, util/time.py:94-108) */
   int64_t lag_index_max;   /* exclusive; both 0 -> full 2n-1 lags */
   int64_t max_work_bytes;  /* cap for the inverse-transform scratch; 0 -> 16 GiB */
-  int32_t n_blocks;        /* 0: automatic; 1: one transform of the whole window; >1 (with nd, dims, block_len): block mode,
-                            * kept lags must be non-negative (lag_index_min >= n-1), see DESIGN.md section 3 */
+  int32_t n_blocks;        /* 0: automatic; 1: one transform of the whole window; >1 (with nd, dims, block_len): block mode
+                            * (cropped lags, shorter transforms) */
   int32_t reserved;
   int64_t block_len;       /* samples per block when n_blocks > 1 */
 } xcb_desc;

@@ -61,7 +61,7 @@ static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_st
     n_blocks = 1;
     int bd[kMaxDims], bnd = 0, nb = 0;
     int64_t bl = 0;
-    if (nd == 0 && i0 >= n - 1 && plan_choose_blocks(n, K, n_signals, n_pairs, bd, &bnd, &nb, &bl)) {
+    if (nd == 0 && plan_choose_blocks(n, K, n_signals, n_pairs, bd, &bnd, &nb, &bl)) {
       n_blocks = nb; block_len = bl; k = bnd;
       for (int a = 0; a < bnd; ++a) d[a] = bd[a];
     }

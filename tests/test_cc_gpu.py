@@ -259,5 +259,11 @@ def test_block_mode_equals_classic_transform(xb, orc, dtype):
     for q, (i, j) in enumerate(pairs[:3]):
         ref = orc.cc(rec[i, 1], rec[j, 1], unbiased=True)
         assert np.max(np.abs(got[q, 1] - ref[n - 1:n - 1 + 20_000])) <= 20 * TOL[np.dtype(dtype)] * np.max(np.abs(ref[n - 1:n - 1 + 20_000]))
-    with pytest.raises(Exception):        # negative lags cannot use blocks
-        xb.CorrelationPlan(n, R, pairs, dtype=tdt, index_min=0, index_max=1000, dims=(200, 200), n_blocks=2, block_len=60_000)
+    # symmetric and negative-only lag windows: segments start before the signal (zeros there)
+    for i0, K in ((n - 1 - 20_000, 40_001), (n - 1 - 50_000, 30_000), (0, 25_000)):
+        auto = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + K)
+        assert auto.n_blocks >= 2
+        got = auto(x).cpu().numpy()
+        for q, (i, j) in list(enumerate(pairs))[::4]:
+            ref = orc.cc(rec[i, 0], rec[j, 0], unbiased=False)
+            assert np.max(np.abs(got[q, 0] - ref[i0:i0 + K])) <= TOL[np.dtype(dtype)] * np.max(np.abs(ref)), (i0, q)

@@ -122,6 +122,9 @@ def test_spectral_stacking_sums_windows():
     (2, (64, 64, 64), 400_000, 100_000, 0),
     (2, (64, 64), 6000, 1500, 700),        # first kept lag > 0
     (4, (100,), 500, 60, 0),               # single-pass transform, F = 200 >= 125 + 60
+    (2, (64, 80), 6000, 3001, -1500),      # symmetric window: segments start before the signal
+    (3, (64, 64), 5001, 1000, -4000),      # negative lags only, odd length, odd offset
+    (2, (80, 80), 6000, 2500, -5999),      # window reaching the most negative lag
 ])
 def test_block_mode_matches_full_transform(B, dims, n, K, lag0):
     """Cropped non-negative lags through B blocks of the second signal and

@@ -312,7 +312,7 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   // non-negative lags -- blocks with a shorter transform (xcb_plan.h, PlanGeom)
   int dims[kMaxDims] = {0, 0, 0, 0}, nd = d->nd, n_blocks = d->n_blocks;
   int64_t block_len = d->block_len;
-  const bool blocks_possible = pl->i0 >= d->n - 1 && !d->stack;
+  const bool blocks_possible = !d->stack;
   if (n_blocks > 1 && (!blocks_possible || nd == 0 || block_len < 1)) { delete pl; return XCB_ERR_ARG; }
   if (n_blocks == 0) {
     n_blocks = 1;

@@ -83,7 +83,7 @@ static int resident_ctas(const void* kernel, int threads, int smem) {
 // 16-byte aligned pitches.  Real input (first forward pass) additionally needs
 // whole rows (n a multiple of the row length): the zero padding is then the
 // tensor map's out-of-bounds fill and costs no traffic.
-template <class T> struct TmaGeom { bool ok; int64_t row_elems, rows, row_pitch, batch_pitch; };
+template <class T> struct TmaGeom { bool ok; const void* base; int64_t row_elems, rows, row_pitch, batch_pitch; };
 
 template <class T> TmaGeom<T> tma_geom(const PassParams<T>& p) {
   TmaGeom<T> g;
@@ -91,7 +91,12 @@ template <class T> TmaGeom<T> tma_geom(const PassParams<T>& p) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("XCB_TMA"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled) return g;
-  if (reinterpret_cast<uintptr_t>(p.in) % 16 != 0) return g;
+  g.base = p.in;
+  if (p.load_mode == CL_REAL) {
+    if (p.real_begin < 0) return g;                       // segment starts before the signal: plain kernel
+    g.base = static_cast<const T*>(p.in) + p.real_begin;
+  }
+  if (reinterpret_cast<uintptr_t>(g.base) % 16 != 0) return g;
   g.row_elems = 2 * p.inner;
   g.row_pitch = g.row_elems * (int64_t)sizeof(T);
   if (g.row_pitch % 16 != 0) return g;
@@ -115,7 +120,7 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
   if (tg.ok) {
     using K = ColTma<T, R1, R2>;
     CUtensorMap map;
-    int rc = encode_col_tile_map(&map, sizeof(T) == 4 ? 0 : 1, p.in, tg.row_elems, tg.rows, p.n_batch, tg.row_pitch,
+    int rc = encode_col_tile_map(&map, sizeof(T) == 4 ? 0 : 1, tg.base, tg.row_elems, tg.rows, p.n_batch, tg.row_pitch,
                                  tg.batch_pitch, K::BOX_ROWS);
     if (rc == 0) {
       static int resident = 0;   // persistent grid: as many CTAs as stay resident

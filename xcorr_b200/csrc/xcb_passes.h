@@ -56,8 +56,9 @@ template <class T> struct PassParams {
   void* out;                 // cx<T>[n_batch][out_stride]
   int64_t in_stride, out_stride;
   // ---- real input (forward first pass) ----
-  int64_t n_real;            // valid samples per signal; the rest of 2M is zero
-  int32_t real_vec_ok;       // 1: every signal base is 2*sizeof(T)-aligned
+  int64_t n_real;            // transform samples [0, n_real) may be non-zero; the rest of 2M is zero
+  int64_t real_begin;        // transform sample q is signal sample real_begin + q (zero where that is < 0)
+  int32_t real_vec_ok;       // 1: signal sample pairs (real_begin + 2m, +1) are 2*sizeof(T)-aligned
   int32_t pad0;
   double* sumsq_partial;     // [n_batch][tiles_per_batch] or null
   // ---- twiddles: W_M^e = tw_hi[e >> shift] * tw_lo[e & mask] ----
@@ -142,15 +143,18 @@ template <class T> XCB_HD cx<T> tw_big(const PassParams<T>& p, uint32_t e) {
   return cmul(ld_ro(p.tw_hi + (e >> p.tw_shift)), ld_ro(p.tw_lo + (e & p.tw_mask)));
 }
 
-// packed real load: complex index m of signal `x` -> (x[2m], x[2m+1]), zero past n_real
+// packed real load: complex index m of the transform -> samples (2m, 2m+1) of the
+// window [real_begin, real_begin + n_real) of signal `x`; zero outside it and
+// before the start of the signal
 template <class T> XCB_HD cx<T> load_real_packed(const PassParams<T>& p, const T* x, int64_t m, double& ss) {
   cx<T> r; r.x = T(0); r.y = T(0);
-  int64_t q = 2 * m;
-  if (q + 1 < p.n_real) {
-    if (p.real_vec_ok) r = *reinterpret_cast<const cx<T>*>(x + q);
-    else { r.x = x[q]; r.y = x[q + 1]; }
-  } else if (q < p.n_real) {
-    r.x = x[q];
+  const int64_t q = 2 * m, i = p.real_begin + q;
+  if (q + 1 < p.n_real && i >= 0) {
+    if (p.real_vec_ok) r = *reinterpret_cast<const cx<T>*>(x + i);
+    else { r.x = x[i]; r.y = x[i + 1]; }
+  } else {
+    if (q < p.n_real && i >= 0) r.x = x[i];
+    if (q + 1 < p.n_real && i + 1 >= 0) r.y = x[i + 1];
   }
   ss += (double)(r.x * r.x + r.y * r.y);
   return r;

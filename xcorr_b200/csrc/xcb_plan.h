@@ -41,9 +41,10 @@ struct PlanGeom {
   int64_t region_lo[kMaxDims] = {0, 0, 0, 0}, region_hi[kMaxDims] = {0, 0, 0, 0};
   int64_t pair_start[kMaxDims + 1] = {0, 0, 0, 0, 0};
   int64_t n_pairs_rows = 0;
-  // Block mode (cropped, non-negative lags [lag0, lag0 + K)): the second signal
+  // Block mode (cropped lags [lag0, lag0 + K), lag0 of either sign): the second signal
   // of a pair is cut into n_blocks blocks of block_len samples, the first into
-  // overlapping segments of L samples starting at b*block_len + lag0; then
+  // overlapping segments of L samples starting at b*block_len + lag0 (zeros
+  // where that falls outside the signal); then
   // r[lag0 + l] = sum_b (segment_b (*) block_b)[l] for l < K as long as
   // L >= block_len + K, so the transforms have length L instead of 2n.
   int n_blocks = 1;
@@ -123,7 +124,7 @@ inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd, int 
   if (g.n_blocks == 1) {
     if (M < n) return false;
   } else {
-    if (block_len < 1 || lag0 < 0 || n_lags < 1 || block_len * g.n_blocks < n) return false;
+    if (block_len < 1 || n_lags < 1 || block_len * g.n_blocks < n) return false;
     if (2 * M < block_len + n_lags) return false;
   }
   g.M = M;
@@ -214,7 +215,7 @@ template <class T> inline void pass_common(PassParams<T>& p, const PlanGeom& g, 
 template <class T>
 inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb, int a, const T* x,
                                        int64_t x_stride, cx<T>* spec, int64_t spec_stride, int n_signals,
-                                       double* sumsq_partial, int64_t n_real = -1) {
+                                       double* sumsq_partial, int64_t n_real = -1, int64_t real_begin = 0) {
   PassParams<T> p;
   pass_common(p, g, tb, a);
   p.n_batch = n_signals;
@@ -224,7 +225,9 @@ inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb
     p.in = x;
     p.in_stride = x_stride;
     p.n_real = n_real >= 0 ? n_real : g.n;
-    p.real_vec_ok = ((reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T))) == 0 && x_stride % 2 == 0) ? 1 : 0;
+    p.real_begin = real_begin;
+    p.real_vec_ok = ((reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T))) == 0 && x_stride % 2 == 0 &&
+                     real_begin % 2 == 0) ? 1 : 0;
     p.sumsq_partial = sumsq_partial;
   } else {
     p.in = spec;
@@ -336,14 +339,16 @@ inline bool run_forward(const PlanGeom& g, const DevTables<T>& tb, const T* x, i
   const int64_t t0 = pass0_tiles(g, C);
   for (int role = 0; role < 2; ++role)
     for (int b = 0; b < B; ++b) {
+      // segment (role 0) starts lag0 samples after its block and may begin before the signal
       const int64_t start = (int64_t)b * g.block_len + (role == 0 ? g.lag0 : 0);
       int64_t valid = g.n - start;
       const int64_t want = role == 0 ? g.L : std::min<int64_t>(g.block_len, g.n - (int64_t)b * g.block_len);
       if (valid > want) valid = want;
       if (valid < 0) valid = 0;
-      PassParams<T> p = make_forward_pass<T>(g, tb, 0, x + start, x_stride, spec + (int64_t)(role * B + b) * g.M,
+      PassParams<T> p = make_forward_pass<T>(g, tb, 0, x, x_stride, spec + (int64_t)(role * B + b) * g.M,
                                              (int64_t)per * g.M, n_signals,
-                                             role == 1 ? partial + (int64_t)b * n_signals * t0 : nullptr, valid);
+                                             role == 1 ? partial + (int64_t)b * n_signals * t0 : nullptr, valid,
+                                             start);
       if (!run(p, g.nd == 1, 0)) return false;
     }
   for (int a = 1; a < g.nd; ++a) {
@@ -380,7 +385,7 @@ inline Job make_job(const PlanGeom& g, int64_t si, int64_t sj, int64_t out_off) 
   return j;
 }
 
-// Block-mode planner: for kept lags [lag0, lag0 + K) with lag0 >= 0 choose the
+// Block-mode planner: for kept lags [lag0, lag0 + K) (any sign of lag0) choose the
 // number of blocks and the transform that minimise the HBM traffic model
 //   P * ((2B + 4) F + K) + N * 2B * 5.5 F      (F = transform length in reals)
 // against the classic  P * (6 L + K) + N * (n + 5 L).  Returns false when the
