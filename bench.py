@@ -286,10 +286,11 @@ def run_gpu(args):
         # per-launch algorithmic bytes of each pass kind: inputs read once + outputs written
         # once, for the transforms the plan actually runs (F = plan.fft_len; block mode: 2B spectra per signal)
         F, B = L, plan.n_blocks
-        per = 2 * B if B > 1 else 1
+        per = plan.spectrum_elems // (F // 2)          # spectra per signal (2B, or 2B-1 when the last segment aliases)
         if B > 1:
             lb = plan.block_len
-            valid = sum(min(F, n - k * lb) for k in range(B)) + sum(min(lb, n - k * lb) for k in range(B))
+            nseg = per - B
+            valid = sum(min(F, n - k * lb) for k in range(nseg)) + sum(min(lb, n - k * lb) for k in range(B))
         else:
             valid = n
         per_step = {}

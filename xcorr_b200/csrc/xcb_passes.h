@@ -85,6 +85,11 @@ template <class T> struct PassParams {
   int32_t n_stack;
   int32_t stack_sig_stride;
   int64_t stack_spec_stride;
+  // block mode (n_stack <= kMaxBlocks): explicit per-block offsets instead of the
+  // stride, so that a segment whose samples equal a block's can share its spectrum
+  int32_t use_blk_off;
+  int32_t pad2;
+  int64_t blk_off_i[8], blk_off_j[8];
   // ---- lag epilogue (inverse last pass) ----
   int64_t n;                 // samples per window
   int64_t L;                 // 2M
@@ -479,8 +484,8 @@ template <class T, int R1, int R2> struct RowPass {
 #pragma unroll
         for (int u = 0; u < PB; ++u) va[u].x = va[u].y = vb[u].x = vb[u].y = T(0);
         for (int w = 0; w < p.n_stack; ++w) {
-          const cx<T>* zi = p.spec + jb.spec_i + w * p.stack_spec_stride;
-          const cx<T>* zj = p.spec + jb.spec_j + w * p.stack_spec_stride;
+          const cx<T>* zi = p.spec + jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride);
+          const cx<T>* zj = p.spec + jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride);
           T scale = T(0.25);
           if (p.normalize)
             scale = T(0.25 * p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);

@@ -49,7 +49,12 @@ struct PlanGeom {
   // L >= block_len + K, so the transforms have length L instead of 2n.
   int n_blocks = 1;
   int64_t block_len = 0, lag0 = 0;
+  // lag0 == 0: the last segment holds exactly the samples of the last block (the
+  // signal ends inside it), so it is not transformed; its spectrum is the block's
+  bool alias_last = false;
 };
+
+constexpr int kMaxBlocks = 8;
 
 inline int pow2_exponent(int v) { int e = 0; while (v % 2 == 0) { v /= 2; ++e; } return e; }
 
@@ -113,6 +118,8 @@ inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd, int 
   g.n_blocks = n_blocks < 1 ? 1 : n_blocks;
   g.block_len = g.n_blocks > 1 ? block_len : 0;
   g.lag0 = g.n_blocks > 1 ? lag0 : 0;
+  g.alias_last = g.n_blocks > 1 && g.lag0 == 0;
+  if (g.n_blocks > kMaxBlocks) return false;
   g.nd = nd;
   int64_t M = 1;
   for (int a = 0; a < nd; ++a) {
@@ -248,6 +255,8 @@ struct CorrFlags {
   int normalize = 1, unbiased = 0, accumulate = 0;
   int n_stack = 1, stack_sig_stride = 0;       // spectral stacking over windows
   int64_t stack_spec_stride = 0;
+  int use_blk_off = 0;                          // block mode: explicit per-block offsets
+  int64_t blk_off_i[8] = {0, 0, 0, 0, 0, 0, 0, 0}, blk_off_j[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // inverse pass a (run a = nd-1 down to 0) over `n_jobs` jobs using work[n_jobs][M]
@@ -268,6 +277,8 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   p.n_stack = f.n_stack;
   p.stack_sig_stride = f.stack_sig_stride;
   p.stack_spec_stride = f.stack_spec_stride;
+  p.use_blk_off = f.use_blk_off;
+  for (int b = 0; b < 8; ++b) { p.blk_off_i[b] = f.blk_off_i[b]; p.blk_off_j[b] = f.blk_off_j[b]; }
   p.normalize = f.normalize;
   p.ccf = ccf;
   p.i0 = f.i0;
@@ -319,8 +330,13 @@ inline int64_t pass0_tiles(const PlanGeom& g, int C) {
   return g.nd > 1 ? (g.M / g.S[0]) * ((g.S[1] + C - 1) / C) : (g.M / g.dims[0] + C - 1) / C;
 }
 
-// spectra per input signal: 1, or 2*n_blocks (segments then blocks) in block mode
-inline int spectra_per_signal(const PlanGeom& g) { return g.n_blocks > 1 ? 2 * g.n_blocks : 1; }
+// Spectra per input signal: 1, or in block mode the segments that need their own
+// transform (n_blocks, or n_blocks-1 when the last one aliases its block) followed
+// by the n_blocks blocks.
+inline int segments_per_signal(const PlanGeom& g) { return g.n_blocks - (g.alias_last ? 1 : 0); }
+inline int spectra_per_signal(const PlanGeom& g) {
+  return g.n_blocks > 1 ? segments_per_signal(g) + g.n_blocks : 1;
+}
 
 // Forward transforms of n_signals signals x[s][x_stride].  `partial` receives the
 // per-tile sums of squares, [n_blocks][n_signals][pass0_tiles].
@@ -335,17 +351,17 @@ inline bool run_forward(const PlanGeom& g, const DevTables<T>& tb, const T* x, i
     }
     return true;
   }
-  const int B = g.n_blocks, per = 2 * B;
+  const int B = g.n_blocks, nseg = segments_per_signal(g), per = spectra_per_signal(g);
   const int64_t t0 = pass0_tiles(g, C);
   for (int role = 0; role < 2; ++role)
-    for (int b = 0; b < B; ++b) {
+    for (int b = 0; b < (role == 0 ? nseg : B); ++b) {
       // segment (role 0) starts lag0 samples after its block and may begin before the signal
       const int64_t start = (int64_t)b * g.block_len + (role == 0 ? g.lag0 : 0);
       int64_t valid = g.n - start;
       const int64_t want = role == 0 ? g.L : std::min<int64_t>(g.block_len, g.n - (int64_t)b * g.block_len);
       if (valid > want) valid = want;
       if (valid < 0) valid = 0;
-      PassParams<T> p = make_forward_pass<T>(g, tb, 0, x, x_stride, spec + (int64_t)(role * B + b) * g.M,
+      PassParams<T> p = make_forward_pass<T>(g, tb, 0, x, x_stride, spec + (int64_t)(role * nseg + b) * g.M,
                                              (int64_t)per * g.M, n_signals,
                                              role == 1 ? partial + (int64_t)b * n_signals * t0 : nullptr, valid,
                                              start);
@@ -362,9 +378,16 @@ template <class T, class Run>
 inline bool run_inverse(const PlanGeom& g, const DevTables<T>& tb, const cx<T>* spec, const double* rnorm,
                         const Job* jobs, int n_jobs, cx<T>* work, T* ccf, CorrFlags f, Run&& run) {
   if (g.n_blocks > 1) {                 // the block sum is the stacking loop of the pair product
+    const int nseg = segments_per_signal(g);
     f.n_stack = g.n_blocks;
     f.stack_sig_stride = 0;
     f.stack_spec_stride = g.M;
+    f.use_blk_off = 1;
+    for (int b = 0; b < g.n_blocks; ++b) {
+      // Job.spec_i is the signal's first segment, Job.spec_j its first block
+      f.blk_off_i[b] = (int64_t)(b < nseg ? b : nseg + b) * g.M;     // aliased segment -> block b of signal i
+      f.blk_off_j[b] = (int64_t)b * g.M;
+    }
   }
   for (int a = g.nd - 1; a >= 0; --a) {
     PassParams<T> p = make_inverse_pass<T>(g, tb, a, spec, rnorm, jobs, n_jobs, work, ccf, f);
@@ -380,7 +403,7 @@ inline Job make_job(const PlanGeom& g, int64_t si, int64_t sj, int64_t out_off) 
   j.sig_i = (int32_t)si;
   j.sig_j = (int32_t)sj;
   j.spec_i = si * per * g.M;                                   // segments of signal i
-  j.spec_j = (sj * per + (g.n_blocks > 1 ? g.n_blocks : 0)) * g.M;   // blocks of signal j
+  j.spec_j = (sj * per + (g.n_blocks > 1 ? segments_per_signal(g) : 0)) * g.M;   // blocks of signal j
   j.out_off = out_off;
   return j;
 }
