@@ -74,28 +74,46 @@ def mirror_address(addr, dims):
     return out  # addr 0 -> 0
 
 
-def pair_product(Zi, Zj, dims, scale=1.0):
-    """V (digit-transposed) whose inverse packed transform is the packed
-    cross-correlation r[2m] + i r[2m+1] (times M)."""
-    M = len(Zi)
+def half_spectrum(Z, dims):
+    """Packed transform Z (digit-transposed) -> half spectrum X of the real
+    signal in the same address order: address of k holds X[k] = rfft(x)[k],
+    k = 0..M-1; address 0 holds X[0] + i X[M] (both real).  This is what the
+    forward transform stores (RS_HALF)."""
+    M = len(Z)
     a = np.arange(M)
     am = mirror_address(a, dims)
     k = freq_of_address(dims)
-    u = np.exp(+2j * np.pi * k / M)          # conj(W_M^k)
-    Ai, Api = Zi, np.conj(Zi[am])
-    Aj, Apj = Zj, np.conj(Zj[am])
-    Si, Di = Ai + Api, Ai - Api
-    Sj, Dj = Aj + Apj, Aj - Apj
-    P1, P2, P3, P4 = Si * np.conj(Sj), Di * np.conj(Dj), Di * np.conj(Sj), Si * np.conj(Dj)
-    return 0.25 * scale * (P1 + P2 + P3 - u * P4)
+    W = np.exp(-2j * np.pi * k / (2 * M))    # W_L^k, L = 2M
+    Zc = np.conj(Z[am])
+    S, D = Z + Zc, Z - Zc
+    X = 0.5 * (S - 1j * W * D)
+    X[0] = (Z[0].real + Z[0].imag) + 1j * (Z[0].real - Z[0].imag)
+    return X
+
+
+def pair_product(Xi, Xj, dims, scale=1.0):
+    """V (digit-transposed) whose inverse packed transform is the packed
+    cross-correlation r[2m] + i r[2m+1] (times M), from the two half spectra."""
+    M = len(Xi)
+    a = np.arange(M)
+    am = mirror_address(a, dims)
+    k = freq_of_address(dims)
+    C = scale * Xi * np.conj(Xj)
+    C0, CM = scale * Xi[0].real * Xj[0].real, scale * Xi[0].imag * Xj[0].imag
+    Cm = np.conj(C[am])
+    E = 0.5 * (C + Cm)
+    O = 0.5 * np.exp(+2j * np.pi * k / (2 * M)) * (C - Cm)
+    V = E + 1j * O
+    V[0] = 0.5 * (C0 + CM) + 0.5j * (C0 - CM)
+    return V
 
 
 def cc_model(x, y, dims, normalize=True):
     n = len(x)
     M = int(np.prod(dims))
     L = 2 * M
-    Zi = forward_packed(x, dims)
-    Zj = forward_packed(y, dims)
+    Zi = half_spectrum(forward_packed(x, dims), dims)
+    Zj = half_spectrum(forward_packed(y, dims), dims)
     scale = 1.0 / (np.linalg.norm(x) * np.linalg.norm(y)) if normalize else 1.0
     V = pair_product(Zi, Zj, dims, scale)
     zr = inverse_packed(V, dims) / M

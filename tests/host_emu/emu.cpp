@@ -79,6 +79,7 @@ static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_st
   DevTables<T> tb;
   tb.hi = ht.hi.data(); tb.lo = ht.lo.data();
   for (int a = 0; a < g.nd; ++a) tb.inner[a] = ht.inner[a].data();
+  tb.hi2 = ht.hi2.data(); tb.lo2 = ht.lo2.data(); tb.inner2 = ht.inner2.data();
 
   auto runner = [&](const PassParams<T>& p, bool row, int) { return run_pass(p, row); };
   const int per = spectra_per_signal(g);

@@ -6,7 +6,7 @@ import pytest
 
 from oracle import cc_oracle as orc
 from tests.emu_util import choose_dims, emu_cc
-from tests.algo_model import forward_packed
+from tests.algo_model import forward_packed, half_spectrum, freq_of_address
 
 MENU = [64, 80, 96, 100, 120, 128, 144, 150, 160, 180, 192, 200, 225, 240, 256, 300, 320, 400]
 
@@ -87,17 +87,27 @@ def test_zero_vector_gives_nan_like_reference():
     assert np.all(np.isnan(out)) and np.all(np.isnan(ref))
 
 
-def test_spectrum_layout_is_digit_transposed():
-    dims = (64, 80)
-    x = np.random.default_rng(2).standard_normal((1, 5000))
-    _, _, spec = emu_cc(x, [(0, 0)], dims=dims, want_spec=True)
-    Z = forward_packed(x[0], dims)
-    assert np.max(np.abs(spec[0] - Z)) < 1e-12 * np.max(np.abs(Z))
+@pytest.mark.parametrize("dims", [(64, 80), (225,), (100, 64, 96)])
+def test_spectrum_is_the_half_spectrum_in_digit_transposed_order(dims):
+    M = int(np.prod(dims))
+    x = np.random.default_rng(2).standard_normal((1, min(5000, 2 * M - 3)))
+    _, _, spec = emu_cc(x[:, :min(x.shape[1], M)], [(0, 0)], dims=dims, want_spec=True)
+    x = x[:, :min(x.shape[1], M)]
+    X = half_spectrum(forward_packed(x[0], dims), dims)
+    assert np.max(np.abs(spec[0] - X)) < 1e-12 * np.max(np.abs(X))
+    # ... which is numpy's rfft of the zero-padded signal, frequency k at its digit-transposed address
+    R = np.fft.rfft(x[0], 2 * M)
+    k = freq_of_address(dims)
+    ref = R[k].copy()
+    ref[0] = R[0].real + 1j * R[M].real
+    assert np.max(np.abs(spec[0] - ref)) < 1e-12 * np.max(np.abs(ref))
 
 
-def test_planner_named_shapes_are_exact():
-    for n in (21_600_000, 4_320_000):
-        assert int(np.prod(choose_dims(n))) == n
+def test_planner_named_shapes():
+    assert int(np.prod(choose_dims(21_600_000))) == 21_600_000
+    # 24 h @ 50 Hz: a 256-point row axis is preferred over the exact 180*150*160 (2.4 % more points)
+    d = choose_dims(4_320_000)
+    assert 4_320_000 <= int(np.prod(d)) <= 1.03 * 4_320_000 and d[-1] == 256
     d = choose_dims(900_000)
     assert 900_000 <= int(np.prod(d)) <= 1.03 * 900_000
     assert choose_dims(5) == (64,)

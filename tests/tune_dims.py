@@ -47,6 +47,8 @@ for dims in sorted(cands):
             row = 2 * dims[1] * dims[2]
             if n % row == 0 and -(-lb // row) * row + KL <= 2 * dims[0] * dims[1] * dims[2]:
                 lb = -(-lb // row) * row
+            elif -(-lb // 32) * 32 + KL <= 2 * dims[0] * dims[1] * dims[2]:
+                lb = -(-lb // 32) * 32
         plan = xb.CorrelationPlan(n, R, pairs, dtype=dtype, index_min=n - 1, index_max=n - 1 + KL, dims=dims,
                                   n_blocks=NB, block_len=lb)
     except Exception as e:

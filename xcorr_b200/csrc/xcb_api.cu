@@ -232,6 +232,9 @@ struct xcb_plan {
   void* d_hi = nullptr;
   void* d_lo = nullptr;
   void* d_inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+  void* d_hi2 = nullptr;
+  void* d_lo2 = nullptr;
+  void* d_inner2 = nullptr;
   Job* d_jobs = nullptr;
   const PassLauncher* launch[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
   // measurement aid (xcb_profile_*): events around every pass launch
@@ -252,18 +255,22 @@ struct LaunchTimer {
 };
 }  // namespace
 
+template <class T> static int upload_table(void** dst, const std::vector<cx<T>>& v) {
+  XCB_CUDA(cudaMalloc(dst, v.size() * sizeof(cx<T>)));
+  XCB_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+  return XCB_OK;
+}
+
 template <class T> static int upload_tables(xcb_plan* pl) {
   HostTables<T> ht;
   build_tables(pl->g, ht);
-  XCB_CUDA(cudaMalloc(&pl->d_hi, ht.hi.size() * sizeof(cx<T>)));
-  XCB_CUDA(cudaMemcpy(pl->d_hi, ht.hi.data(), ht.hi.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
-  XCB_CUDA(cudaMalloc(&pl->d_lo, ht.lo.size() * sizeof(cx<T>)));
-  XCB_CUDA(cudaMemcpy(pl->d_lo, ht.lo.data(), ht.lo.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
-  for (int a = 0; a < pl->g.nd; ++a) {
-    XCB_CUDA(cudaMalloc(&pl->d_inner[a], ht.inner[a].size() * sizeof(cx<T>)));
-    XCB_CUDA(cudaMemcpy(pl->d_inner[a], ht.inner[a].data(), ht.inner[a].size() * sizeof(cx<T>),
-                        cudaMemcpyHostToDevice));
-  }
+  int rc;
+  if ((rc = upload_table<T>(&pl->d_hi, ht.hi)) || (rc = upload_table<T>(&pl->d_lo, ht.lo))) return rc;
+  for (int a = 0; a < pl->g.nd; ++a)
+    if ((rc = upload_table<T>(&pl->d_inner[a], ht.inner[a]))) return rc;
+  if ((rc = upload_table<T>(&pl->d_hi2, ht.hi2)) || (rc = upload_table<T>(&pl->d_lo2, ht.lo2)) ||
+      (rc = upload_table<T>(&pl->d_inner2, ht.inner2)))
+    return rc;
   return XCB_OK;
 }
 
@@ -272,6 +279,9 @@ template <class T> static DevTables<T> dev_tables(const xcb_plan* pl) {
   tb.hi = static_cast<const cx<T>*>(pl->d_hi);
   tb.lo = static_cast<const cx<T>*>(pl->d_lo);
   for (int a = 0; a < pl->g.nd; ++a) tb.inner[a] = static_cast<const cx<T>*>(pl->d_inner[a]);
+  tb.hi2 = static_cast<const cx<T>*>(pl->d_hi2);
+  tb.lo2 = static_cast<const cx<T>*>(pl->d_lo2);
+  tb.inner2 = static_cast<const cx<T>*>(pl->d_inner2);
   return tb;
 }
 
@@ -282,6 +292,9 @@ extern "C" int xcb_plan_destroy(xcb_plan* pl) {
   cudaFree(pl->d_hi);
   cudaFree(pl->d_lo);
   for (int a = 0; a < kMaxDims; ++a) cudaFree(pl->d_inner[a]);
+  cudaFree(pl->d_hi2);
+  cudaFree(pl->d_lo2);
+  cudaFree(pl->d_inner2);
   cudaFree(pl->d_jobs);
   delete pl;
   return XCB_OK;

@@ -80,10 +80,16 @@ static int resident_ctas(const void* kernel, int threads, int smem) {
 }
 
 // TMA path: the pass input viewed as [batch][rows][128-byte column tiles] with
-// 16-byte aligned pitches.  Real input (first forward pass) additionally needs
-// whole rows (n a multiple of the row length): the zero padding is then the
-// tensor map's out-of-bounds fill and costs no traffic.
-template <class T> struct TmaGeom { bool ok; const void* base; int64_t row_elems, rows, row_pitch, batch_pitch; };
+// 16-byte aligned pitches.  Real input (first forward pass): the zero padding is
+// the tensor map's out-of-bounds fill and costs no traffic.  When the samples end
+// inside a row (n_real = rows_full * row + rem) two maps are used: column tiles
+// left of the end read rows_full + 1 rows, the others rows_full; this needs the
+// end to fall on a tile boundary (rem a multiple of 128 bytes).
+template <class T> struct TmaGeom {
+  bool ok;
+  const void* base;
+  int64_t row_elems, rows, rows_tail, split_col, row_pitch, batch_pitch;
+};
 
 template <class T> TmaGeom<T> tma_geom(const PassParams<T>& p) {
   TmaGeom<T> g;
@@ -100,15 +106,20 @@ template <class T> TmaGeom<T> tma_geom(const PassParams<T>& p) {
   g.row_elems = 2 * p.inner;
   g.row_pitch = g.row_elems * (int64_t)sizeof(T);
   if (g.row_pitch % 16 != 0) return g;
+  g.split_col = 0;
   if (p.load_mode == CL_REAL) {
-    if (p.n_real % g.row_elems != 0) return g;
-    g.rows = p.n_real / g.row_elems;
+    const int64_t tile_reals = 128 / (int64_t)sizeof(T);
+    const int64_t rem = p.n_real % g.row_elems;
+    if (rem % tile_reals != 0) return g;
+    g.rows_tail = p.n_real / g.row_elems;
+    g.rows = g.rows_tail + (rem ? 1 : 0);
+    g.split_col = rem / 2;
     g.batch_pitch = p.in_stride * (int64_t)sizeof(T);
   } else {
-    g.rows = p.M / p.inner;
+    g.rows = g.rows_tail = p.M / p.inner;
     g.batch_pitch = p.in_stride * (int64_t)sizeof(cx<T>);
   }
-  if (g.batch_pitch % 16 != 0 || g.rows < 1) return g;
+  if (g.batch_pitch % 16 != 0 || g.rows_tail < 1) return g;
   g.ok = true;
   return g;
 }
@@ -119,14 +130,21 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
   const TmaGeom<T> tg = tma_geom(p);
   if (tg.ok) {
     using K = ColTma<T, R1, R2>;
-    CUtensorMap map;
+    CUtensorMap map, map_tail;
     int rc = encode_col_tile_map(&map, sizeof(T) == 4 ? 0 : 1, tg.base, tg.row_elems, tg.rows, p.n_batch, tg.row_pitch,
                                  tg.batch_pitch, K::BOX_ROWS);
+    if (rc == 0) {
+      if (tg.rows_tail != tg.rows)
+        rc = encode_col_tile_map(&map_tail, sizeof(T) == 4 ? 0 : 1, tg.base, tg.row_elems, tg.rows_tail, p.n_batch,
+                                 tg.row_pitch, tg.batch_pitch, K::BOX_ROWS);
+      else
+        map_tail = map;
+    }
     if (rc == 0) {
       static int resident = 0;   // persistent grid: as many CTAs as stay resident
       if (!resident) resident = resident_ctas((const void*)xcb_col_pass_tma<T, R1, R2>, K::THREADS, K::SMEM);
       int64_t grid = nblocks < resident ? nblocks : resident;
-      xcb_col_pass_tma<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, p);
+      xcb_col_pass_tma<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       return (int)cudaGetLastError();
     }
   }
@@ -134,29 +152,9 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
   return (int)cudaGetLastError();
 }
 
-template <class T> bool bulk_eligible(const PassParams<T>& p) {
-  static int enabled = -1;
-  if (enabled < 0) { const char* e = getenv("XCB_BULK"); enabled = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured slower than the plain kernel
-  if (!enabled) return false;
-  if (p.store_mode == RS_EPI) return false;
-  if (p.load_mode == RL_PROLOGUE) return p.n_stack == 1 && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0;
-  if (p.load_mode == RL_CPLX)
-    return reinterpret_cast<uintptr_t>(p.in) % 16 == 0 && (p.in_stride * (int64_t)sizeof(cx<T>)) % 16 == 0;
-  return false;
-}
-
 template <class T, int R1, int R2> int launch_row(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
-  using K = RowBulk<T, R1, R2>;
-  PassParams<T> p = *static_cast<const PassParams<T>*>(params);
-  if (K::kRowsAligned && bulk_eligible(p)) {
-    p.tile_major = 0;        // the persistent variant walks tiles job-major
-    static int resident = 0;
-    if (!resident) resident = resident_ctas((const void*)xcb_row_pass_bulk<T, R1, R2>, K::THREADS, K::SMEM);
-    int64_t grid = nblocks < resident ? nblocks : resident;
-    xcb_row_pass_bulk<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(p);
-    return (int)cudaGetLastError();
-  }
+  const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
   xcb_row_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
@@ -169,9 +167,6 @@ template <class T, int R1, int R2> int prepare() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            ColTma<T, R1, R2>::SMEM);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(xcb_row_pass_bulk<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           RowBulk<T, R1, R2>::SMEM);
   return (int)e;
 }
 

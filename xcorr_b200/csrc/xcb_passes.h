@@ -29,7 +29,7 @@ namespace xcb {
 enum ColLoad : int32_t { CL_REAL = 0, CL_CPLX = 1, CL_CPLX_INV = 2 };
 enum ColStore : int32_t { CS_TW = 0, CS_CONJ = 1, CS_EPI = 2 };
 enum RowLoad : int32_t { RL_CPLX = 0, RL_REAL = 1, RL_PROLOGUE = 2 };
-enum RowStore : int32_t { RS_CPLX = 0, RS_CONJ = 1, RS_EPI = 2 };
+enum RowStore : int32_t { RS_CPLX = 0, RS_CONJ = 1, RS_EPI = 2, RS_HALF = 3 };
 
 constexpr int kMaxDims = 4;
 
@@ -68,6 +68,14 @@ template <class T> struct PassParams {
   int32_t tw_shift;
   uint32_t tw_mask;
   uint32_t tw_scale;         // col pass: exponent = tw_scale * column * index
+  // ---- half-step twiddles of the real <-> packed conversion: W_L^e (L = 2M), same split ----
+  const cx<T>* tw2_hi;
+  const cx<T>* tw2_lo;
+  const cx<T>* tw2_inner;    // W_{2N}^t, t in [0, N) (row axis)
+  // row pass: 1 = a tile is C/2 mirrored row pairs (ra, rb) in columns (2q, 2q+1)
+  // (forward last pass with the half-spectrum store, and the pair product)
+  int32_t pair_tiles;
+  int32_t pad1;
   // ---- pair product (inverse first pass) ----
   int32_t nd;                // number of passes p
   int32_t dims[kMaxDims];    // N_1..N_p
@@ -399,11 +407,13 @@ template <class T, int R1, int R2> struct RowPass {
     else { batch = bid / p.tiles_per_batch; tile = bid - batch * p.tiles_per_batch; }
   }
 
-  // column c of tile `tile` -> global row (pair product: rows ra / rb of pair slot c/2)
+  // column c of tile `tile` -> global row.  Pair tiles: columns (2q, 2q+1) hold
+  // the mirrored rows (ra, rb) of pair slot q: element e of ra is frequency k,
+  // element em of rb is frequency M - k.
   static XCB_HD RowInfo<T> row_info(const PassParams<T>& p, int64_t tile, int c) {
     RowInfo<T> ri;
     ri.row = -1; ri.store = 0; ri.pad = 0; ri.wrow.x = T(1); ri.wrow.y = T(0);
-    if (p.load_mode == RL_PROLOGUE) {
+    if (p.pair_tiles) {
       int64_t q = tile * (C / 2) + (c >> 1);
       if (q < p.n_pairs_rows) {
         int64_t ra = 0, rb = 0;
@@ -414,10 +424,14 @@ template <class T, int R1, int R2> struct RowPass {
           ra = p.region_lo[g] + tt;
           rb = p.region_hi[g] - 1 - tt;
         }
+        const bool self_dup = (c & 1) && ra == rb;     // a self-mirrored row lives in column 2q only
         ri.row = (c & 1) ? rb : ra;
-        ri.store = ((c & 1) && ra == rb) ? 0 : 1;
-        // both columns of a pair carry the twiddle of the first row
-        ri.wrow = tw_big(p, klow_of_row(p, ra));
+        ri.store = self_dup ? 0 : 1;
+        // forward: the duplicate column is not loaded at all (it would count twice in the norms)
+        if (self_dup && p.load_mode != RL_PROLOGUE) ri.row = -1;
+        // both columns of a pair carry the half-step twiddle W_L^klow of the first row
+        const uint32_t kl = klow_of_row(p, ra);
+        ri.wrow = cmul(ld_ro(p.tw2_hi + (kl >> p.tw_shift)), ld_ro(p.tw2_lo + (kl & p.tw_mask)));
       }
     } else {
       int64_t row = tile * C + c;
@@ -434,22 +448,31 @@ template <class T, int R1, int R2> struct RowPass {
     info_ptr(smem_raw)[ctx.tid] = row_info(p, tile, ctx.tid);
   }
 
-  // pair product of one element pair (k, M-k): A, B at (row ra, e); Am, Bm at
-  // (row rb, em).  Returns conj(V[k]) and conj(V[M-k]) scaled (the inverse runs
-  // as conj . FFT . conj).
-  static XCB_HD void pair_product(const cx<T>& A, const cx<T>& Am, const cx<T>& B, const cx<T>& Bm,
-                                  const cx<T>& wrow, const cx<T>& we, T scale, cx<T>& va, cx<T>& vb) {
-    const cx<T> Ap = cconj(Am), Bp = cconj(Bm);
-    const cx<T> Si = cadd(A, Ap), Di = csub(A, Ap);
-    const cx<T> Sj = cadd(B, Bp), Dj = csub(B, Bp);
-    const cx<T> P1 = cmulc(Si, Sj), P2 = cmulc(Di, Dj), P3 = cmulc(Di, Sj), P4 = cmulc(Si, Dj);
-    const cx<T> uw = cconj(cmul(wrow, we));        // conj(W_M^k), k = klow(row) + (M/N) e
-    const cx<T> uP4 = cmul(uw, P4);
-    const cx<T> s12 = cadd(P1, P2);
-    const cx<T> V = csub(cadd(s12, P3), uP4);      // V[k]
-    const cx<T> Vm = cadd(csub(s12, P3), uP4);     // conj(V[M-k])
-    va.x = V.x * scale;  va.y = -V.y * scale;
-    vb.x = Vm.x * scale; vb.y = Vm.y * scale;
+  // Spectra are stored as HALF SPECTRA of the real signals (store mode RS_HALF):
+  // address of frequency k holds X[k], k = 0..M-1, slot 0 holds (X[0], X[M]) (both
+  // real).  With Z the packed transform, S = Z[k] + conj(Z[M-k]), D = Z[k] -
+  // conj(Z[M-k]) and W = W_L^k:   X[k] = (S - i W D)/2,  X[M-k] = conj((S + i W D)/2).
+  static XCB_HD void untangle(const cx<T>& Zk, const cx<T>& Zm, const cx<T>& W, cx<T>& Xk, cx<T>& Xm) {
+    cx<T> S, D;
+    S.x = Zk.x + Zm.x; S.y = Zk.y - Zm.y;
+    D.x = Zk.x - Zm.x; D.y = Zk.y + Zm.y;
+    const cx<T> WD = cmul(W, D);                   // -i W D = (WD.y, -WD.x)
+    Xk.x = T(0.5) * (S.x + WD.y); Xk.y = T(0.5) * (S.y - WD.x);
+    Xm.x = T(0.5) * (S.x - WD.y); Xm.y = T(-0.5) * (S.y + WD.x);
+  }
+
+  // Cross-spectrum C[k] = sum X_i[k] conj(X_j[k]) of a real correlation r (length
+  // L) -> packed spectrum V of z[m] = r[2m] + i r[2m+1]:  E = (C[k] + conj(C[M-k]))/2,
+  // O = conj(W_L^k) (C[k] - conj(C[M-k]))/2,  V[k] = E + iO,  V[M-k] = conj(E) + i conj(O).
+  // Returns fs * conj(V[k]) and fs * conj(V[M-k]) with fs carrying the 1/2 (the
+  // inverse runs as conj . FFT . conj).
+  static XCB_HD void tangle(const cx<T>& Ck, const cx<T>& Cm, const cx<T>& W, T fs, cx<T>& va, cx<T>& vb) {
+    cx<T> E, D;
+    E.x = Ck.x + Cm.x; E.y = Ck.y - Cm.y;
+    D.x = Ck.x - Cm.x; D.y = Ck.y + Cm.y;
+    const cx<T> O = cmulc(D, W);                   // conj(W) D
+    va.x = fs * (E.x - O.y); va.y = -fs * (E.y + O.x);
+    vb.x = fs * (E.x + O.y); vb.y = fs * (E.y - O.x);
   }
 
   // Thread <-> data mapping of the cooperative phases: every column c of the
@@ -477,18 +500,21 @@ template <class T, int R1, int R2> struct RowPass {
       const bool ok = ia.row >= 0;
       const int64_t off_a = (ok ? ia.row : 0) * N, off_b = (ok ? rb : 0) * N;
       const bool row0 = ia.row == 0;
+      // one scale for all terms (block mode, plain pairs) is applied once at the end
+      const bool per_term = p.normalize && p.stack_sig_stride != 0;
+      T fs = T(0.5);
+      if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
       constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
       constexpr int PB = 2;
       for (int it0 = 0; it0 < ITER; it0 += PB) {
-        cx<T> va[PB], vb[PB];
+        cx<T> ca[PB], cb[PB];
 #pragma unroll
-        for (int u = 0; u < PB; ++u) va[u].x = va[u].y = vb[u].x = vb[u].y = T(0);
+        for (int u = 0; u < PB; ++u) ca[u].x = ca[u].y = cb[u].x = cb[u].y = T(0);
         for (int w = 0; w < p.n_stack; ++w) {
           const cx<T>* zi = p.spec + jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride);
           const cx<T>* zj = p.spec + jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride);
-          T scale = T(0.25);
-          if (p.normalize)
-            scale = T(0.25 * p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+          T sw = T(1);
+          if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
           cx<T> A[PB], Am[PB], B[PB], Bm[PB];
 #pragma unroll
           for (int u = 0; u < PB; ++u) {
@@ -502,10 +528,13 @@ template <class T, int R1, int R2> struct RowPass {
           for (int u = 0; u < PB; ++u) {
             const int e = t + (it0 + u) * 2 * TJ;
             if (ok && e < N) {
-              cx<T> pa, pb;
-              pair_product(A[u], Am[u], B[u], Bm[u], ia.wrow, ld_ro(p.tw_inner + e), scale, pa, pb);
-              va[u] = cadd(va[u], pa);
-              vb[u] = cadd(vb[u], pb);
+              const cx<T> a = {A[u].x * sw, A[u].y * sw}, am = {Am[u].x * sw, Am[u].y * sw};
+              if (row0 && e == 0) {                 // slot 0 = (X[0], X[M]), both real
+                ca[u].x += a.x * B[u].x; ca[u].y += a.y * B[u].y;
+              } else {
+                ca[u].x += a.x * B[u].x + a.y * B[u].y;    ca[u].y += a.y * B[u].x - a.x * B[u].y;
+                cb[u].x += am.x * Bm[u].x + am.y * Bm[u].y; cb[u].y += am.y * Bm[u].x - am.x * Bm[u].y;
+              }
             }
           }
         }
@@ -514,8 +543,18 @@ template <class T, int R1, int R2> struct RowPass {
           const int e = t + (it0 + u) * 2 * TJ;
           if (e < N) {
             const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-            smem[e * CP + 2 * lp] = va[u];
-            smem[em * CP + 2 * lp + 1] = vb[u];
+            cx<T> va, vb;
+            va.x = va.y = vb.x = vb.y = T(0);
+            if (ok) {
+              if (row0 && e == 0) {                 // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
+                va.x = fs * (ca[u].x + ca[u].y); va.y = -fs * (ca[u].x - ca[u].y);
+                vb = va;
+              } else {
+                tangle(ca[u], cb[u], cmul(ia.wrow, ld_ro(p.tw2_inner + e)), fs, va, vb);
+              }
+            }
+            smem[e * CP + 2 * lp] = va;
+            smem[em * CP + 2 * lp + 1] = vb;
           }
         }
       }
@@ -588,7 +627,27 @@ template <class T, int R1, int R2> struct RowPass {
     const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
     int64_t batch, tile_;
     decode(p, ctx.bid, batch, tile_);
-    if (p.store_mode == RS_EPI) {
+    if (p.store_mode == RS_HALF) {
+      // forward last pass: packed transform Z of the pair tile -> half spectrum X
+      const int lp = ctx.tid / (2 * TJ), t = ctx.tid - lp * (2 * TJ);
+      const RowInfo<T> ia = info[2 * lp];
+      const int64_t rb = info[2 * lp + 1].row;
+      if (ia.row >= 0) {
+        const bool self = rb < 0, row0 = ia.row == 0;
+        const int cm = self ? 2 * lp : 2 * lp + 1;
+        cx<T>* base = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride;
+        cx<T>* dst_a = base + ia.row * N;
+        cx<T>* dst_b = base + (self ? ia.row : rb) * N;
+        for (int e = t; e < N; e += 2 * TJ) {
+          const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+          cx<T> Xk, Xm;
+          untangle(smem[e * CP + 2 * lp], smem[em * CP + cm], cmul(ia.wrow, ld_ro(p.tw2_inner + e)), Xk, Xm);
+          if (row0 && e == 0) Xk.y = Xm.x;          // slot 0 = (X[0], X[M])
+          dst_a[e] = Xk;
+          if (!self) dst_b[em] = Xm;
+        }
+      }
+    } else if (p.store_mode == RS_EPI) {
       T* outp = p.ccf + p.jobs[batch].out_off;
       for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
         int c = idx / N, e = idx - c * N;

@@ -71,15 +71,20 @@ inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
       double m = 1;
       int mx = 0;
       bool good_last = false;     // a length <= 256 and multiple of 16 can be the contiguous (row) axis
+      bool has256 = false;
       for (int i = 0; i < p; ++i) {
         const int N = kMenu[idx[i]].N;
         m *= N;
         if (N > mx) mx = N;
         if (N <= 256 && N % 16 == 0) good_last = true;
+        if (N == 256) has256 = true;
       }
       if (m >= (double)n_min && m < 2147483648.0) {
-        // primary: HBM traffic; ties: row axis that fits two CTAs per SM, then balanced lengths
-        double cost = m * (p + 0.5) * (1.0 + (good_last || p == 1 ? 0.0 : 1e-3) + 1e-6 * mx);
+        // primary: HBM traffic; ties: row axis that fits two CTAs per SM, then balanced lengths.
+        // A 256-point row axis (16 x 16, every thread busy in both radix stages, shift/mask
+        // indexing) runs the row passes -- pair product, forward last -- ~20 % faster
+        // (profiles/tune_r01_dims.log), worth ~6 % more points.
+        double cost = m * (p + 0.5 - (has256 && p > 1 ? 0.2 : 0.0)) * (1.0 + (good_last || p == 1 ? 0.0 : 1e-3) + 1e-6 * mx);
         if (cost < best) { best = cost; bn = p; for (int i = 0; i < p; ++i) bd[i] = kMenu[idx[i]].N; }
       }
       int k = p - 1;
@@ -169,6 +174,7 @@ template <class T> inline cx<T> unit_root(int64_t num, int64_t den) {   // exp(-
 template <class T> struct HostTables {
   std::vector<cx<T>> hi, lo;
   std::vector<cx<T>> inner[kMaxDims];
+  std::vector<cx<T>> hi2, lo2, inner2;     // W_L^e (L = 2M) and W_{2 N_p}^t: real <-> packed conversion
 };
 
 template <class T> inline void build_tables(const PlanGeom& g, HostTables<T>& t) {
@@ -182,12 +188,22 @@ template <class T> inline void build_tables(const PlanGeom& g, HostTables<T>& t)
     t.inner[a].resize(g.dims[a]);
     for (int k = 0; k < g.dims[a]; ++k) t.inner[a][k] = unit_root<T>(k, g.dims[a]);
   }
+  t.lo2.resize(step);
+  for (int64_t j = 0; j < step; ++j) t.lo2[j] = unit_root<T>(j, g.L);
+  t.hi2.resize(nh);
+  for (int64_t h = 0; h < nh; ++h) t.hi2[h] = unit_root<T>(h * step, g.L);
+  const int Np = g.dims[g.nd - 1];
+  t.inner2.resize(Np);
+  for (int k = 0; k < Np; ++k) t.inner2[k] = unit_root<T>(k, 2 * (int64_t)Np);
 }
 
 template <class T> struct DevTables {      // pointers valid where the passes run
   const cx<T>* hi = nullptr;
   const cx<T>* lo = nullptr;
   const cx<T>* inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
+  const cx<T>* hi2 = nullptr;
+  const cx<T>* lo2 = nullptr;
+  const cx<T>* inner2 = nullptr;
 };
 
 template <class T> inline int tile_cols() { return 128 / (2 * (int)sizeof(T)); }
@@ -202,6 +218,13 @@ template <class T> inline void pass_common(PassParams<T>& p, const PlanGeom& g, 
   p.tw_inner = tb.inner[a];
   p.tw_shift = g.tw_shift;
   p.tw_mask = (uint32_t)((1LL << g.tw_shift) - 1);
+  p.tw2_hi = tb.hi2;
+  p.tw2_lo = tb.lo2;
+  p.tw2_inner = tb.inner2;
+  p.n_regions = g.n_regions;
+  for (int r = 0; r < kMaxDims; ++r) { p.region_lo[r] = g.region_lo[r]; p.region_hi[r] = g.region_hi[r]; }
+  for (int r = 0; r <= kMaxDims; ++r) p.pair_start[r] = g.pair_start[r];
+  p.n_pairs_rows = g.n_pairs_rows;
   p.nd = g.nd;
   for (int i = 0; i < kMaxDims; ++i) p.dims[i] = g.dims[i];
   p.n = g.n;
@@ -244,8 +267,12 @@ inline PassParams<T> make_forward_pass(const PlanGeom& g, const DevTables<T>& tb
     p.load_mode = (a == 0) ? CL_REAL : CL_CPLX;
     p.store_mode = CS_TW;
   } else {
+    // last pass: tiles of mirrored row pairs, packed transform -> half spectrum on store
     p.load_mode = (a == 0) ? RL_REAL : RL_CPLX;
-    p.store_mode = RS_CPLX;
+    p.store_mode = RS_HALF;
+    p.pair_tiles = 1;
+    const int C = tile_cols<T>();
+    p.tiles_per_batch = (g.n_pairs_rows + (C / 2) - 1) / (C / 2);
   }
   return p;
 }
@@ -286,10 +313,6 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   p.escale = (T)(1.0 / (double)g.M);
   p.unbiased = f.unbiased;
   p.accumulate = f.accumulate;
-  p.n_regions = g.n_regions;
-  for (int r = 0; r < kMaxDims; ++r) { p.region_lo[r] = g.region_lo[r]; p.region_hi[r] = g.region_hi[r]; }
-  for (int r = 0; r <= kMaxDims; ++r) p.pair_start[r] = g.pair_start[r];
-  p.n_pairs_rows = g.n_pairs_rows;
   // rows k of the last column pass (element m = k*S[1] + col) that can hold a kept lag
   p.keep_lo[0] = p.keep_lo[1] = 0;
   p.keep_hi[0] = p.keep_hi[1] = 0;
@@ -311,6 +334,7 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   }
   if (a == g.nd - 1) {
     p.tile_major = 1;
+    p.pair_tiles = 1;
     p.load_mode = RL_PROLOGUE;
     p.store_mode = (g.nd == 1) ? RS_EPI : RS_CONJ;
     p.tiles_per_batch = (g.n_pairs_rows + (C / 2) - 1) / (C / 2);
@@ -327,7 +351,7 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
 // passes, nd..2nd-1 inverse passes of the same axes.  Returns false on failure.
 // ---------------------------------------------------------------------------
 inline int64_t pass0_tiles(const PlanGeom& g, int C) {
-  return g.nd > 1 ? (g.M / g.S[0]) * ((g.S[1] + C - 1) / C) : (g.M / g.dims[0] + C - 1) / C;
+  return g.nd > 1 ? (g.M / g.S[0]) * ((g.S[1] + C - 1) / C) : (g.n_pairs_rows + (C / 2) - 1) / (C / 2);
 }
 
 // Spectra per input signal: 1, or in block mode the segments that need their own
@@ -428,11 +452,17 @@ inline bool plan_choose_blocks(int64_t n, int64_t n_lags, int n_recv, int n_pair
     if (!plan_choose_dims((lb + n_lags + 1) / 2, bd, &bnd)) continue;
     int64_t M = 1;
     for (int a = 0; a < bnd; ++a) M *= bd[a];
-    // whole rows of the first pass (row = 2*S[1] reals) keep every piece TMA-legal
+    // TMA-legal pieces: whole rows of the first pass (row = 2*S[1] reals), else
+    // whole 128-byte column tiles (32 reals covers both dtypes)
     int64_t row = 2 * (M / bd[0]);
+    bool rounded = false;
     if (bnd > 1 && n % row == 0) {
       int64_t lb_rows = (lb + row - 1) / row * row;
-      if (lb_rows + n_lags <= 2 * M) lb = lb_rows;
+      if (lb_rows + n_lags <= 2 * M) { lb = lb_rows; rounded = true; }
+    }
+    if (!rounded) {
+      int64_t lb32 = (lb + 31) / 32 * 32;
+      if (lb32 + n_lags <= 2 * M) lb = lb32;
     }
     if (lb + n_lags > 2 * M) continue;
     int Beff = (int)((n + lb - 1) / lb);

@@ -81,7 +81,8 @@ template <class T, int R1, int R2> struct ColTma {
 
 template <class T, int R1, int R2>
 __global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, 2)
-xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ PassParams<T> p) {
+xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
+                 const int64_t split_col, const __grid_constant__ PassParams<T> p) {
   using K = ColTma<T, R1, R2>;
   constexpr int N = K::N, C = K::C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -102,9 +103,11 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const int32_t y0 = (int32_t)(o * N);                          // row within the signal
     unsigned char* dst = smem_raw + s * K::SLOT_BYTES;
     mbar_expect_tx(&full[s], (uint32_t)K::SLOT_BYTES);
+    // real input ending inside a row: column tiles left of the end see one more valid row
+    const CUtensorMap* map = (cb * C < split_col) ? &tmap : &tmap_tail;
 #pragma unroll
     for (int b = 0; b < K::NBOX; ++b)
-      tma_load_3d(dst + b * (K::SLOT_BYTES / K::NBOX), &tmap, &full[s], x0, y0 + b * K::BOX_ROWS, (int32_t)batch);
+      tma_load_3d(dst + b * (K::SLOT_BYTES / K::NBOX), map, &full[s], x0, y0 + b * K::BOX_ROWS, (int32_t)batch);
   };
 
   if (tid == 0) {
@@ -201,148 +204,6 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         }
       }
     }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Persistent row pass with bulk-async staging
-// ---------------------------------------------------------------------------
-// A tile is C contiguous rows (forward last pass) or C/2 mirrored row pairs of
-// two spectra (pair product).  Warp 0 fetches the NEXT tile's rows with
-// cp.async.bulk (one instruction per row, completion on an mbarrier) into a
-// staging area while all warps transform the current tile in the padded
-// transposed buffer; staging -> buffer is a shared-memory pass (pair product
-// fused there), so no thread ever waits on an HBM load.
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <class T, int R1, int R2> struct RowBulk {
-  using G = Cfg<T, R1, R2>;
-  static constexpr int N = G::N, C = G::C, CP = G::CP, THREADS = G::THREADS;
-  static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
-  static constexpr int FFT_BYTES = N * CP * 2 * (int)sizeof(T);
-  static constexpr int INFO_OFF = FFT_BYTES;                          // == RowPass::info_ptr offset
-  static constexpr int STAGE_OFF = (FFT_BYTES + 2 * C * 32 + 127) / 128 * 128;
-  static constexpr int STAGE_BYTES = 2 * C * ROW_BYTES;               // pair product: 4 x C/2 rows
-  static constexpr int BAR_OFF = STAGE_OFF + STAGE_BYTES;
-  static constexpr int SMEM = BAR_OFF + 64;
-  static constexpr bool kRowsAligned = (ROW_BYTES % 16) == 0;
-};
-
-template <class T, int R1, int R2>
-__global__ void __launch_bounds__(RowBulk<T, R1, R2>::THREADS, 2)
-xcb_row_pass_bulk(const __grid_constant__ PassParams<T> p) {
-  using K = RowBulk<T, R1, R2>;
-  using P = RowPass<T, R1, R2>;
-  constexpr int N = K::N, C = K::C, CP = K::CP, H = K::C / 2;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  cx<T>* fft = reinterpret_cast<cx<T>*>(smem_raw);
-  RowInfo<T>* info2 = reinterpret_cast<RowInfo<T>*>(smem_raw + K::INFO_OFF);    // [2][C]
-  cx<T>* stage = reinterpret_cast<cx<T>*>(smem_raw + K::STAGE_OFF);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + K::BAR_OFF);
-
-  const int tid = threadIdx.x;
-  const bool prologue = p.load_mode == RL_PROLOGUE;
-  const int64_t ntiles = (int64_t)p.n_batch * p.tiles_per_batch;
-  const int64_t stride_tiles = gridDim.x;
-
-  // warp 0: bookkeeping of `tile` into info2[slot], then the bulk copies
-  auto prefetch = [&](int64_t tile, int slot) {
-    const int64_t batch = tile / p.tiles_per_batch;
-    const int64_t tl = tile - batch * p.tiles_per_batch;
-    RowInfo<T>* inf = info2 + slot * C;
-    if (tid < C) inf[tid] = P::row_info(p, tl, tid);
-    __syncwarp();
-    if (prologue) {
-      const Job jb = p.jobs[batch];
-      const int kind = tid / H, lp = tid % H;           // 0: Zi(ra) 1: Zj(ra) 2: Zi(rb) 3: Zj(rb)
-      int64_t row = -1;
-      if (tid < 4 * H) row = inf[2 * lp + (kind >> 1)].row;
-      const bool valid = row >= 0;
-      const unsigned mask = __ballot_sync(0xffffffffu, valid);
-      if (tid == 0) mbar_expect_tx(full, (uint32_t)(__popc(mask) * K::ROW_BYTES));
-      __syncwarp();
-      if (valid) {
-        const cx<T>* src = p.spec + ((kind & 1) ? jb.spec_j : jb.spec_i) + row * N;
-        bulk_load(stage + (size_t)(kind * H + lp) * N, src, (uint32_t)K::ROW_BYTES, full);
-      }
-    } else if (tid == 0) {
-      int64_t nrows = p.rows - tl * C;
-      if (nrows > C) nrows = C;
-      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + batch * p.in_stride + tl * (int64_t)(C * N);
-      mbar_expect_tx(full, (uint32_t)(nrows * K::ROW_BYTES));
-      bulk_load(stage, src, (uint32_t)(nrows * K::ROW_BYTES), full);
-    }
-  };
-
-  if (tid == 0) { mbar_init(full, 1); fence_barrier_init(); }
-  __syncthreads();
-  if (tid < 32 && (int64_t)blockIdx.x < ntiles) prefetch(blockIdx.x, 0);
-
-  typename P::Ctx ctx;
-  ctx.tid = tid;
-  uint32_t it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += stride_tiles, ++it) {
-    const int slot = (int)(it & 1u);
-    const RowInfo<T>* info = info2 + slot * C;
-    ctx.bid = tile;
-    const int64_t batch = tile / p.tiles_per_batch;
-    __syncthreads();                       // info[slot] visible; previous tile's store phase has left `fft`
-    mbar_wait(full, it & 1u);
-    if (prologue) {
-      const Job jb = p.jobs[batch];
-      T scale = T(0.25);
-      if (p.normalize) scale = T(0.25 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
-      constexpr int TJ = P::TJ;
-      const int lp = tid / (2 * TJ), t = tid - lp * (2 * TJ);    // pair slot owned by 2*TJ threads
-      const RowInfo<T> ia = info[2 * lp];
-      const bool ok = ia.row >= 0, row0 = ia.row == 0;
-      const cx<T>* sA = stage + (0 * H + lp) * N;
-      const cx<T>* sB = stage + (1 * H + lp) * N;
-      const cx<T>* sAm = stage + (2 * H + lp) * N;
-      const cx<T>* sBm = stage + (3 * H + lp) * N;
-      constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
-#pragma unroll
-      for (int i = 0; i < ITER; ++i) {
-        const int e = t + i * 2 * TJ;
-        if (e < N) {
-          const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-          cx<T> va, vb;
-          va.x = va.y = vb.x = vb.y = T(0);
-          if (ok) P::pair_product(sA[e], sAm[em], sB[e], sBm[em], ia.wrow, ld_ro(p.tw_inner + e), scale, va, vb);
-          fft[e * CP + 2 * lp] = va;
-          fft[em * CP + 2 * lp + 1] = vb;
-        }
-      }
-    } else {
-      constexpr int TJ = P::TJ;
-      const int c = tid / TJ, t = tid - c * TJ;
-      const bool ok = info[c].row >= 0;
-      const cx<T>* src = stage + c * N + t;
-      cx<T>* dst = fft + t * CP + c;
-#pragma unroll
-      for (int i = 0; i < P::RMIN; ++i) {
-        cx<T> v; v.x = v.y = T(0);
-        if (ok) v = src[i * TJ];
-        dst[i * TJ * CP] = v;
-      }
-    }
-    fence_proxy_async_smem();              // our reads of `stage` precede its next async fill
-    __syncthreads();
-    if (tid < 32) {
-      const int64_t next = tile + stride_tiles;
-      if (next < ntiles) prefetch(next, slot ^ 1);
-    }
-    P::phase_s1_read(p, ctx, smem_raw);
-    __syncthreads();
-    P::phase_s1_write(p, ctx, smem_raw);
-    __syncthreads();
-    P::phase_s2(p, ctx, smem_raw);
-    __syncthreads();
-    P::phase_store(p, ctx, smem_raw, info);
   }
 }
 
