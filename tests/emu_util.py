@@ -39,6 +39,16 @@ def choose_dims(n):
     return tuple(d[i] for i in range(nd.value))
 
 
+def choose_blocks(n, n_lags, n_recv, n_pairs):
+    """(n_blocks, dims, block_len) of the automatic planner (n_blocks == 1: classic transform)."""
+    d = (ctypes.c_int * 4)()
+    nd = ctypes.c_int()
+    bl = ctypes.c_int64()
+    nb = lib().emu_choose_blocks(ctypes.c_int64(n), ctypes.c_int64(n_lags), n_recv, n_pairs, d, ctypes.byref(nd),
+                                 ctypes.byref(bl))
+    return nb, tuple(d[i] for i in range(nd.value)) if nb > 1 else choose_dims(n), bl.value
+
+
 def emu_cc(x, pairs, dims=None, i0=None, i1=None, normalize=True, unbiased=False,
            want_spec=False, n_stack=1, n_blocks=1, block_len=0):
     """x: (S, n) float32/float64.  Returns (ccf[P, K], sumsq[S], spec or None)."""

@@ -26,18 +26,34 @@ template <class T, int R1, int R2> static void emu_col(const PassParams<T>& p) {
 }
 
 template <class T, int R1, int R2> static void emu_row(const PassParams<T>& p) {
-  using P = RowPass<T, R1, R2>;
   using G = Cfg<T, R1, R2>;
   std::vector<unsigned char> smem(G::ROW_SMEM + 64);
-  std::vector<typename P::Ctx> ctx(G::THREADS);
   int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
-  for (int64_t b = 0; b < nblocks; ++b) {
-    for (int t = 0; t < G::THREADS; ++t) { ctx[t].tid = t; ctx[t].bid = b; P::phase_info(p, ctx[t], smem.data()); }
-    for (int t = 0; t < G::THREADS; ++t) P::phase_load(p, ctx[t], smem.data());
-    for (int t = 0; t < G::THREADS; ++t) P::phase_s1_read(p, ctx[t], smem.data());
-    for (int t = 0; t < G::THREADS; ++t) P::phase_s1_write(p, ctx[t], smem.data());
-    for (int t = 0; t < G::THREADS; ++t) P::phase_s2(p, ctx[t], smem.data());
-    for (int t = 0; t < G::THREADS; ++t) P::phase_store(p, ctx[t], smem.data());
+  if constexpr (R1 == 16) {          // warp-synchronous variant: phases are separated by __syncwarp on the device
+    using P = RowWarp<T, R1, R2>;
+    std::vector<typename P::Ctx> ctx(G::THREADS);
+    std::vector<typename P::Slot> slot(G::THREADS);
+    for (int64_t b = 0; b < nblocks; ++b) {
+      for (int t = 0; t < G::THREADS; ++t) {
+        ctx[t].tid = t; ctx[t].bid = b;
+        slot[t] = P::decode(p, ctx[t], smem.data());
+        P::phase_a(p, ctx[t], slot[t], smem.data());
+      }
+      for (int t = 0; t < G::THREADS; ++t) P::phase_b(p, ctx[t], slot[t]);
+      for (int t = 0; t < G::THREADS; ++t) P::phase_c(p, ctx[t], slot[t]);
+      for (int t = 0; t < G::THREADS; ++t) P::phase_d(p, ctx[t], slot[t], smem.data());
+    }
+  } else {
+    using P = RowPass<T, R1, R2>;
+    std::vector<typename P::Ctx> ctx(G::THREADS);
+    for (int64_t b = 0; b < nblocks; ++b) {
+      for (int t = 0; t < G::THREADS; ++t) { ctx[t].tid = t; ctx[t].bid = b; P::phase_info(p, ctx[t], smem.data()); }
+      for (int t = 0; t < G::THREADS; ++t) P::phase_load(p, ctx[t], smem.data());
+      for (int t = 0; t < G::THREADS; ++t) P::phase_s1_read(p, ctx[t], smem.data());
+      for (int t = 0; t < G::THREADS; ++t) P::phase_s1_write(p, ctx[t], smem.data());
+      for (int t = 0; t < G::THREADS; ++t) P::phase_s2(p, ctx[t], smem.data());
+      for (int t = 0; t < G::THREADS; ++t) P::phase_store(p, ctx[t], smem.data());
+    }
   }
 }
 
@@ -109,6 +125,13 @@ static int emu_cc_t(int64_t n, const int* dims, int nd, const T* x, int64_t x_st
 extern "C" {
 
 int emu_choose_dims(int64_t n, int* dims, int* nd) { return plan_choose_dims(n, dims, nd) ? 0 : -1; }
+
+// block planner as xcb_plan_create runs it; returns the number of blocks (1 = classic transform)
+int emu_choose_blocks(int64_t n, int64_t n_lags, int n_recv, int n_pairs, int* dims, int* nd, int64_t* block_len) {
+  int nb = 1;
+  if (!plan_choose_blocks(n, n_lags, n_recv, n_pairs, dims, nd, &nb, block_len)) return 1;
+  return nb;
+}
 
 // dtype: 0 = f32, 1 = f64.  x: [n_signals][x_stride]; pairs: [n_pairs][2]; out: [n_pairs][i1-i0]
 int emu_cc(int dtype, int64_t n, const int* dims, int nd, const void* x, int64_t x_stride, int n_signals,

@@ -177,7 +177,7 @@ def test_day_at_50hz_against_oracle(xb, orc, dtype):
     rec = orc.synthetic_receivers(2, n, seed=1000, delay=137)
     i0, i1 = n - 1, n - 1 + 1_620_000
     plan = xb.CorrelationPlan(n, 2, [(0, 1)], dtype=tdt, index_min=i0, index_max=i1)
-    assert int(np.prod(plan.dims)) == n
+    assert n <= int(np.prod(plan.dims)) <= 1.03 * n
     got = plan(torch.from_numpy(rec.astype(dtype)).cuda()).cpu().numpy()[0, 0]
     ref = orc.cc_smooth(rec[0], rec[1])
     peak = np.max(np.abs(ref))
@@ -201,7 +201,7 @@ def test_day_at_250hz_full_size(xb, orc):
     i0, i1 = n - 1, n - 1 + 8_100_000
     pairs = [(0, 1), (0, 2), (1, 2), (1, 0)]
     plan = xb.CorrelationPlan(n, 3, pairs, dtype=torch.float32, index_min=i0, index_max=i1)
-    assert int(np.prod(plan.dims)) == n
+    assert n <= int(np.prod(plan.dims)) <= 1.03 * n
     x = torch.from_numpy(rec).cuda()
     ccf = plan(x)
     idx, val = plan.argmax(ccf)
@@ -233,7 +233,7 @@ def test_block_mode_equals_classic_transform(xb, orc, dtype):
     pairs = xb.all_pairs(R)
     rec = np.stack([orc.synthetic_receivers(R, n, seed=400 + w, delay=61) for w in range(W)], axis=1)
     x = torch.from_numpy(rec.astype(dtype)).cuda()
-    for lag0, K in ((0, 45_000), (1_000, 30_000)):
+    for lag0, K in ((0, 30_000), (1_000, 25_000)):
         i0 = n - 1 + lag0
         auto = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + K)
         classic = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + K, n_blocks=1)

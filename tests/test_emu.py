@@ -171,3 +171,40 @@ def test_block_planner_picks_blocks_for_cropped_day():
     # a single pair of two receivers: the classic transform stays cheaper
     emu_cc(x[:2], [(0, 1)], dims=None, i0=39_999, i1=39_999 + 15_000, n_blocks=-1)
     assert emu_cc.last_blocks == 1
+
+
+# ---- warp-synchronous row pass (row axis 16 x R2: 128, 160, 192, 240, 256) ----
+@pytest.mark.parametrize("dims", [(64, 128), (80, 240), (100, 160), (96, 192), (64, 64, 256), (150, 256)])
+def test_warp_row_pass_as_last_axis_f64(dims):
+    M = int(np.prod(dims))
+    n = min(M, 200_000) - 5
+    x = orc.synthetic_receivers(3, n, seed=M % 1000, delay=137)
+    _check(x, [(0, 1), (2, 1)], dims, 1e-13)
+    i0 = n - 1 - 1000
+    _check(x, [(0, 2)], dims, 1e-12, i0=i0, i1=i0 + 4001, unbiased=True)
+
+
+@pytest.mark.parametrize("dims", [(64, 256), (80, 240), (64, 64, 128)])
+def test_warp_row_pass_f32(dims):
+    M = int(np.prod(dims))
+    x = orc.synthetic_receivers(3, min(M, 150_000) - 1, seed=11, delay=29).astype(np.float32)
+    _check(x, [(0, 1), (1, 2)], dims, 1e-5)
+
+
+def test_warp_row_pass_blocks_and_stacking():
+    n, K = 30_000, 9_000
+    x = orc.synthetic_receivers(3, n, seed=77, delay=41)
+    pairs = [(0, 1), (2, 1), (0, 2)]
+    for lag0 in (0, -4500):
+        i0 = n - 1 + lag0
+        out, ss, _ = emu_cc(x, pairs, dims=(64, 256), i0=i0, i1=i0 + K, n_blocks=2, block_len=15_008)
+        assert emu_cc.last_blocks == 2
+        for q, (i, j) in enumerate(pairs):
+            ref = orc.cc(x[i], x[j], unbiased=False)
+            assert np.max(np.abs(out[q] - ref[i0:i0 + K])) <= 1e-13 * np.max(np.abs(ref)), (lag0, q)
+    R, W, nw = 3, 3, 9000
+    rec = np.stack([orc.synthetic_receivers(R, nw, seed=90 + w, delay=17) for w in range(W)], axis=1)
+    out, _, _ = emu_cc(rec.reshape(R * W, nw), pairs, dims=(64, 160), n_stack=W)
+    for q, (i, j) in enumerate(pairs):
+        ref = sum(orc.cc(rec[i, w], rec[j, w], unbiased=False) for w in range(W))
+        assert np.max(np.abs(out[q] - ref)) <= 1e-13 * np.max(np.abs(ref))

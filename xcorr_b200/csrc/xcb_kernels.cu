@@ -53,21 +53,38 @@ template <class T, int R1, int R2>
 __global__ void __launch_bounds__(Cfg<T, R1, R2>::THREADS)
 xcb_row_pass(const __grid_constant__ PassParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  using P = RowPass<T, R1, R2>;
-  typename P::Ctx ctx;
-  ctx.tid = threadIdx.x;
-  ctx.bid = blockIdx.x;
-  P::phase_info(p, ctx, smem);
-  __syncthreads();
-  P::phase_load(p, ctx, smem);
-  __syncthreads();
-  P::phase_s1_read(p, ctx, smem);
-  __syncthreads();
-  P::phase_s1_write(p, ctx, smem);
-  __syncthreads();
-  P::phase_s2(p, ctx, smem);
-  __syncthreads();
-  P::phase_store(p, ctx, smem);
+  if constexpr (R1 == 16) {
+    // one warp per mirrored row pair, warp-synchronous (RowWarp in xcb_passes.h)
+    using P = RowWarp<T, R1, R2>;
+    typename P::Ctx ctx;
+    ctx.tid = threadIdx.x;
+    ctx.bid = blockIdx.x;
+    const typename P::Slot slot = P::decode(p, ctx, smem);
+    P::phase_a(p, ctx, slot, smem);
+    __syncwarp();
+    P::phase_b(p, ctx, slot);
+    __syncwarp();
+    P::phase_c(p, ctx, slot);
+    __syncwarp();
+    if (p.sumsq_partial && p.load_mode == RL_REAL) __syncthreads();   // single-pass plans: norms of the tile
+    P::phase_d(p, ctx, slot, smem);
+  } else {
+    using P = RowPass<T, R1, R2>;
+    typename P::Ctx ctx;
+    ctx.tid = threadIdx.x;
+    ctx.bid = blockIdx.x;
+    P::phase_info(p, ctx, smem);
+    if (p.load_mode != RL_PROLOGUE) __syncthreads();   // the pair product derives its rows itself
+    P::phase_load(p, ctx, smem);
+    __syncthreads();
+    P::phase_s1_read(p, ctx, smem);
+    __syncthreads();
+    P::phase_s1_write(p, ctx, smem);
+    __syncthreads();
+    P::phase_s2(p, ctx, smem);
+    __syncthreads();
+    P::phase_store(p, ctx, smem);
+  }
 }
 
 static int resident_ctas(const void* kernel, int threads, int smem) {

@@ -395,8 +395,12 @@ template <class T, int R1, int R2> struct RowPass {
   static XCB_HD uint32_t klow_of_row(const PassParams<T>& p, int64_t row) {
     // row = ((k_1 N_2 + k_2) N_3 + ...) + k_{p-1};  klow = sum k_a * (N_1..N_{a-1})
     uint32_t digits[kMaxDims];
-    int64_t r = row;
-    for (int a = p.nd - 2; a >= 0; --a) { digits[a] = (uint32_t)(r % p.dims[a]); r /= p.dims[a]; }
+    uint32_t r = (uint32_t)row;            // rows < M < 2^31
+    for (int a = p.nd - 2; a >= 0; --a) {
+      const uint32_t d = (uint32_t)p.dims[a], qq = r / d;
+      digits[a] = r - qq * d;
+      r = qq;
+    }
     uint32_t k = 0, base = 1;
     for (int a = 0; a < p.nd - 1; ++a) { k += digits[a] * base; base *= (uint32_t)p.dims[a]; }
     return k;
@@ -407,6 +411,20 @@ template <class T, int R1, int R2> struct RowPass {
     else { batch = bid / p.tiles_per_batch; tile = bid - batch * p.tiles_per_batch; }
   }
 
+  // row pair q -> its two mirrored rows (pair 0 = row 0 with itself); false past the last pair
+  static XCB_HD bool pair_rows(const PassParams<T>& p, int64_t q, int64_t& ra, int64_t& rb) {
+    ra = rb = 0;
+    if (q >= p.n_pairs_rows) return false;
+    if (q > 0) {
+      int g = 0;
+      while (g + 1 < p.n_regions && q >= p.pair_start[g + 1]) ++g;
+      const int64_t tt = q - p.pair_start[g];
+      ra = p.region_lo[g] + tt;
+      rb = p.region_hi[g] - 1 - tt;
+    }
+    return true;
+  }
+
   // column c of tile `tile` -> global row.  Pair tiles: columns (2q, 2q+1) hold
   // the mirrored rows (ra, rb) of pair slot q: element e of ra is frequency k,
   // element em of rb is frequency M - k.
@@ -414,16 +432,8 @@ template <class T, int R1, int R2> struct RowPass {
     RowInfo<T> ri;
     ri.row = -1; ri.store = 0; ri.pad = 0; ri.wrow.x = T(1); ri.wrow.y = T(0);
     if (p.pair_tiles) {
-      int64_t q = tile * (C / 2) + (c >> 1);
-      if (q < p.n_pairs_rows) {
-        int64_t ra = 0, rb = 0;
-        if (q > 0) {
-          int g = 0;
-          while (g + 1 < p.n_regions && q >= p.pair_start[g + 1]) ++g;
-          int64_t tt = q - p.pair_start[g];
-          ra = p.region_lo[g] + tt;
-          rb = p.region_hi[g] - 1 - tt;
-        }
+      int64_t ra, rb;
+      if (pair_rows(p, tile * (C / 2) + (c >> 1), ra, rb)) {
         const bool self_dup = (c & 1) && ra == rb;     // a self-mirrored row lives in column 2q only
         ri.row = (c & 1) ? rb : ra;
         ri.store = self_dup ? 0 : 1;
@@ -492,71 +502,86 @@ template <class T, int R1, int R2> struct RowPass {
     decode(p, ctx.bid, batch, tile_);
     ctx.ss = 0.0;
     if (p.load_mode == RL_PROLOGUE) {
-      // pair slot lp is owned by 2*TJ threads
-      const int lp = ctx.tid / (2 * TJ), t = ctx.tid - lp * (2 * TJ);
+      // Pair slot lp (rows ra, rb) is owned by 2*TJ threads; nothing here reads
+      // `info`, so the kernel does not wait for phase_info before loading.
+      constexpr int TS = 2 * TJ;
+      constexpr int ITER = (N + TS - 1) / TS;
+      constexpr bool EXACT = (N % TS) == 0;
+      constexpr int PB = (ITER >= 4 && sizeof(T) == 4) ? 4 : (ITER >= 2 ? 2 : 1);
+      constexpr bool WHOLE = (ITER % PB) == 0;           // else the last batch is partial
+      const int lp = ctx.tid / TS, t = ctx.tid - lp * TS;
+      int64_t ra, rb;
+      if (!pair_rows(p, tile_ * (C / 2) + lp, ra, rb)) {
+        cx<T> z; z.x = z.y = T(0);
+        for (int e = t; e < N; e += TS) { smem[e * CP + 2 * lp] = z; smem[e * CP + 2 * lp + 1] = z; }
+        return;
+      }
+      const bool row0 = ra == 0;
+      const int emb = row0 ? N : N - 1;                  // mirrored element: emb - e (0 for element 0 of row 0)
+      const uint32_t kl = klow_of_row(p, ra);
+      const cx<T> wh = ld_ro(p.tw2_hi + (kl >> p.tw_shift)), wl = ld_ro(p.tw2_lo + (kl & p.tw_mask));
       const Job jb = p.jobs[batch];
-      const RowInfo<T> ia = info[2 * lp];
-      const int64_t rb = info[2 * lp + 1].row;
-      const bool ok = ia.row >= 0;
-      const int64_t off_a = (ok ? ia.row : 0) * N, off_b = (ok ? rb : 0) * N;
-      const bool row0 = ia.row == 0;
       // one scale for all terms (block mode, plain pairs) is applied once at the end
       const bool per_term = p.normalize && p.stack_sig_stride != 0;
       T fs = T(0.5);
       if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
-      constexpr int ITER = (N + 2 * TJ - 1) / (2 * TJ);
-      constexpr int PB = 2;
+      const cx<T>* za = p.spec + ra * N + t;             // frequency k side
+      const cx<T>* zb = p.spec + rb * N + (emb - t);     // frequency M - k side (walks backwards)
+      const int fix0 = (row0 && t == 0) ? -N : 0;        // element 0 of row 0 mirrors itself
+      const cx<T> wrow = cmul(wh, wl);
       for (int it0 = 0; it0 < ITER; it0 += PB) {
         cx<T> ca[PB], cb[PB];
 #pragma unroll
         for (int u = 0; u < PB; ++u) ca[u].x = ca[u].y = cb[u].x = cb[u].y = T(0);
         for (int w = 0; w < p.n_stack; ++w) {
-          const cx<T>* zi = p.spec + jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride);
-          const cx<T>* zj = p.spec + jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride);
+          const int64_t oi = jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride);
+          const int64_t oj = jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride);
           T sw = T(1);
           if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
           cx<T> A[PB], Am[PB], B[PB], Bm[PB];
 #pragma unroll
           for (int u = 0; u < PB; ++u) {
-            const int e = t + (it0 + u) * 2 * TJ;
-            if (ok && e < N) {
-              const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-              A[u] = zi[off_a + e]; Am[u] = zi[off_b + em]; B[u] = zj[off_a + e]; Bm[u] = zj[off_b + em];
+            const int de = (it0 + u) * TS;
+            if ((WHOLE || it0 + u < ITER) && (EXACT || t + de < N)) {
+              const int dm = (it0 + u == 0) ? fix0 - de : -de;
+              A[u] = za[oi + de]; Am[u] = zb[oi + dm]; B[u] = za[oj + de]; Bm[u] = zb[oj + dm];
             }
           }
 #pragma unroll
           for (int u = 0; u < PB; ++u) {
-            const int e = t + (it0 + u) * 2 * TJ;
-            if (ok && e < N) {
-              const cx<T> a = {A[u].x * sw, A[u].y * sw}, am = {Am[u].x * sw, Am[u].y * sw};
-              if (row0 && e == 0) {                 // slot 0 = (X[0], X[M]), both real
-                ca[u].x += a.x * B[u].x; ca[u].y += a.y * B[u].y;
-              } else {
-                ca[u].x += a.x * B[u].x + a.y * B[u].y;    ca[u].y += a.y * B[u].x - a.x * B[u].y;
-                cb[u].x += am.x * Bm[u].x + am.y * Bm[u].y; cb[u].y += am.y * Bm[u].x - am.x * Bm[u].y;
-              }
+            if ((WHOLE || it0 + u < ITER) && (EXACT || t + (it0 + u) * TS < N)) {
+              const T ax = A[u].x * sw, ay = A[u].y * sw, mx = Am[u].x * sw, my = Am[u].y * sw;
+              ca[u].x += ax * B[u].x + ay * B[u].y;  ca[u].y += ay * B[u].x - ax * B[u].y;
+              cb[u].x += mx * Bm[u].x + my * Bm[u].y; cb[u].y += my * Bm[u].x - mx * Bm[u].y;
             }
           }
         }
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
-          const int e = t + (it0 + u) * 2 * TJ;
-          if (e < N) {
-            const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
+          const int e = t + (it0 + u) * TS;
+          if ((WHOLE || it0 + u < ITER) && (EXACT || e < N)) {
+            const int em = (it0 + u == 0 && fix0) ? 0 : emb - e;
             cx<T> va, vb;
-            va.x = va.y = vb.x = vb.y = T(0);
-            if (ok) {
-              if (row0 && e == 0) {                 // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
-                va.x = fs * (ca[u].x + ca[u].y); va.y = -fs * (ca[u].x - ca[u].y);
-                vb = va;
-              } else {
-                tangle(ca[u], cb[u], cmul(ia.wrow, ld_ro(p.tw2_inner + e)), fs, va, vb);
-              }
-            }
+            tangle(ca[u], cb[u], cmul(wrow, ld_ro(p.tw2_inner + e)), fs, va, vb);
             smem[e * CP + 2 * lp] = va;
             smem[em * CP + 2 * lp + 1] = vb;
           }
         }
+      }
+      if (row0 && t == 0) {
+        // slot 0 holds (X[0], X[M]), both real: C[0] and C[M] are plain products and
+        // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
+        T c0 = T(0), cm = T(0);
+        for (int w = 0; w < p.n_stack; ++w) {
+          const cx<T> a = p.spec[jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride)];
+          const cx<T> b = p.spec[jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride)];
+          T sw = T(1);
+          if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+          c0 += a.x * sw * b.x;
+          cm += a.y * sw * b.y;
+        }
+        cx<T> v0; v0.x = fs * (c0 + cm); v0.y = -fs * (c0 - cm);
+        smem[2 * lp] = v0;
       }
     } else if (p.load_mode == RL_REAL) {
       const T* x = reinterpret_cast<const T*>(p.in) + batch * p.in_stride;
@@ -638,13 +663,24 @@ template <class T, int R1, int R2> struct RowPass {
         cx<T>* base = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride;
         cx<T>* dst_a = base + ia.row * N;
         cx<T>* dst_b = base + (self ? ia.row : rb) * N;
-        for (int e = t; e < N; e += 2 * TJ) {
-          const int em = row0 ? (e == 0 ? 0 : N - e) : N - 1 - e;
-          cx<T> Xk, Xm;
-          untangle(smem[e * CP + 2 * lp], smem[em * CP + cm], cmul(ia.wrow, ld_ro(p.tw2_inner + e)), Xk, Xm);
-          if (row0 && e == 0) Xk.y = Xm.x;          // slot 0 = (X[0], X[M])
-          dst_a[e] = Xk;
-          if (!self) dst_b[em] = Xm;
+        constexpr int TS = 2 * TJ;
+        constexpr int ITER = (N + TS - 1) / TS;
+        const int emb = row0 ? N : N - 1;
+        const cx<T>* sa = smem + t * CP + 2 * lp;
+        const cx<T>* sb = smem + (emb - t) * CP + cm;
+        dst_a += t;
+        dst_b += emb - t;
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+          const int de = it * TS;
+          if ((N % TS) == 0 || t + de < N) {
+            const bool first = it == 0 && row0 && t == 0;        // element 0 of row 0 mirrors itself
+            cx<T> Xk, Xm;
+            untangle(sa[de * CP], first ? sa[0] : sb[-de * CP], cmul(ia.wrow, ld_ro(p.tw2_inner + t + de)), Xk, Xm);
+            if (first) Xk.y = Xm.x;                              // slot 0 = (X[0], X[M])
+            dst_a[de] = Xk;
+            if (!self) dst_b[-de] = Xm;
+          }
         }
       }
     } else if (p.store_mode == RS_EPI) {
@@ -675,5 +711,237 @@ template <class T, int R1, int R2> struct RowPass {
       block_sumsq<G::THREADS>(p.sumsq_partial + ctx.bid, red_ptr(smem_raw), ctx.tid);
   }
 };
+
+// ---------------------------------------------------------------------------
+// Row pass, warp-synchronous variant (R1 == 16)
+// ---------------------------------------------------------------------------
+// One warp owns one mirrored row pair: lanes 0-15 the row ra (frequencies k),
+// lanes 16-31 its mirror rb (frequencies M - k).  Lane j of a half loads the
+// stage-1 inputs e = j + R2 r of its row straight from HBM into registers (a
+// half-warp reads 16 consecutive elements = one 128-byte line per r), runs
+// radix-R1, swaps through a padded per-row buffer in shared memory, runs
+// radix-R2 and stores k = j + R1 r straight from registers (again full lines).
+// The only synchronisation is __syncwarp: warps never wait for each other, and
+// every element makes ONE shared-memory round trip per exchange instead of
+// three.  The real <-> packed conversion needs the mirrored element (row rb,
+// N-1-e): both halves publish their values to the row buffers (linear index)
+// and read the partner's.
+//
+//   forward last pass : A load, radix-R1, write stage layout | B read, twiddle,
+//                       radix-R2 | C publish Z | D read mirror, untangle, store X
+//   pair product      : A X_i conj(X_j) summed over blocks / stacked windows,
+//                       publish C | B read mirror, tangle, radix-R1 | C write
+//                       stage layout | D read, twiddle, radix-R2, store
+template <class T, int R1, int R2> struct RowWarp {
+  static_assert(R1 == 16 && R2 <= 16, "one half-warp per row");
+  using G = Cfg<T, R1, R2>;
+  using Ctx = ThreadCtx<T, 16>;
+  static constexpr int N = R1 * R2, C = G::C, THREADS = 16 * C;
+  static constexpr int P1 = R1 + 1;                  // padded pitch of the stage exchange
+  static constexpr int COLBUF = R2 * P1;             // complex elements per row buffer (>= N)
+  static constexpr int SMEM = C * COLBUF * 2 * (int)sizeof(T) + THREADS * 8;
+  static_assert(SMEM <= G::ROW_SMEM, "fits the row-pass allocation");
+
+  struct Slot {
+    int64_t batch, row;
+    cx<T>* buf;        // this half's row buffer
+    const cx<T>* mbuf; // buffer holding the mirrored row
+    int j;
+    bool active;       // this half-warp has a row
+    bool row0;         // row 0 mirrors itself with e -> (N - e) mod N
+  };
+
+  static XCB_HD Slot decode(const PassParams<T>& p, const Ctx& ctx, unsigned char* smem_raw) {
+    Slot s;
+    // grids stay below 2^31 CTAs: 32-bit division
+    const uint32_t bid = (uint32_t)ctx.bid;
+    uint32_t tile, batch;
+    if (p.tile_major) { tile = bid / (uint32_t)p.n_batch; batch = bid - tile * (uint32_t)p.n_batch; }
+    else { batch = bid / (uint32_t)p.tiles_per_batch; tile = bid - batch * (uint32_t)p.tiles_per_batch; }
+    s.batch = batch;
+    const int col = ctx.tid >> 4, side = col & 1;
+    s.j = ctx.tid & 15;
+    int64_t ra, rb;
+    const bool valid = RowPass<T, R1, R2>::pair_rows(p, (int64_t)tile * (C / 2) + (col >> 1), ra, rb);
+    const bool self = ra == rb;
+    s.active = valid && !(side && self);
+    s.row = side ? rb : ra;
+    s.row0 = ra == 0;
+    cx<T>* base = reinterpret_cast<cx<T>*>(smem_raw);
+    s.buf = base + col * COLBUF;
+    s.mbuf = base + (self ? col : (col ^ 1)) * COLBUF;
+    return s;
+  }
+  static XCB_HD double* red_ptr(unsigned char* smem_raw) {
+    return reinterpret_cast<double*>(smem_raw + (size_t)C * COLBUF * sizeof(cx<T>));
+  }
+  static XCB_HD int mirror(const Slot& s, int e) { return s.row0 ? (e == 0 ? 0 : N - e) : N - 1 - e; }
+  static XCB_HD cx<T> row_twiddle(const PassParams<T>& p, int64_t row) {
+    const uint32_t kl = RowPass<T, R1, R2>::klow_of_row(p, row);
+    return cmul(ld_ro(p.tw2_hi + (kl >> p.tw_shift)), ld_ro(p.tw2_lo + (kl & p.tw_mask)));
+  }
+  // offsets of term w (block / stacked window) of a job's two spectra, and its scale
+  static XCB_HD void term(const PassParams<T>& p, const Job& jb, int w, bool per_term, int64_t& oi, int64_t& oj, T& sw) {
+    oi = jb.spec_i + (p.use_blk_off ? p.blk_off_i[w] : w * p.stack_spec_stride);
+    oj = jb.spec_j + (p.use_blk_off ? p.blk_off_j[w] : w * p.stack_spec_stride);
+    sw = T(1);
+    if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+  }
+
+  static XCB_HD void phase_a(const PassParams<T>& p, Ctx& ctx, const Slot& s, unsigned char* smem_raw) {
+    cx<T>* v = ctx.v;
+    ctx.ss = 0.0;
+    if (s.active && s.j < R2) {
+      if (p.load_mode == RL_PROLOGUE) {
+        const Job jb = p.jobs[s.batch];
+        const bool per_term = p.normalize && p.stack_sig_stride != 0;
+        const cx<T>* z = p.spec + s.row * N + s.j;
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r].x = v[r].y = T(0);
+        for (int w = 0; w < p.n_stack; ++w) {
+          int64_t oi, oj;
+          T sw;
+          term(p, jb, w, per_term, oi, oj, sw);
+          constexpr int H = R1 / 2;                 // two batches of loads bound the registers
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            cx<T> a[H], b[H];
+#pragma unroll
+            for (int r = 0; r < H; ++r) { a[r] = z[oi + (h * H + r) * R2]; b[r] = z[oj + (h * H + r) * R2]; }
+#pragma unroll
+            for (int r = 0; r < H; ++r) {
+              const T ax = a[r].x * sw, ay = a[r].y * sw;
+              v[h * H + r].x += ax * b[r].x + ay * b[r].y;
+              v[h * H + r].y += ay * b[r].x - ax * b[r].y;
+            }
+          }
+        }
+        if (s.row0 && s.j == 0) {
+          // slot 0 holds (X[0], X[M]), both real: C[0], C[M] are plain products
+          T c0 = T(0), cm = T(0);
+          for (int w = 0; w < p.n_stack; ++w) {
+            int64_t oi, oj;
+            T sw;
+            term(p, jb, w, per_term, oi, oj, sw);
+            const cx<T> a = p.spec[oi], b = p.spec[oj];
+            c0 += a.x * sw * b.x;
+            cm += a.y * sw * b.y;
+          }
+          v[0].x = c0; v[0].y = cm;
+        }
+#pragma unroll
+        for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];       // publish C (linear index)
+      } else {
+        if (p.load_mode == RL_REAL) {
+          const T* x = reinterpret_cast<const T*>(p.in) + s.batch * p.in_stride;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) v[r] = load_real_packed(p, x, s.row * N + s.j + r * R2, ctx.ss);
+        } else {
+          const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + s.batch * p.in_stride + s.row * N + s.j;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) v[r] = src[r * R2];
+        }
+        fft_reg<R1>(v);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) s.buf[s.j * P1 + r] = v[r];       // stage layout
+      }
+    }
+    if (p.sumsq_partial && p.load_mode == RL_REAL) red_ptr(smem_raw)[ctx.tid] = ctx.ss;
+  }
+
+  // stage 2: read the stage layout, inner twiddles, radix-R2 -> v[r] = element j + R1 r
+  static XCB_HD void stage2(const PassParams<T>& p, const Slot& s, cx<T>* v) {
+#pragma unroll
+    for (int r = 0; r < R2; ++r) v[r] = s.buf[r * P1 + s.j];
+    twiddle_powers<R2>(ld_ro(p.tw_inner + s.j), v);
+    fft_reg<R2>(v);
+  }
+
+  static XCB_HD void phase_b(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
+    cx<T>* v = ctx.v;
+    if (!s.active) return;
+    if (p.load_mode == RL_PROLOGUE) {
+      if (s.j >= R2) return;
+      const Job jb = p.jobs[s.batch];
+      const bool per_term = p.normalize && p.stack_sig_stride != 0;
+      T fs = T(0.5);
+      if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
+      const cx<T> wrow = row_twiddle(p, s.row);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        const int e = s.j + r * R2;
+        const cx<T> cm = s.mbuf[mirror(s, e)];
+        const cx<T> W = cmul(wrow, ld_ro(p.tw2_inner + e));
+        // E = C[k] + conj(C[M-k]), D = C[k] - conj(C[M-k]), O = conj(W) D, V = (E + iO)/2; keep fs conj(V)
+        cx<T> E, D;
+        E.x = v[r].x + cm.x; E.y = v[r].y - cm.y;
+        D.x = v[r].x - cm.x; D.y = v[r].y + cm.y;
+        const cx<T> O = cmulc(D, W);
+        cx<T> o;
+        o.x = fs * (E.x - O.y); o.y = -fs * (E.y + O.x);
+        if (r == 0 && s.row0 && s.j == 0) {          // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
+          o.x = fs * (v[0].x + v[0].y); o.y = -fs * (v[0].x - v[0].y);
+        }
+        v[r] = o;
+      }
+      fft_reg<R1>(v);
+    } else {
+      stage2(p, s, v);
+    }
+  }
+
+  static XCB_HD void phase_c(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
+    const cx<T>* v = ctx.v;
+    if (!s.active) return;
+    if (p.load_mode == RL_PROLOGUE) {
+      if (s.j >= R2) return;
+#pragma unroll
+      for (int r = 0; r < R1; ++r) s.buf[s.j * P1 + r] = v[r];         // stage layout
+    } else {
+#pragma unroll
+      for (int r = 0; r < R2; ++r) s.buf[s.j + r * R1] = v[r];         // publish Z (linear index)
+    }
+  }
+
+  static XCB_HD void phase_d(const PassParams<T>& p, Ctx& ctx, const Slot& s, unsigned char* smem_raw) {
+    cx<T>* v = ctx.v;
+    if (s.active) {
+      if (p.load_mode == RL_PROLOGUE) {
+        stage2(p, s, v);
+        if (p.store_mode == RS_EPI) {
+          T* outp = p.ccf + p.jobs[s.batch].out_off;
+#pragma unroll
+          for (int r = 0; r < R2; ++r)
+            epilogue_store(p, outp, (uint32_t)(s.row * N + s.j + r * R1), v[r].x, -v[r].y);
+        } else {
+          cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+#pragma unroll
+          for (int r = 0; r < R2; ++r) dst[r * R1] = cconj(v[r]);
+        }
+      } else {
+        // X[k] = (S - i W D)/2 with S = Z[k] + conj(Z[M-k]), D = Z[k] - conj(Z[M-k]), W = W_L^k
+        const cx<T> wrow = row_twiddle(p, s.row);
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const int k = s.j + r * R1;
+          const cx<T> zm = s.mbuf[mirror(s, k)];
+          const cx<T> W = cmul(wrow, ld_ro(p.tw2_inner + k));
+          cx<T> S, D;
+          S.x = v[r].x + zm.x; S.y = v[r].y - zm.y;
+          D.x = v[r].x - zm.x; D.y = v[r].y + zm.y;
+          const cx<T> WD = cmul(W, D);
+          cx<T> X;
+          X.x = T(0.5) * (S.x + WD.y); X.y = T(0.5) * (S.y - WD.x);
+          if (r == 0 && s.row0 && s.j == 0) { X.x = v[0].x + v[0].y; X.y = v[0].x - v[0].y; }   // (X[0], X[M])
+          dst[r * R1] = X;
+        }
+      }
+    }
+    if (p.sumsq_partial && p.load_mode == RL_REAL)
+      block_sumsq<THREADS>(p.sumsq_partial + ctx.bid, red_ptr(smem_raw), ctx.tid);
+  }
+};
+
 
 }  // namespace xcb
