@@ -133,6 +133,32 @@ int emu_choose_blocks(int64_t n, int64_t n_lags, int n_recv, int n_pairs, int* d
   return nb;
 }
 
+// Job grouping of the staged pair product for `n_pairs` pairs of one window (classic plan over M points).
+// Writes per job its group id; returns the number of groups, or a negative code when a group is inconsistent.
+int emu_pair_groups(const int* pairs, int n_pairs, int max_jobs, int max_rows, int* group_of_job, int* rows_total) {
+  PlanGeom g;
+  int d[1] = {64};
+  plan_geom_init(g, 50, d, 1);
+  std::vector<Job> jobs(n_pairs);
+  for (int q = 0; q < n_pairs; ++q) jobs[q] = make_job(g, pairs[2 * q], pairs[2 * q + 1], (int64_t)q * 99);
+  std::vector<PairGroup> groups;
+  build_pair_groups(jobs.data(), n_pairs, max_jobs, max_rows, groups);
+  for (int q = 0; q < n_pairs; ++q) group_of_job[q] = -1;
+  *rows_total = 0;
+  for (size_t k = 0; k < groups.size(); ++k) {
+    const PairGroup& gr = groups[k];
+    if (gr.n_jobs < 1 || gr.n_jobs > max_jobs || gr.n_i + gr.n_j > max_rows) return -1;
+    *rows_total += gr.n_i + gr.n_j;
+    for (int w = 0; w < gr.n_jobs; ++w) {
+      const int q = gr.job[w];
+      if (q < 0 || q >= n_pairs || group_of_job[q] != -1) return -2;
+      if (gr.spec_i[gr.ji[w]] != jobs[q].spec_i || gr.spec_j[gr.jj[w]] != jobs[q].spec_j) return -3;
+      group_of_job[q] = (int)k;
+    }
+  }
+  return (int)groups.size();
+}
+
 // dtype: 0 = f32, 1 = f64.  x: [n_signals][x_stride]; pairs: [n_pairs][2]; out: [n_pairs][i1-i0]
 int emu_cc(int dtype, int64_t n, const int* dims, int nd, const void* x, int64_t x_stride, int n_signals,
            const int* pairs, int n_pairs, int64_t i0, int64_t i1, int normalize, int unbiased, void* out,

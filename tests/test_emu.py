@@ -208,3 +208,27 @@ def test_warp_row_pass_blocks_and_stacking():
     for q, (i, j) in enumerate(pairs):
         ref = sum(orc.cc(rec[i, w], rec[j, w], unbiased=False) for w in range(W))
         assert np.max(np.abs(out[q] - ref)) <= 1e-13 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("max_jobs,max_rows", [(8, 9), (4, 4)])
+def test_pair_groups_cover_every_job_once(max_jobs, max_rows):
+    """Planner grouping for the staged pair product: every job in exactly one group,
+    group sizes within the kernel's limits, and spectra shared within groups."""
+    import ctypes
+    from tests.emu_util import lib
+    rng = np.random.default_rng(5)
+    cases = [[(i, j) for i in range(16) for j in range(i + 1, 16)],              # all pairs of 16 receivers
+             [(0, 1)], [(2, 2), (0, 1), (1, 0)],
+             [tuple(p) for p in rng.integers(0, 9, size=(40, 2))]]               # arbitrary list with repeats
+    for pairs in cases:
+        arr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32))
+        grp = np.zeros(len(pairs), dtype=np.int32)
+        rows = ctypes.c_int()
+        n = lib().emu_pair_groups(arr.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(pairs), max_jobs, max_rows,
+                                  grp.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.byref(rows))
+        assert n >= 1, n
+        assert np.all(grp >= 0)
+        assert np.bincount(grp).max() <= max_jobs
+        if len(pairs) == 120:
+            # sharing: clearly fewer staged rows than the 2 per job of the ungrouped kernel
+            assert rows.value <= (0.9 if max_jobs == 8 else 1.2) * len(pairs), rows.value

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(32) xcb_argmax_final_rows(const T* __restrict_
 struct xcb_plan {
   xcb_desc desc;
   std::vector<int32_t> pairs;
+  std::vector<Job> jobs;
   PlanGeom g;
   int dtype = 0;
   int device = 0;
@@ -236,6 +237,10 @@ struct xcb_plan {
   void* d_lo2 = nullptr;
   void* d_inner2 = nullptr;
   Job* d_jobs = nullptr;
+  // staged pair product: job groups per launch chunk (chunk c covers jobs [c*jobs_in_flight, ...))
+  PairGroup* d_groups = nullptr;
+  unsigned long long* d_counter = nullptr;
+  std::vector<int64_t> group_off;     // first group of chunk c; group_off[n_chunks] = total
   const PassLauncher* launch[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
   // measurement aid (xcb_profile_*): events around every pass launch
   struct Timed { cudaEvent_t a, b; int kind; };
@@ -296,6 +301,8 @@ extern "C" int xcb_plan_destroy(xcb_plan* pl) {
   cudaFree(pl->d_lo2);
   cudaFree(pl->d_inner2);
   cudaFree(pl->d_jobs);
+  cudaFree(pl->d_groups);
+  cudaFree(pl->d_counter);
   delete pl;
   return XCB_OK;
 }
@@ -373,7 +380,8 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   const int64_t ws = (d->recv_stride == 0 && d->win_stride == 0) ? 1 : d->win_stride;
   pl->win_stride = ws;
   if (pl->n_jobs > 0) {
-    std::vector<Job> jobs((size_t)pl->n_jobs);
+    std::vector<Job>& jobs = pl->jobs;
+    jobs.resize((size_t)pl->n_jobs);
     const int64_t nw = d->stack ? 1 : d->n_windows;
     for (int64_t w = 0; w < nw; ++w)
       for (int64_t q = 0; q < d->n_pairs; ++q) {
@@ -398,6 +406,23 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   if (fl > pl->n_jobs) fl = pl->n_jobs > 0 ? pl->n_jobs : 1;
   pl->jobs_in_flight = fl;
   pl->work_bytes = align_up((size_t)fl * per_job, 256);
+
+  // job groups of the staged pair product (row axes 16 x R2 only; see launch_row)
+  if (pl->n_jobs > 0 && menu_find(dims[nd - 1])->R1 == 16) {
+    const int warps = C / 2, max_rows = pl->dtype == XCB_F32 ? 6 : 4;     // PairGrouped::MAX_ROWS
+    std::vector<PairGroup> all, chunk;
+    pl->group_off.push_back(0);
+    for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += fl) {
+      const int nj = (int)std::min<int64_t>(fl, pl->n_jobs - j0);
+      build_pair_groups(pl->jobs.data() + j0, nj, warps, max_rows, chunk);
+      all.insert(all.end(), chunk.begin(), chunk.end());
+      pl->group_off.push_back((int64_t)all.size());
+    }
+    cudaError_t e = cudaMalloc(&pl->d_groups, all.size() * sizeof(PairGroup));
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_groups, all.data(), all.size() * sizeof(PairGroup), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->d_counter, sizeof(unsigned long long));
+    if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "group table"); }
+  }
   *out = pl;
   return XCB_OK;
 }
@@ -428,9 +453,16 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
 template <class T> struct DeviceRunner {
   const xcb_plan* pl;
   cudaStream_t st;
+  int64_t chunk = -1; // inverse passes: launch chunk (selects the job groups)
   int err = 0;        // cudaError_t of a failed launch, or -1 for an oversized grid
-  bool operator()(const PassParams<T>& p, bool row, int kind) {
+  bool operator()(const PassParams<T>& p0, bool row, int kind) {
     const int a = kind % pl->g.nd;
+    PassParams<T> p = p0;
+    if (row && p.load_mode == RL_PROLOGUE && pl->d_groups && chunk >= 0) {
+      p.groups = pl->d_groups + pl->group_off[(size_t)chunk];
+      p.n_groups = (int32_t)(pl->group_off[(size_t)chunk + 1] - pl->group_off[(size_t)chunk]);
+      p.work_counter = pl->d_counter;
+    }
     const int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
     if (nblocks >= 2147483647LL) { err = -1; return false; }
     int e;
@@ -490,6 +522,7 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
   DeviceRunner<T> run{pl, st};
   for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
     int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
+    run.chunk = j0 / pl->jobs_in_flight;
     if (!run_inverse<T>(g, tb, static_cast<const cx<T>*>(spec), rnorm, pl->d_jobs + j0, nj, work,
                         static_cast<T*>(ccf), f, run))
       return run.err < 0 ? XCB_ERR_UNSUPPORTED : cuda_fail((cudaError_t)run.err, "inverse pass launch");

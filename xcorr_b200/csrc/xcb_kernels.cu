@@ -172,6 +172,22 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
 template <class T, int R1, int R2> int launch_row(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
   const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
+  if constexpr (R1 == 16) {
+    using K = PairGrouped<T, R1, R2>;
+    static int staged = -1;
+    if (staged < 0) { const char* e = getenv("XCB_STAGED"); staged = (e && e[0] == '0') ? 0 : 1; }
+    if (K::kOk && staged && p.load_mode == RL_PROLOGUE && p.n_groups > 0 && p.work_counter &&
+        reinterpret_cast<uintptr_t>(p.spec) % 16 == 0) {
+      static int resident = 0;   // persistent grid
+      if (!resident) resident = resident_ctas((const void*)xcb_pair_product_grouped<T, R1, R2>, K::THREADS, K::SMEM);
+      const int64_t items = p.n_pairs_rows * (int64_t)p.n_groups;
+      const int64_t grid = items < resident ? items : resident;
+      cudaError_t ce = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
+      if (ce != cudaSuccess) return (int)ce;
+      xcb_pair_product_grouped<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(p);
+      return (int)cudaGetLastError();
+    }
+  }
   xcb_row_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
@@ -184,6 +200,10 @@ template <class T, int R1, int R2> int prepare() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            ColTma<T, R1, R2>::SMEM);
+  if (e != cudaSuccess) return (int)e;
+  if constexpr (R1 == 16)
+    e = cudaFuncSetAttribute(xcb_pair_product_grouped<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             PairGrouped<T, R1, R2>::SMEM);
   return (int)e;
 }
 

@@ -41,6 +41,17 @@ struct Job {
   int32_t sig_i, sig_j;     // indices into sumsq[]
 };
 
+// Up to 8 jobs of one launch that share spectra (pair product, grouped kernel):
+// the distinct first-role / second-role spectra are staged once per row pair in
+// shared memory and every job of the group (one warp each) reads them there.
+constexpr int kGroupJobs = 8;
+struct PairGroup {
+  int32_t n_jobs, n_i, n_j, pad;
+  int64_t spec_i[kGroupJobs], spec_j[kGroupJobs];   // distinct spectrum bases (complex-element offsets)
+  int32_t job[kGroupJobs];                          // index of the job within the launch
+  uint8_t ji[kGroupJobs], jj[kGroupJobs];           // staged row used by each job
+};
+
 template <class T> struct PassParams {
   // ---- geometry ----
   int32_t N;                 // sub-FFT length of this pass
@@ -75,7 +86,9 @@ template <class T> struct PassParams {
   // row pass: 1 = a tile is C/2 mirrored row pairs (ra, rb) in columns (2q, 2q+1)
   // (forward last pass with the half-spectrum store, and the pair product)
   int32_t pair_tiles;
-  int32_t pad1;
+  int32_t n_groups;          // pair product: job groups of this launch (0 = ungrouped kernel)
+  const PairGroup* groups;
+  unsigned long long* work_counter;   // staged pair product: next work item (zeroed before the launch)
   // ---- pair product (inverse first pass) ----
   int32_t nd;                // number of passes p
   int32_t dims[kMaxDims];    // N_1..N_p
@@ -746,6 +759,7 @@ template <class T, int R1, int R2> struct RowWarp {
     int64_t batch, row;
     cx<T>* buf;        // this half's row buffer
     const cx<T>* mbuf; // buffer holding the mirrored row
+    cx<T> wrow;        // W_L^klow(row): half-step twiddle of the row's leading digits
     int j;
     bool active;       // this half-warp has a row
     bool row0;         // row 0 mirrors itself with e -> (N - e) mod N
@@ -770,6 +784,8 @@ template <class T, int R1, int R2> struct RowWarp {
     cx<T>* base = reinterpret_cast<cx<T>*>(smem_raw);
     s.buf = base + col * COLBUF;
     s.mbuf = base + (self ? col : (col ^ 1)) * COLBUF;
+    s.wrow.x = T(1); s.wrow.y = T(0);
+    if (s.active) s.wrow = row_twiddle(p, s.row);
     return s;
   }
   static XCB_HD double* red_ptr(unsigned char* smem_raw) {
@@ -788,6 +804,40 @@ template <class T, int R1, int R2> struct RowWarp {
     if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
   }
 
+  // v[r] += sw * a[r R2] * conj(b[r R2]), r < R1: this lane's share of one term
+  // (block / stacked window) of the cross-spectrum; a, b point at the lane's first
+  // element of the two rows (global memory, or rows staged in shared memory)
+  static XCB_HD void accumulate(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw) {
+    constexpr int H = R1 / 2;                       // two batches of loads bound the registers
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      cx<T> a[H], b[H];
+#pragma unroll
+      for (int r = 0; r < H; ++r) { a[r] = a_row[(h * H + r) * R2]; b[r] = b_row[(h * H + r) * R2]; }
+#pragma unroll
+      for (int r = 0; r < H; ++r) {
+        const T ax = a[r].x * sw, ay = a[r].y * sw;
+        v[h * H + r].x += ax * b[r].x + ay * b[r].y;
+        v[h * H + r].y += ay * b[r].x - ax * b[r].y;
+      }
+    }
+  }
+
+  // slot 0 of a spectrum holds (X[0], X[M]), both real: C[0] and C[M] are plain products
+  static XCB_HD cx<T> packed_dc(const PassParams<T>& p, const Job& jb, bool per_term) {
+    T c0 = T(0), cm = T(0);
+    for (int w = 0; w < p.n_stack; ++w) {
+      int64_t oi, oj;
+      T sw;
+      term(p, jb, w, per_term, oi, oj, sw);
+      const cx<T> a = p.spec[oi], b = p.spec[oj];
+      c0 += a.x * sw * b.x;
+      cm += a.y * sw * b.y;
+    }
+    cx<T> r; r.x = c0; r.y = cm;
+    return r;
+  }
+
   static XCB_HD void phase_a(const PassParams<T>& p, Ctx& ctx, const Slot& s, unsigned char* smem_raw) {
     cx<T>* v = ctx.v;
     ctx.ss = 0.0;
@@ -802,33 +852,9 @@ template <class T, int R1, int R2> struct RowWarp {
           int64_t oi, oj;
           T sw;
           term(p, jb, w, per_term, oi, oj, sw);
-          constexpr int H = R1 / 2;                 // two batches of loads bound the registers
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            cx<T> a[H], b[H];
-#pragma unroll
-            for (int r = 0; r < H; ++r) { a[r] = z[oi + (h * H + r) * R2]; b[r] = z[oj + (h * H + r) * R2]; }
-#pragma unroll
-            for (int r = 0; r < H; ++r) {
-              const T ax = a[r].x * sw, ay = a[r].y * sw;
-              v[h * H + r].x += ax * b[r].x + ay * b[r].y;
-              v[h * H + r].y += ay * b[r].x - ax * b[r].y;
-            }
-          }
+          accumulate(v, z + oi, z + oj, sw);
         }
-        if (s.row0 && s.j == 0) {
-          // slot 0 holds (X[0], X[M]), both real: C[0], C[M] are plain products
-          T c0 = T(0), cm = T(0);
-          for (int w = 0; w < p.n_stack; ++w) {
-            int64_t oi, oj;
-            T sw;
-            term(p, jb, w, per_term, oi, oj, sw);
-            const cx<T> a = p.spec[oi], b = p.spec[oj];
-            c0 += a.x * sw * b.x;
-            cm += a.y * sw * b.y;
-          }
-          v[0].x = c0; v[0].y = cm;
-        }
+        if (s.row0 && s.j == 0) v[0] = packed_dc(p, jb, per_term);
 #pragma unroll
         for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];       // publish C (linear index)
       } else {
@@ -866,7 +892,7 @@ template <class T, int R1, int R2> struct RowWarp {
       const bool per_term = p.normalize && p.stack_sig_stride != 0;
       T fs = T(0.5);
       if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
-      const cx<T> wrow = row_twiddle(p, s.row);
+      const cx<T> wrow = s.wrow;
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         const int e = s.j + r * R2;
@@ -920,7 +946,7 @@ template <class T, int R1, int R2> struct RowWarp {
         }
       } else {
         // X[k] = (S - i W D)/2 with S = Z[k] + conj(Z[M-k]), D = Z[k] - conj(Z[M-k]), W = W_L^k
-        const cx<T> wrow = row_twiddle(p, s.row);
+        const cx<T> wrow = s.wrow;
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
 #pragma unroll
         for (int r = 0; r < R2; ++r) {

@@ -5,7 +5,9 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include <algorithm>
+#include <map>
 #include <vector>
 #include "xcb_passes.h"
 
@@ -430,6 +432,67 @@ inline Job make_job(const PlanGeom& g, int64_t si, int64_t sj, int64_t out_off) 
   j.spec_j = (sj * per + (g.n_blocks > 1 ? segments_per_signal(g) : 0)) * g.M;   // blocks of signal j
   j.out_off = out_off;
   return j;
+}
+
+// Grouping of the jobs of one launch for the staged pair product (xcb_tma.cuh):
+// each group has at most max_jobs jobs and at most max_rows distinct spectra
+// (first-role + second-role).  Greedy: two first-role spectra that share
+// second-role partners form a 2 x k block (k + 2 rows for 2k jobs), otherwise one
+// first-role spectrum with up to max_rows - 1 partners (k + 1 rows for k jobs).
+inline void build_pair_groups(const Job* jobs, int n_jobs, int max_jobs, int max_rows, std::vector<PairGroup>& out) {
+  out.clear();
+  if (max_jobs > kGroupJobs) max_jobs = kGroupJobs;
+  std::vector<char> used((size_t)n_jobs, 0);
+  std::map<int64_t, std::vector<int>> by_i;              // first-role spectrum -> its jobs, in order
+  for (int q = 0; q < n_jobs; ++q) by_i[jobs[q].spec_i].push_back(q);
+  auto add = [&](PairGroup& g, int q) {
+    const Job& jb = jobs[q];
+    int a = 0, b = 0;
+    while (a < g.n_i && g.spec_i[a] != jb.spec_i) ++a;
+    if (a == g.n_i) g.spec_i[g.n_i++] = jb.spec_i;
+    while (b < g.n_j && g.spec_j[b] != jb.spec_j) ++b;
+    if (b == g.n_j) g.spec_j[g.n_j++] = jb.spec_j;
+    g.job[g.n_jobs] = q;
+    g.ji[g.n_jobs] = (uint8_t)a;
+    g.jj[g.n_jobs] = (uint8_t)b;
+    ++g.n_jobs;
+    used[(size_t)q] = 1;
+  };
+  for (int q0 = 0; q0 < n_jobs;) {
+    if (used[(size_t)q0]) { ++q0; continue; }              // (a block may leave q0 for a later group)
+    PairGroup g;
+    memset(&g, 0, sizeof(g));
+    auto it1 = by_i.find(jobs[q0].spec_i);
+    std::vector<int> mine;                                // unused jobs of this first-role spectrum
+    for (int q : it1->second) if (!used[(size_t)q]) mine.push_back(q);
+    // best partner among the following first-role spectra (jobs are window-major: neighbours share a window)
+    const int kcols = std::min(max_jobs / 2, max_rows - 2);
+    std::vector<std::pair<int, int>> best;                // (my job, partner's job) with the same second role
+    if (kcols >= 2 && mine.size() >= 2) {
+      auto it2 = it1;
+      for (int tries = 0; tries < 16; ++tries) {
+        if (++it2 == by_i.end()) break;
+        std::vector<std::pair<int, int>> common;
+        for (int qa : mine)
+          for (int qb : it2->second) {
+            if (used[(size_t)qb] || jobs[qb].spec_j != jobs[qa].spec_j) continue;
+            bool taken = false;                           // (a pair listed twice must not match the same partner twice)
+            for (const auto& c : common) taken = taken || c.second == qb;
+            if (!taken) { common.push_back({qa, qb}); break; }
+          }
+        if (common.size() > best.size()) best = common;
+        if ((int)best.size() >= kcols) break;
+      }
+    }
+    if (best.size() >= 2) {
+      const int k = std::min<int>((int)best.size(), kcols);
+      for (int c = 0; c < k; ++c) { add(g, best[(size_t)c].first); add(g, best[(size_t)c].second); }
+    } else {
+      const int k = std::min<int>((int)mine.size(), std::min(max_jobs, max_rows - 1));
+      for (int c = 0; c < k; ++c) add(g, mine[(size_t)c]);
+    }
+    out.push_back(g);
+  }
 }
 
 // Block-mode planner: for kept lags [lag0, lag0 + K) (any sign of lag0) choose the

@@ -207,6 +207,181 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------------------
+// Pair product with staged, shared spectra rows (16 x R2 row axes)
+// ---------------------------------------------------------------------------
+// Every pair (i, j) reads the rows of X_i and X_j; the pairs of a window share
+// receivers, so a CTA takes ONE mirrored row pair and a GROUP of up to WARPS jobs
+// whose distinct spectra (PairGroup, built by the planner) are fetched once with
+// cp.async.bulk into shared memory -- one 1-D bulk copy per row, completion on an
+// mbarrier -- and then read by all the group's warps (one job per warp, RowWarp
+// arithmetic).  Terms (blocks / stacked windows) alternate between two staging
+// buffers; the CTA is persistent and the copies of the next item's first terms are
+// in flight while the current item is transformed and stored, so no warp waits on
+// an L2 / HBM load and the L2 -> SM traffic drops by the sharing factor.
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class T, int R1, int R2> struct PairGrouped {
+  using W = RowWarp<T, R1, R2>;
+  static constexpr int N = W::N, C = W::C, WARPS = W::THREADS / 32;      // consumer warps = jobs per group
+  static constexpr int THREADS = W::THREADS + 32;                        // + one producer warp
+  static constexpr int MAX_ROWS = sizeof(T) == 4 ? 6 : 4;                // distinct spectra per group
+  static constexpr int NBUF = sizeof(T) == 4 ? 3 : 2;                    // staging ring
+  static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
+  static constexpr int STAGE_BYTES = MAX_ROWS * 2 * ROW_BYTES;           // [row][side]
+  static constexpr int EXCH_OFF = NBUF * STAGE_BYTES;
+  static constexpr int BAR_OFF = EXCH_OFF + C * W::COLBUF * 2 * (int)sizeof(T);
+  static constexpr int MAIL_OFF = BAR_OFF + 64;
+  static constexpr int SMEM = MAIL_OFF + NBUF * 64;
+  static constexpr bool kOk = (ROW_BYTES % 16) == 0 && SMEM <= 113 * 1024 && 2 * MAX_ROWS <= 32;   // two CTAs per SM
+};
+
+// what the producer tells the consumers about the item whose first term sits in a buffer
+template <class T> struct alignas(64) PairMail {
+  int64_t item;        // -1: no more work
+  int64_t ra, rb;
+  cx<T> wrow[2];
+};
+
+template <class T, int R1, int R2>
+__global__ void __launch_bounds__(PairGrouped<T, R1, R2>::THREADS, 2)
+xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
+  using K = PairGrouped<T, R1, R2>;
+  using W = RowWarp<T, R1, R2>;
+  using RP = RowPass<T, R1, R2>;
+  constexpr int N = K::N, NBUF = K::NBUF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + K::BAR_OFF);   // [NBUF] filled by the bulk copies
+  uint64_t* empty = full + NBUF;                                         // [NBUF] released by the consumer warps
+  cx<T>* exch = reinterpret_cast<cx<T>*>(smem_raw + K::EXCH_OFF);
+  PairMail<T>* mail = reinterpret_cast<PairMail<T>*>(smem_raw + K::MAIL_OFF);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_items = p.n_pairs_rows * (int64_t)p.n_groups;          // item = row pair * n_groups + group
+  const int n_terms = p.n_stack;
+
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], K::WARPS); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == K::WARPS) {
+    // ---- producer warp: takes items in order from a global counter (so that the
+    // CTAs of the grid stay on neighbouring row pairs and the spectra rows they share
+    // come from L2), lane l fetches staged row l/2, side l%2 ----
+    uint32_t step = 0;
+    for (;;) {
+      unsigned long long it = 0;
+      if (lane == 0) it = atomicAdd(p.work_counter, 1ULL);
+      const int64_t item = (int64_t)__shfl_sync(0xffffffffu, it, 0);
+      if (item >= n_items) {
+        const int buf = (int)(step % NBUF);
+        mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
+        if (lane == 0) { mail[buf].item = -1; mbar_arrive(&full[buf]); }
+        break;
+      }
+      const int64_t q = item / p.n_groups;
+      const PairGroup& g = p.groups[item - q * p.n_groups];
+      int64_t ra, rb;
+      RP::pair_rows(p, q, ra, rb);
+      const int sides = ra == rb ? 1 : 2, n_i = g.n_i, rows = n_i + g.n_j;
+      const int r = lane >> 1, sd = lane & 1;
+      const bool mine = r < rows && sd < sides;
+      int64_t src = 0;
+      if (mine) src = (r < n_i ? g.spec_i[r] : g.spec_j[r - n_i]) + (sd ? rb : ra) * N;
+      cx<T> wr; wr.x = T(1); wr.y = T(0);
+      if (lane < 2) wr = W::row_twiddle(p, lane ? rb : ra);
+      for (int w = 0; w < n_terms; ++w, ++step) {
+        const int buf = (int)(step % NBUF);
+        mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
+        if (w == 0 && lane < 2) {
+          mail[buf].wrow[lane] = wr;
+          if (lane == 0) { mail[buf].item = item; mail[buf].ra = ra; mail[buf].rb = rb; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(rows * sides * K::ROW_BYTES));
+        if (mine) {
+          const int64_t toff = p.use_blk_off ? (r < n_i ? p.blk_off_i[w] : p.blk_off_j[w]) : w * p.stack_spec_stride;
+          bulk_load(smem_raw + buf * K::STAGE_BYTES + (r * 2 + sd) * K::ROW_BYTES, p.spec + src + toff, K::ROW_BYTES,
+                    &full[buf]);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps: one job of the group each ----
+  const int side = (tid >> 4) & 1;
+  typename W::Ctx ctx;
+  ctx.tid = tid;
+  uint32_t step = 0;
+  const bool per_term = p.normalize && p.stack_sig_stride != 0;
+  for (;;) {
+    int buf = (int)(step % NBUF);
+    mbar_wait(&full[buf], (step / NBUF) & 1u);
+    const int64_t item = mail[buf].item;
+    if (item < 0) break;
+    const int64_t ra = mail[buf].ra, rb = mail[buf].rb;
+    const int64_t q = item / p.n_groups;
+    const PairGroup& g = p.groups[item - q * p.n_groups];
+    const bool self = ra == rb;
+    typename W::Slot s;
+    const bool has_job = warp < g.n_jobs;
+    s.batch = has_job ? g.job[warp] : 0;
+    s.row = side ? rb : ra;
+    s.row0 = ra == 0;
+    s.j = tid & 15;
+    s.active = has_job && !(side && self);
+    s.wrow = mail[buf].wrow[side];
+    const int col = tid >> 4;
+    s.buf = exch + col * W::COLBUF;
+    s.mbuf = exch + (self ? col : (col ^ 1)) * W::COLBUF;
+    ctx.bid = item;
+    const bool lane_on = s.active && s.j < R2;
+    const Job jb = p.jobs[s.batch];
+    const int row_i = has_job ? g.ji[warp] : 0, row_j = has_job ? g.n_i + g.jj[warp] : 0;
+
+    cx<T>* v = ctx.v;
+#pragma unroll
+    for (int r = 0; r < R1; ++r) v[r].x = v[r].y = T(0);
+    for (int w = 0; w < n_terms; ++w, ++step) {
+      if (w > 0) {
+        buf = (int)(step % NBUF);
+        mbar_wait(&full[buf], (step / NBUF) & 1u);
+      }
+      if (lane_on) {
+        const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
+        T sw = T(1);
+        if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+        W::accumulate(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[buf]);       // this warp is done with the buffer (and its mail)
+    }
+    if (lane_on) {
+      if (s.row0 && s.j == 0) v[0] = W::packed_dc(p, jb, per_term);
+#pragma unroll
+      for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];           // publish C (linear index)
+    }
+    __syncwarp();
+    W::phase_b(p, ctx, s);
+    __syncwarp();
+    W::phase_c(p, ctx, s);
+    __syncwarp();
+    W::phase_d(p, ctx, s, smem_raw);
+    __syncwarp();                    // the exchange buffers are reused by the next item
+  }
+}
+
 // Host: 3-D tensor map [batch][rows][row_elems] of T over the pass input, box =
 // [1][box_rows][128 bytes]; rows >= `rows` and columns >= row_elems read as
 // zero.  Implemented in xcb_api.cu (needs the driver entry point).
