@@ -191,7 +191,10 @@ def run_gpu(args):
     plan = xb.CorrelationPlan(n, R, pairs, n_windows=1, dtype=tdt, index_min=i0, index_max=i1, device=dev)
     L, M = plan.fft_len, plan.spectrum_elems
     nd = len(plan.dims)
-    launches_per_step = nd + 1 + nd * ((plan.n_jobs + plan.jobs_in_flight - 1) // plan.jobs_in_flight)
+    chunks = (plan.n_jobs + plan.jobs_in_flight - 1) // plan.jobs_in_flight
+    fwd0_launches = (plan.spectrum_elems // (plan.fft_len // 2)) if plan.n_blocks > 1 else 1
+    # forward: pass 0 per segment/block + the other passes + norms; inverse: 1/||x|| + nd passes per chunk
+    launches_per_step = fwd0_launches + (nd - 1) + 1 + 1 + nd * chunks
 
     x = make_inputs(torch, R, n, dev, tdt, seed=3000 + rank)
     ccf = torch.empty((P, 1, K), dtype=tdt, device=dev)
@@ -298,12 +301,15 @@ def run_gpu(args):
             rd = R * valid * b if a == 0 else R * per * F * b
             per_step[f"fwd_pass{a}_N{plan.dims[a]}"] = rd + R * per * F * b
             if a == nd - 1:
-                bytes_job = (2 * B if B > 1 else 2) * F * b + (F * b if nd > 1 else K * b)
+                # pair product: every distinct spectrum of the window is read from HBM once per launch
+                # (the pairs that share it are served by L2 / the staged shared-memory rows), one packed
+                # spectrum written per pair
+                bytes_inv = R * per * F * b + plan.n_jobs * (F * b if nd > 1 else K * b)
             elif a == 0:
-                bytes_job = F * b + K * b
+                bytes_inv = (F * b + K * b) * plan.n_jobs
             else:
-                bytes_job = 2 * F * b
-            per_step[f"inv_pass{a}_N{plan.dims[a]}"] = bytes_job * plan.n_jobs
+                bytes_inv = 2 * F * b * plan.n_jobs
+            per_step[f"inv_pass{a}_N{plan.dims[a]}"] = bytes_inv
         table = []
         for name, ms, cnt in kinds:
             if cnt == 0:
@@ -315,7 +321,7 @@ def run_gpu(args):
         dom = max(table, key=lambda t: t["total_ms"])
         # step model of SURVEY 8d: a property of the PROBLEM (full-window transform length L_alg, two HBM
         # passes per transform), independent of how the plan factorises or blocks the work
-        L_alg = 2 * int(np.prod(xb._lib.choose_transform(n)))
+        L_alg = 2 * n                     # SURVEY 8 named shapes: L = 2n is smooth
         b_alg = (R * (n * b + 3 * L_alg * b) + P * (4 * L_alg * b + K * b)) / P
         out = {
             "metric": "pair-days/s (24h@250Hz CCF)" if n == 21_600_000 else "pair-windows/s",

@@ -44,7 +44,7 @@ def timed(fn, steps, warmup):
 def b_alg(N, P, n, L, K, b, n_raw=0):
     """SURVEY 8d bytes per pair-window: [N(F + R) + P I] / P, with the problem's
     full-window transform length (not the plan's, which may use blocks)."""
-    L = 2 * int(np.prod(xb._lib.choose_transform(n)))
+    L = 2 * n                         # SURVEY 8 named shapes: L = 2n is smooth
     F = n * b + 3 * L * b
     R = 2 * n_raw * b + n * b if n_raw else 0
     return (N * (F + R) + P * (4 * L * b + K * b)) / P
