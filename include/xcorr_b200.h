@@ -103,7 +103,8 @@ XCB_API int xcb_plan_get_info(const xcb_plan* plan, xcb_plan_info* info);
  * Replaces the two fft() calls and both np.linalg.norm() of util/cc.py:66-77,
  * done once per receiver-window instead of once per pair.
  *   x      device, dtype[n_signals][x_stride] (x_stride >= n)
- *   spec   device, complex<dtype>[n_signals][spectrum_elems] (digit-transposed packed spectrum)
+ *   spec   device, complex<dtype>[n_signals][spectrum_elems] (half spectrum rfft(x)[k], k < M, in
+ *          digit-transposed order; slot 0 = X[0] + i X[M])
  *   sumsq  device, double[n_signals] */
 XCB_API int xcb_forward(const xcb_plan* plan, const void* x, int64_t x_stride, void* spec, double* sumsq,
                 void* workspace, void* stream);
@@ -151,6 +152,8 @@ typedef struct xcb_sos {
   double coef[12][5];        /* b0 b1 b2 a1 a2 per section (a0 = 1) */
   const double* carry;       /* device, [2S][2S] row-major: state transition over `chunk` samples */
   const double* carry_group; /* device, [2S][2S]: carry^256 (one carry group = 256 chunks) */
+  const double* init_state;  /* device, [n_signals][2S] or NULL: sosfilt(..., zi=) state before the first processed
+                              * sample (scipy layout zi[section][2]); used by sosfiltfilt (signal/filter.py:96) */
 } xcb_sos;
 
 /* stats[s] = {sum x, sum i*x, x[0], x[n-1]} (device double[n_signals][4]) */
@@ -165,6 +168,58 @@ XCB_API int xcb_sosfilt_workspace_bytes(int64_t n, int32_t n_signals, const xcb_
 XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32_t dtype_out, void* y,
                         int64_t y_stride, int64_t n, int32_t n_signals, const xcb_sos* f, const xcb_pointwise* pre,
                         const double* stats, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Plain complex transforms on the same pass kernels, and DFTs of ARBITRARY
+ * length through Bluestein's algorithm.  They replace the numpy / pyfftw calls
+ * of signal/fft.py:15-18,109-112 and the whole-trace FFTs inside obspy
+ * Trace.resample (stream/process.py:61) and signal/timeshift.py:90-96, which
+ * need the DFT of exactly npts points.
+ * ------------------------------------------------------------------------ */
+typedef struct xcb_fft xcb_fft;
+
+/* smallest supported transform length >= n_min (product of 1-4 compiled pass sizes) */
+XCB_API int xcb_fft_good_length(int64_t n_min, int64_t* length);
+XCB_API int xcb_fft_create(xcb_fft** fft, int32_t dtype, int64_t length, int32_t max_batch);
+XCB_API int xcb_fft_destroy(xcb_fft* fft);
+/* spec[b][length] = DFT of x[b][0..n_valid) zero-padded to `length` (sign -1), in the plan's
+ * digit-transposed order: pointwise products of spectra of the same plan need no reordering.
+ *   x device complex<dtype>[batch][x_stride]; spec device complex<dtype>[batch][length] */
+XCB_API int xcb_fft_forward(const xcb_fft* fft, const void* x, int64_t x_stride, int64_t n_valid, int32_t batch,
+                            void* spec, void* stream);
+/* y[b][0..n_out) = (1/length) * inverse DFT of conj(spec_conj[b]); spec_conj (the CONJUGATE of the
+ * spectrum, digit-transposed) is transformed in place and destroyed. */
+XCB_API int xcb_fft_inverse_conj(const xcb_fft* fft, void* spec_conj, int32_t batch, void* y, int64_t y_stride,
+                                 int64_t n_out, void* stream);
+/* y[k] = scale * sum_n x[n] exp(sign * 2 pi i n k / K), k < n_out <= K, for ANY K with 2K - 1 <= length.
+ *   x_mode 0: x real dtype[batch][x_stride]; 1: complex; 2: half spectrum (K/2 + 1 entries) of a real
+ *   signal, extended by conjugate symmetry (irfft; n_in must be K).  n_in <= K samples, zero beyond.
+ *   y complex<dtype>[batch][y_stride], or its real part only (y_real).
+ *   filter_spec device complex<dtype>[length]: spectrum of the chirp filter of (K, sign); written when
+ *   filter_ready == 0, reused afterwards.  work device complex<dtype>[batch * (K + length)]. */
+XCB_API int xcb_dft_bluestein(const xcb_fft* fft, int64_t K, int32_t sign, const void* x, int32_t x_mode,
+                              int64_t x_stride, int64_t n_in, int32_t batch, void* y, int32_t y_real,
+                              int64_t y_stride, int64_t n_out, double scale, void* filter_spec,
+                              int32_t filter_ready, void* work, void* stream);
+
+/* X[b][k] *= exp(-2 pi i * delay[b] * df * k), k < m: the phase ramp of signal/timeshift.py:90-96
+ * (delay: device double[batch], seconds; df: frequency step in Hz). */
+XCB_API int xcb_phase_ramp(int32_t dtype, void* spec, int64_t stride, int64_t m, int32_t batch, const double* delay,
+                           double df, void* stream);
+/* obspy Trace.resample (stream/process.py:52 -> eval at :280): spectrum of npts samples (npts/2 + 1 bins)
+ * times the ifftshift-ed window (0 none, 1 'hann'), linearly interpolated onto the num/2 + 1 bins of the
+ * new length (np.interp semantics, frequency steps df -> dlf). */
+XCB_API int xcb_resample_spectrum(int32_t dtype, const void* spec_in, int64_t in_stride, void* spec_out,
+                                  int64_t out_stride, int64_t npts, int64_t num, double df, double dlf,
+                                  int32_t window, int32_t batch, void* stream);
+/* obspy Trace.interpolate(method='lanczos', a): y[idx] = sum_i x[i] L(dt*idx + offset - i), L = sinc(u) sinc(u/a)
+ * on |u| <= a; dt and offset in units of input samples. */
+XCB_API int xcb_lanczos(int32_t dtype, const void* x, int64_t x_stride, int64_t n_in, void* y, int64_t y_stride,
+                        int64_t n_out, double dt, double offset, int32_t a, int32_t batch, void* stream);
+/* signal/snr.py:107-121: per row max |x| over [sig_begin, sig_end) with its first index, and the sum of
+ * squares over [noise_begin, noise_end).  out: device double[n_rows][3] = {max, index, sumsq}. */
+XCB_API int xcb_window_stats(int32_t dtype, const void* x, int64_t stride, int32_t n_rows, int64_t sig_begin,
+                             int64_t sig_end, int64_t noise_begin, int64_t noise_end, double* out, void* stream);
 
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward

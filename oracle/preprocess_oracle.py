@@ -17,7 +17,7 @@ import numpy as np
 from scipy import signal
 
 __all__ = ["detrend", "cosine_taper", "taper_window", "taper", "butter_sos", "filter_",
-           "cheby2_lowpass_sos", "decimate", "trim", "process"]
+           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "process"]
 
 
 def detrend(x, type="simple"):
@@ -144,6 +144,80 @@ def decimate(x, sampling_rate, factor, no_filter=False):
     return x[::factor].copy(), sampling_rate / float(factor)
 
 
+def resample(x, sampling_rate, new_sampling_rate, window="hann", no_filter=True):
+    """obspy ``Trace.resample`` (Fourier method): real FFT of the
+    whole trace in scipy.fftpack's packed real layout, times the ifftshift-ed window,
+    real and imaginary parts linearly interpolated (``np.interp``) onto the new
+    frequency grid, inverse real FFT to ``num = int(npts / factor)`` samples, scaled
+    by ``num / npts``.  Returns (data, new_sampling_rate)."""
+    x = np.asarray(x, dtype=np.float64)
+    npts = len(x)
+    factor = sampling_rate / float(new_sampling_rate)
+    if not no_filter:
+        if factor > 16:
+            raise ArithmeticError("Automatic filter design is unstable for resampling factors above 16.")
+        x = signal.sosfilt(cheby2_lowpass_sos(sampling_rate, sampling_rate * 0.5 / float(factor)), x)
+    X = np.fft.rfft(x)
+    x_r = X.real.copy()
+    x_i = X.imag.copy()
+    x_i[0] = 0.0
+    if npts % 2 == 0:
+        x_i[-1] = 0.0
+    if window is not None:
+        large_w = np.fft.ifftshift(signal.get_window(window, npts))
+        x_r *= large_w[:npts // 2 + 1]
+        x_i *= large_w[:npts // 2 + 1]
+    num = int(npts / factor)
+    delta = 1.0 / sampling_rate
+    df = 1.0 / (npts * delta)
+    d_large_f = 1.0 / num * new_sampling_rate
+    f = df * np.arange(0, npts // 2 + 1, dtype=np.int32)
+    n_large_f = num // 2 + 1
+    large_f = d_large_f * np.arange(0, n_large_f, dtype=np.int32)
+    y_r = np.interp(large_f, f, x_r)
+    y_i = np.interp(large_f, f, x_i)
+    y_i[0] = 0.0
+    if num % 2 == 0:
+        y_i[-1] = 0.0
+    y = np.fft.irfft(y_r + 1j * y_i, n=num) * (float(num) / float(npts))
+    return y, float(new_sampling_rate)
+
+
+def interpolate_lanczos(x, sampling_rate, new_sampling_rate, a, time_shift=0.0, start_offset=0.0, npts=None):
+    """obspy ``Trace.interpolate(method='lanczos', a=a)`` -> ``lanczos_interpolation`` (C:
+    obspy/signal/src/lanczos.c): windowed-sinc kernel of half-width ``a`` input samples
+    evaluated at the new sample times.  ``start_offset``: new start minus old start in
+    seconds (after ``time_shift``).  Returns (data, new_sampling_rate)."""
+    x = np.asarray(x, dtype=np.float64)
+    old_dt = 1.0 / sampling_rate
+    new_dt = 1.0 / float(new_sampling_rate)
+    old_len = (len(x) - 1) * old_dt
+    start = start_offset
+    if npts is None:
+        npts = int(np.floor((old_len - start) / new_dt)) + 1
+    dt = new_dt / old_dt
+    offset = start / old_dt
+    y = np.zeros(npts)
+    idx = np.arange(npts)
+    pos = dt * idx + offset
+    fl = np.floor(pos).astype(np.int64)
+
+    def sinc(u):
+        out = np.ones_like(u)
+        nz = np.abs(u) >= 1e-10
+        out[nz] = np.sin(np.pi * u[nz]) / (np.pi * u[nz])
+        return out
+
+    for m in range(-a, a + 1):
+        i = fl - m
+        ok = (i >= 0) & (i < len(x))
+        u = pos - i
+        ok &= (u >= -a) & (u <= a)
+        ii = np.where(ok, i, 0)
+        y += np.where(ok, x[ii] * sinc(u) * sinc(u / a), 0.0)
+    return y, float(new_sampling_rate)
+
+
 def trim(x, start=0, length=None):
     """Array form of the time-based trims (``stream/client.py:1017`` and
     ``core/process.py:156-157``): samples ``[start, start+length)``."""
@@ -167,6 +241,14 @@ def process(x, sampling_rate, operations):
             y, fs = decimate(y, fs, **params)
         elif name == "trim":
             y = trim(y, **params)
+        elif name == "resample":
+            params = dict(params)
+            y, fs = resample(y, fs, params.pop("sampling_rate"), **params)
+        elif name == "interpolate":
+            params = dict(params)
+            if params.pop("method", None) != "lanczos":
+                raise NotImplementedError("only method='lanczos' is restated")
+            y, fs = interpolate_lanczos(y, fs, params.pop("sampling_rate"), **params)
         else:
             raise NotImplementedError(f"operation {name!r} is outside the array-valued hot path")
     return y, fs

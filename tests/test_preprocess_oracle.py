@@ -78,3 +78,61 @@ def test_process_chain_config2():
     y, fs2 = pre.process(x, fs, ops)
     assert fs2 == 50.0 and len(y) == n // 5 and abs(y.mean()) < 1e-3 * np.std(y) + 1e-12
     assert y[0] == 0.0 and abs(y[-1]) < 1e-12
+
+
+# ---- sampling-rate changes and the CCF post-processing restatements (known answers) ----
+def test_resample_known_answers():
+    from oracle import preprocess_oracle as pre
+    fs, new_fs, n = 40.0, 50.0, 4000
+    t = np.arange(n) / fs
+    f0 = 1.0
+    y, fo = pre.resample(np.sin(2 * np.pi * f0 * t), fs, new_fs)
+    assert fo == new_fs and len(y) == int(n / (fs / new_fs)) == 5000
+    # a bin-centred sinusoid keeps its frequency; its amplitude is the Hann spectral window at f0
+    gain = 0.5 + 0.5 * np.cos(np.pi * f0 / (fs / 2))
+    ref = gain * np.sin(2 * np.pi * f0 * np.arange(5000) / new_fs)
+    assert np.max(np.abs(y - ref)) < 1e-9
+    # no window: exact band-limited interpolation; same rate: identity
+    y, _ = pre.resample(np.sin(2 * np.pi * f0 * t), fs, new_fs, window=None)
+    assert np.max(np.abs(y - np.sin(2 * np.pi * f0 * np.arange(5000) / new_fs))) < 1e-9
+    x = np.random.default_rng(0).standard_normal(1001)
+    y, _ = pre.resample(x, 20.0, 20.0, window=None)
+    assert np.max(np.abs(y - x)) < 1e-12
+    # downsampling by 5 keeps int(npts / 5) samples
+    assert len(pre.resample(np.zeros(21_601), 250.0, 50.0)[0]) == 4320
+
+
+def test_lanczos_known_answers():
+    from oracle import preprocess_oracle as pre
+    x = np.random.default_rng(1).standard_normal(500)
+    # same rate, no shift: the kernel is 1 at 0 and 0 at the other integers -> identity
+    y, _ = pre.interpolate_lanczos(x, 10.0, 10.0, a=5)
+    assert len(y) == 500 and np.max(np.abs(y - x)) < 1e-12
+    # output length: floor(duration / new_dt) + 1
+    assert len(pre.interpolate_lanczos(x, 10.0, 25.0, a=5)[0]) == int(np.floor(49.9 * 25.0)) + 1
+    # a slow sinusoid is reproduced between the samples
+    t = np.arange(2000) / 40.0
+    y, _ = pre.interpolate_lanczos(np.sin(2 * np.pi * 0.5 * t), 40.0, 50.0, a=20)
+    tn = np.arange(len(y)) / 50.0
+    assert np.max(np.abs(y[100:-100] - np.sin(2 * np.pi * 0.5 * tn)[100:-100])) < 5e-4   # Lanczos kernel ripple
+
+
+def test_signal_oracle_known_answers():
+    from oracle import signal_oracle as so
+    n, fs = 2000, 50.0
+    x = np.random.default_rng(2).standard_normal((2, n))
+    # integer-sample delay == circular roll; zero delay == identity
+    assert np.max(np.abs(so.timeshift(x, 5 / fs, 0.0, 1 / fs) - np.roll(x, 5, axis=-1))) < 1e-12
+    assert np.max(np.abs(so.timeshift(x, 0.0, 0.0, 1 / fs) - x)) < 1e-13
+    assert so.timeshift(x[:, :1999], 0.0, 0.0, 1 / fs).shape[-1] == 1998       # odd length: one sample trimmed
+    # window: ones in the middle, periodic Hann halves of nmax samples at both ends
+    w = so.window(n, fs, max_length=5.0)
+    assert w[0] == 0.0 and np.all(w[250:-250] == 1.0) and abs(w[125] - 0.5) < 1e-12
+    # zero-phase high-pass removes the mean and keeps a 10 Hz line's phase
+    t = np.arange(n) / fs
+    y = so.filter(np.sin(2 * np.pi * 10 * t) + 4.0, fs, 3.0)
+    assert abs(np.mean(y[200:-200])) < 1e-3
+    assert np.max(np.abs(y[200:-200] - np.sin(2 * np.pi * 10 * t)[200:-200])) < 5e-3
+    r, s, nn, idx = so.snr(np.r_[np.ones(10), [-7.0], np.ones(9)], np.r_[np.zeros(8, bool), np.ones(12, bool)],
+                           np.r_[np.ones(8, bool), np.zeros(12, bool)])
+    assert s == 7.0 and nn == 1.0 and idx == 10 and r == 7.0

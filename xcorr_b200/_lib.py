@@ -80,6 +80,7 @@ class xcb_sos(ctypes.Structure):
         ("coef", (ctypes.c_double * 5) * 12),
         ("carry", ctypes.POINTER(ctypes.c_double)),
         ("carry_group", ctypes.POINTER(ctypes.c_double)),
+        ("init_state", ctypes.POINTER(ctypes.c_double)),
     ]
 
 
@@ -107,6 +108,19 @@ SYMBOLS = {
     "xcb_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "xcb_profile_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(_i64)]),
+    "xcb_fft_good_length": (ctypes.c_int, [_i64, ctypes.POINTER(_i64)]),
+    "xcb_fft_create": (ctypes.c_int, [ctypes.POINTER(_vp), _i32, _i64, _i32]),
+    "xcb_fft_destroy": (ctypes.c_int, [_vp]),
+    "xcb_fft_forward": (ctypes.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp]),
+    "xcb_fft_inverse_conj": (ctypes.c_int, [_vp, _vp, _i32, _vp, _i64, _i64, _vp]),
+    "xcb_dft_bluestein": (ctypes.c_int, [_vp, _i64, _i32, _vp, _i32, _i64, _i64, _i32, _vp, _i32, _i64, _i64,
+                                         ctypes.c_double, _vp, _i32, _vp, _vp]),
+    "xcb_phase_ramp": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, ctypes.c_double, _vp]),
+    "xcb_resample_spectrum": (ctypes.c_int, [_i32, _vp, _i64, _vp, _i64, _i64, _i64, ctypes.c_double,
+                                             ctypes.c_double, _i32, _i32, _vp]),
+    "xcb_lanczos": (ctypes.c_int, [_i32, _vp, _i64, _i64, _vp, _i64, _i64, ctypes.c_double, ctypes.c_double, _i32,
+                                   _i32, _vp]),
+    "xcb_window_stats": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
     "xcb_cc_host": (ctypes.c_int, [_i32, _i64, _vp, _vp, _i32, _i32, _i64, _i64, _vp]),
 }
 

@@ -1,4 +1,6 @@
 """Mirror of the reference's ``xcorr.core`` namespace for the hot path:
-``init`` (CF-1.9 variable layout) and the batched ``process`` driver."""
+``init`` (CF-1.9 variable layout), the batched ``process`` driver and the predefined
+``postprocess`` chain."""
 from .init import init, CCDataset, Variable  # noqa: F401
 from .process import process  # noqa: F401
+from .postprocess import postprocess  # noqa: F401

@@ -601,6 +601,266 @@ extern "C" int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64
 }
 
 // ---------------------------------------------------------------------------
+// Plain complex transforms on the same pass kernels, and Bluestein's chirp-z
+// for arbitrary lengths (obspy Trace.resample, signal/timeshift.py need the
+// DFT of exactly npts points).
+// ---------------------------------------------------------------------------
+struct xcb_fft {
+  xcb_plan* pl = nullptr;        // geometry, twiddle tables, launchers (no pairs)
+  Job* d_jobs = nullptr;         // output offsets of the inverse epilogue
+  int32_t max_batch = 0;
+};
+
+__global__ void xcb_fill_jobs(Job* jobs, int32_t n, int64_t out_stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { Job j; j.spec_i = j.spec_j = 0; j.sig_i = j.sig_j = 0; j.out_off = (int64_t)i * out_stride; jobs[i] = j; }
+}
+
+extern "C" int xcb_fft_good_length(int64_t n_min, int64_t* length) {
+  if (n_min < 1 || !length) return XCB_ERR_ARG;
+  int d[kMaxDims] = {0, 0, 0, 0}, k = 0;
+  if (!plan_choose_dims(n_min, d, &k)) return XCB_ERR_SIZE;
+  int64_t m = 1;
+  for (int a = 0; a < k; ++a) m *= d[a];
+  *length = m;
+  return XCB_OK;
+}
+
+extern "C" int xcb_fft_destroy(xcb_fft* f) {
+  if (!f) return XCB_OK;
+  xcb_plan_destroy(f->pl);
+  cudaFree(f->d_jobs);
+  delete f;
+  return XCB_OK;
+}
+
+extern "C" int xcb_fft_create(xcb_fft** out, int32_t dtype, int64_t length, int32_t max_batch) {
+  if (!out || length < 1 || max_batch < 1) return XCB_ERR_ARG;
+  *out = nullptr;
+  int d[kMaxDims] = {0, 0, 0, 0}, k = 0;
+  if (!plan_choose_dims(length, d, &k)) return XCB_ERR_SIZE;
+  int64_t m = 1;
+  for (int a = 0; a < k; ++a) m *= d[a];
+  if (m != length) return XCB_ERR_SIZE;            // use xcb_fft_good_length
+  xcb_desc desc;
+  memset(&desc, 0, sizeof(desc));
+  desc.n = length;
+  desc.dtype = dtype;
+  desc.nd = k;
+  for (int a = 0; a < k; ++a) desc.dims[a] = d[a];
+  desc.n_receivers = 1;
+  desc.n_windows = 1;
+  desc.n_blocks = 1;
+  xcb_fft* f = new (std::nothrow) xcb_fft();
+  if (!f) return XCB_ERR_ALLOC;
+  int rc = xcb_plan_create(&f->pl, &desc);
+  if (rc) { delete f; return rc; }
+  f->max_batch = max_batch;
+  cudaError_t e = cudaMalloc(&f->d_jobs, sizeof(Job) * (size_t)max_batch);
+  if (e != cudaSuccess) { xcb_fft_destroy(f); return cuda_fail(e, "cudaMalloc(fft jobs)"); }
+  *out = f;
+  return XCB_OK;
+}
+
+template <class T>
+static int fft_forward_t(const xcb_fft* f, const void* x, int64_t x_stride, int64_t n_valid, int32_t batch, void* spec,
+                         cudaStream_t st) {
+  const xcb_plan* pl = f->pl;
+  const PlanGeom& g = pl->g;
+  DevTables<T> tb = dev_tables<T>(pl);
+  DeviceRunner<T> run{pl, st};
+  for (int a = 0; a < g.nd; ++a) {
+    // interleaved complex input == packed real input of 2 n_valid samples
+    PassParams<T> p = make_forward_pass<T>(g, tb, a, static_cast<const T*>(x), 2 * x_stride, static_cast<cx<T>*>(spec),
+                                           g.M, batch, nullptr, 2 * n_valid, 0);
+    if (a == g.nd - 1) p.store_mode = RS_CPLX;      // no real <-> packed conversion
+    if (!run(p, a == g.nd - 1, a))
+      return run.err < 0 ? XCB_ERR_UNSUPPORTED : cuda_fail((cudaError_t)run.err, "fft forward launch");
+  }
+  return XCB_OK;
+}
+
+extern "C" int xcb_fft_forward(const xcb_fft* f, const void* x, int64_t x_stride, int64_t n_valid, int32_t batch,
+                               void* spec, void* stream) {
+  if (!f || !x || !spec || batch < 1 || n_valid < 0 || n_valid > f->pl->g.M || x_stride < n_valid) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return f->pl->dtype == XCB_F32 ? fft_forward_t<float>(f, x, x_stride, n_valid, batch, spec, st)
+                                 : fft_forward_t<double>(f, x, x_stride, n_valid, batch, spec, st);
+}
+
+template <class T>
+static int fft_inverse_t(const xcb_fft* f, void* spec, int32_t batch, void* y, int64_t y_stride, int64_t n_out,
+                         cudaStream_t st) {
+  const xcb_plan* pl = f->pl;
+  const PlanGeom& g = pl->g;
+  DevTables<T> tb = dev_tables<T>(pl);
+  xcb_fill_jobs<<<(batch + 127) / 128, 128, 0, st>>>(f->d_jobs, batch, 2 * y_stride);
+  XCB_CUDA(cudaGetLastError());
+  CorrFlags fl;
+  fl.i0 = 0;
+  fl.i1 = 2 * n_out;
+  fl.normalize = 0;
+  DeviceRunner<T> run{pl, st};
+  for (int a = g.nd - 1; a >= 0; --a) {
+    PassParams<T> p = make_inverse_pass<T>(g, tb, a, nullptr, nullptr, f->d_jobs, batch, static_cast<cx<T>*>(spec),
+                                           static_cast<T*>(y), fl);
+    // output element m = (re, im) of point m: the "direct" lag epilogue with 2 n_out kept reals
+    p.epi_direct = 1;
+    p.keep_lo[0] = p.keep_lo[1] = p.keep_hi[1] = 0;
+    p.keep_hi[0] = g.nd > 1 ? (int32_t)((n_out - 1) / g.S[1] + 1) : 0;
+    if (a == g.nd - 1) {               // the spectrum is given (already conjugated), not a pair product
+      p.load_mode = RL_CPLX;
+      p.tile_major = 0;
+    }
+    if (!run(p, a == g.nd - 1, g.nd + a))
+      return run.err < 0 ? XCB_ERR_UNSUPPORTED : cuda_fail((cudaError_t)run.err, "fft inverse launch");
+  }
+  return XCB_OK;
+}
+
+extern "C" int xcb_fft_inverse_conj(const xcb_fft* f, void* spec_conj, int32_t batch, void* y, int64_t y_stride,
+                                    int64_t n_out, void* stream) {
+  if (!f || !spec_conj || !y || batch < 1 || batch > f->max_batch || n_out < 1 || n_out > f->pl->g.M ||
+      y_stride < n_out)
+    return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return f->pl->dtype == XCB_F32 ? fft_inverse_t<float>(f, spec_conj, batch, y, y_stride, n_out, st)
+                                 : fft_inverse_t<double>(f, spec_conj, batch, y, y_stride, n_out, st);
+}
+
+// chirp w[k] = exp(sign * i pi k^2 / K): the phase is reduced exactly in integers (k^2 mod 2K)
+__device__ __forceinline__ void chirp(int64_t k, int64_t K, int sign, double& c, double& s) {
+  const unsigned long long kk = (unsigned long long)(k % (2 * K));       // < 2^32 for every supported K
+  const unsigned long long r = (kk * kk) % (unsigned long long)(2 * K);
+  sincospi((double)r / (double)K, &s, &c);
+  s *= (double)sign;
+}
+
+// a[b][k] = x[b][k] * chirp(k), k < n.  MODE 0: x real; 1: x complex; 2: x is the half spectrum
+// (K/2 + 1 entries) of a real signal, extended to all K frequencies by conjugate symmetry (imaginary
+// parts of the zero and Nyquist bins ignored, like numpy's irfft).
+template <class T, int MODE>
+__global__ void xcb_chirp_in(const void* __restrict__ x, int64_t x_stride, cx<T>* __restrict__ a, int64_t a_stride,
+                             int64_t n, int64_t K, int sign) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t b = blockIdx.y;
+  double c, s;
+  chirp(k, K, sign, c, s);
+  double re, im = 0.0;
+  if (MODE == 0) {
+    re = static_cast<const T*>(x)[b * x_stride + k];
+  } else if (MODE == 1) {
+    const cx<T> v = static_cast<const cx<T>*>(x)[b * x_stride + k];
+    re = v.x; im = v.y;
+  } else {
+    const int64_t kh = k <= K / 2 ? k : K - k;
+    const cx<T> v = static_cast<const cx<T>*>(x)[b * x_stride + kh];
+    re = v.x;
+    im = k <= K / 2 ? (double)v.y : -(double)v.y;
+    if (k == 0 || 2 * k == K) im = 0.0;
+  }
+  cx<T> o; o.x = (T)(re * c - im * s); o.y = (T)(re * s + im * c);
+  a[b * a_stride + k] = o;
+}
+
+// filter b[m] = chirp(-sign)(m) for |m| < K, circular over M points
+template <class T> __global__ void xcb_chirp_filter(cx<T>* __restrict__ bf, int64_t M, int64_t K, int sign) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  cx<T> o; o.x = o.y = T(0);
+  int64_t d = -1;
+  if (m < K) d = m; else if (M - m < K) d = M - m;
+  if (d >= 0) { double c, s; chirp(d, K, -sign, c, s); o.x = (T)c; o.y = (T)s; }
+  bf[m] = o;
+}
+
+// out = conj(a * b)  (both digit-transposed spectra of the same plan; b is shared by the batch)
+template <class T>
+__global__ void xcb_mul_conj(cx<T>* __restrict__ a, const cx<T>* __restrict__ b, int64_t M) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  cx<T>* row = a + (int64_t)blockIdx.y * M;
+  const cx<T> v = cmul(row[m], b[m]);
+  row[m] = cconj(v);
+}
+
+// y[b][k] = scale * c[b][k] * chirp(k) (optionally conjugated / real part only)
+template <class T, bool REAL_OUT>
+__global__ void xcb_chirp_out(const cx<T>* __restrict__ c_, int64_t c_stride, void* __restrict__ y, int64_t y_stride,
+                              int64_t K, int64_t n_out, int sign, int conj_out, double scale) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_out) return;
+  double c, s;
+  chirp(k, K, sign, c, s);
+  const cx<T> v = c_[(int64_t)blockIdx.y * c_stride + k];
+  const double re = ((double)v.x * c - (double)v.y * s) * scale, im = ((double)v.x * s + (double)v.y * c) * scale;
+  if (REAL_OUT) static_cast<T*>(y)[(int64_t)blockIdx.y * y_stride + k] = (T)re;
+  else { cx<T> o; o.x = (T)re; o.y = (T)(conj_out ? -im : im); static_cast<cx<T>*>(y)[(int64_t)blockIdx.y * y_stride + k] = o; }
+}
+
+template <class T>
+static int bluestein_t(const xcb_fft* f, int64_t K, int32_t sign, const void* x, int32_t x_complex, int64_t x_stride,
+                       int64_t n_in, int32_t batch, void* y, int32_t y_real, int64_t y_stride, int64_t n_out,
+                       double scale, void* filter_spec, int32_t filter_ready, void* work, cudaStream_t st) {
+  const int64_t M = f->pl->g.M;
+  cx<T>* a = static_cast<cx<T>*>(work);                 // [batch][K] chirped input, later [batch][n_out] result
+  cx<T>* spec = a + (int64_t)batch * K;                 // [batch][M]
+  cx<T>* bf = static_cast<cx<T>*>(filter_spec);         // [M] spectrum of the chirp filter
+  const int TB = 256;
+  if (!filter_ready) {
+    // the filter's time series is built in `spec` (scratch) and transformed into bf
+    xcb_chirp_filter<T><<<(unsigned)((M + TB - 1) / TB), TB, 0, st>>>(spec, M, K, sign);
+    XCB_CUDA(cudaGetLastError());
+    int rc = xcb_fft_forward(f, spec, M, M, 1, bf, st);
+    if (rc) return rc;
+  }
+  // x is zero beyond n_in (n_in <= K); the DFT sign convention: sign = -1 forward, +1 backward
+  XCB_CUDA(cudaMemsetAsync(a, 0, sizeof(cx<T>) * (size_t)batch * K, st));
+  dim3 gi((unsigned)((n_in + TB - 1) / TB), (unsigned)batch);
+  if (x_complex == 2) xcb_chirp_in<T, 2><<<gi, TB, 0, st>>>(x, x_stride, a, K, n_in, K, sign);
+  else if (x_complex == 1) xcb_chirp_in<T, 1><<<gi, TB, 0, st>>>(x, x_stride, a, K, n_in, K, sign);
+  else xcb_chirp_in<T, 0><<<gi, TB, 0, st>>>(x, x_stride, a, K, n_in, K, sign);
+  XCB_CUDA(cudaGetLastError());
+  // NB: the chirp of sample k uses length K even when n_in < K (zero-padded DFT of K points)
+  int rc = xcb_fft_forward(f, a, K, K, batch, spec, st);
+  if (rc) return rc;
+  dim3 gm((unsigned)((M + TB - 1) / TB), (unsigned)batch);
+  xcb_mul_conj<T><<<gm, TB, 0, st>>>(spec, bf, M);
+  XCB_CUDA(cudaGetLastError());
+  rc = xcb_fft_inverse_conj(f, spec, batch, a, K, n_out, st);
+  if (rc) return rc;
+  dim3 go((unsigned)((n_out + TB - 1) / TB), (unsigned)batch);
+  if (y_real) xcb_chirp_out<T, true><<<go, TB, 0, st>>>(a, K, y, y_stride, K, n_out, sign, 0, scale);
+  else xcb_chirp_out<T, false><<<go, TB, 0, st>>>(a, K, y, y_stride, K, n_out, sign, 0, scale);
+  XCB_CUDA(cudaGetLastError());
+  return XCB_OK;
+}
+
+// DFT of exactly K points (any K) of `batch` signals through Bluestein's algorithm on a plan of
+// length M >= 2K - 1:  y[k] = scale * sum_n x[n] exp(sign * 2 pi i n k / K), k < n_out <= K.
+//   x     device, real dtype[batch][x_stride] (x_complex 0), complex (1), or the half spectrum of a real signal
+//         (2: K/2 + 1 complex entries per signal, n_in = K); n_in <= K samples (zero beyond)
+//   y     device, complex[batch][y_stride], or real part only (y_real)
+//   filter_spec  device complex[M]: spectrum of the chirp filter; computed when !filter_ready (cache it per (K, sign))
+//   work  device, complex[batch * (K + M)]
+extern "C" int xcb_dft_bluestein(const xcb_fft* f, int64_t K, int32_t sign, const void* x, int32_t x_complex,
+                                 int64_t x_stride, int64_t n_in, int32_t batch, void* y, int32_t y_real,
+                                 int64_t y_stride, int64_t n_out, double scale, void* filter_spec,
+                                 int32_t filter_ready, void* work, void* stream) {
+  if (!f || !x || !y || !filter_spec || !work || K < 1 || batch < 1 || batch > f->max_batch) return XCB_ERR_ARG;
+  if (x_complex < 0 || x_complex > 2 || (x_complex == 2 && n_in != K)) return XCB_ERR_ARG;
+  if ((sign != 1 && sign != -1) || n_in < 1 || n_in > K || n_out < 1 || n_out > K) return XCB_ERR_ARG;
+  if (f->pl->g.M < 2 * K - 1) return XCB_ERR_SIZE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return f->pl->dtype == XCB_F32
+             ? bluestein_t<float>(f, K, sign, x, x_complex, x_stride, n_in, batch, y, y_real, y_stride, n_out, scale,
+                                  filter_spec, filter_ready, work, st)
+             : bluestein_t<double>(f, K, sign, x, x_complex, x_stride, n_in, batch, y, y_real, y_stride, n_out, scale,
+                                   filter_spec, filter_ready, work, st);
+}
+
+// ---------------------------------------------------------------------------
 // cc() with host buffers
 // ---------------------------------------------------------------------------
 extern "C" int xcb_cc_host(int32_t dtype, int64_t n, const void* x, const void* y, int32_t normalize,

@@ -923,7 +923,7 @@ template <class T, int R1, int R2> struct RowWarp {
       if (s.j >= R2) return;
 #pragma unroll
       for (int r = 0; r < R1; ++r) s.buf[s.j * P1 + r] = v[r];         // stage layout
-    } else {
+    } else if (p.store_mode == RS_HALF) {
 #pragma unroll
       for (int r = 0; r < R2; ++r) s.buf[s.j + r * R1] = v[r];         // publish Z (linear index)
     }
@@ -944,6 +944,17 @@ template <class T, int R1, int R2> struct RowWarp {
 #pragma unroll
           for (int r = 0; r < R2; ++r) dst[r * R1] = cconj(v[r]);
         }
+      } else if (p.store_mode == RS_EPI) {
+        // plain complex transform, last inverse pass of a single-pass plan: interleaved output
+        T* outp = p.ccf + p.jobs[s.batch].out_off;
+#pragma unroll
+        for (int r = 0; r < R2; ++r)
+          epilogue_store(p, outp, (uint32_t)(s.row * N + s.j + r * R1), v[r].x, -v[r].y);
+      } else if (p.store_mode != RS_HALF) {
+        // plain complex transform (xcb_fft_*): no real <-> packed conversion
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) dst[r * R1] = p.store_mode == RS_CONJ ? cconj(v[r]) : v[r];
       } else {
         // X[k] = (S - i W D)/2 with S = Z[k] + conj(Z[M-k]), D = Z[k] - conj(Z[M-k]), W = W_L^k
         const cx<T> wrow = s.wrow;

@@ -353,13 +353,13 @@ __global__ void __launch_bounds__(32) sos_carry_group(const double* __restrict__
 // sequential sweep over groups (one warp per signal): gstate holds e_g on entry,
 // the group START states on exit; PG = P^kGroup.
 __global__ void __launch_bounds__(32) sos_carry_sweep(int d, int64_t n_groups, const double* __restrict__ PG,
-                                                      double* __restrict__ gstate) {
+                                                      double* __restrict__ gstate, const double* __restrict__ init) {
   const int lane = threadIdx.x;
   const int64_t sig = blockIdx.x;
   double prow[24];
 #pragma unroll
   for (int k = 0; k < 24; ++k) prow[k] = (lane < d && k < d) ? PG[lane * d + k] : 0.0;
-  double s = 0.0;
+  double s = (init && lane < d) ? init[sig * d + lane] : 0.0;   // sosfilt(..., zi=...): state before the first sample
   double* base = gstate + sig * n_groups * d;
   constexpr int kPf = 8;
   double cur[kPf], nxt[kPf];
@@ -552,7 +552,7 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   if (run_phase_s(f->n_sections, 1, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
   const unsigned ng = (unsigned)((int64_t)n_signals * L.n_groups);
   sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 0, dg, ds);
-  sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg);
+  sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg, f->init_state);
   sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 2, dg, ds);
   if (cudaGetLastError() != cudaSuccess) return XCB_ERR_CUDA;
   if (run_phase_s(f->n_sections, 3, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;

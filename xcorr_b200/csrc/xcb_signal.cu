@@ -1,0 +1,200 @@
+// Small array kernels next to the FFT path: spectral resampling and Lanczos
+// interpolation (obspy Trace.resample / Trace.interpolate, named by the
+// reference's op-lists, stream/process.py:51-52), the phase ramp of
+// signal/timeshift.py:90-96 and the window statistics of signal/snr.py:107-121.
+// Arithmetic is float64 whatever the storage dtype.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/xcorr_b200.h"
+
+namespace {
+
+template <class T> struct c2 { T x, y; };
+
+// X[b][k] *= exp(-2 pi i * delay[b] * df * k)
+template <class T>
+__global__ void k_phase_ramp(c2<T>* __restrict__ X, int64_t stride, int64_t m, const double* __restrict__ delay,
+                             double df) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int64_t b = blockIdx.y;
+  // phase in turns, reduced before the sincos
+  double turns = delay[b] * (df * (double)k);
+  turns -= floor(turns);
+  double s, c;
+  sincospi(-2.0 * turns, &s, &c);
+  c2<T>* p = X + b * stride + k;
+  const double re = p->x, im = p->y;
+  p->x = (T)(re * c - im * s);
+  p->y = (T)(re * s + im * c);
+}
+
+// obspy Trace.resample: windowed spectrum on the old frequency grid f = df * k,
+// k <= npts/2, linearly interpolated (np.interp, clamped at the ends) onto
+// large_f = dlf * j, j <= num/2.  window: 0 none, 1 'hann' (periodic,
+// ifftshift-ed: large_w[k] = 0.5 - 0.5 cos(2 pi (k + npts/2) / npts)).
+// The fftpack real format drops the imaginary parts of the zero bin and (num
+// even) of the last bin.
+template <class T>
+__global__ void k_resample_spectrum(const c2<T>* __restrict__ X, int64_t x_stride, c2<T>* __restrict__ Y,
+                                    int64_t y_stride, int64_t npts, int64_t num, double df, double dlf, int window) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t m_in = npts / 2 + 1, m_out = num / 2 + 1;
+  if (j >= m_out) return;
+  const int64_t b = blockIdx.y;
+  const c2<T>* x = X + b * x_stride;
+  auto win = [&](int64_t k) -> double {
+    if (window == 0) return 1.0;
+    return 0.5 - 0.5 * cospi(2.0 * (double)((k + npts / 2) % npts) / (double)npts);
+  };
+  // fftpack layout: x_r[k] = Re X[k]; x_i[0] = 0, x_i[k] = Im X[k], and for even npts x_i[npts/2] = 0
+  auto xr = [&](int64_t k) -> double { return (double)x[k].x * win(k); };
+  auto xi = [&](int64_t k) -> double {
+    if (k == 0 || (npts % 2 == 0 && k == npts / 2)) return 0.0;
+    return (double)x[k].y * win(k);
+  };
+  const double lf = dlf * (double)j;
+  double re, im;
+  const double f_last = df * (double)(m_in - 1);
+  if (lf >= f_last) { re = xr(m_in - 1); im = xi(m_in - 1); }
+  else {
+    // np.interp: largest k with f[k] <= lf
+    int64_t k = (int64_t)floor(lf / df);
+    if (k < 0) k = 0;
+    if (k > m_in - 2) k = m_in - 2;
+    while (k > 0 && df * (double)k > lf) --k;
+    while (k < m_in - 2 && df * (double)(k + 1) <= lf) ++k;
+    const double f0 = df * (double)k, f1 = df * (double)(k + 1);
+    const double r0 = xr(k), r1 = xr(k + 1), i0 = xi(k), i1 = xi(k + 1);
+    re = (r1 - r0) / (f1 - f0) * (lf - f0) + r0;
+    im = (i1 - i0) / (f1 - f0) * (lf - f0) + i0;
+  }
+  if (j == 0 || (num % 2 == 0 && j == num / 2)) im = 0.0;
+  c2<T> o; o.x = (T)re; o.y = (T)im;
+  Y[b * y_stride + j] = o;
+}
+
+__device__ __forceinline__ double sinc_pi(double x) {
+  if (fabs(x) < 1e-10) return 1.0;
+  return sinpi(x) / (M_PI * x);
+}
+
+// obspy lanczos_resample (signal/src/lanczos.c): y[idx] = sum_{m=-a..a} x[i] L(pos - i), i = floor(pos) - m,
+// pos = dt * idx + offset in units of input samples, L(u) = sinc(u) sinc(u / a) on |u| <= a.
+template <class T>
+__global__ void k_lanczos(const T* __restrict__ x, int64_t x_stride, int64_t n_in, T* __restrict__ y,
+                          int64_t y_stride, int64_t n_out, double dt, double offset, int a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_out) return;
+  const int64_t b = blockIdx.y;
+  const T* xs = x + b * x_stride;
+  const double pos = dt * (double)idx + offset;
+  const int64_t fl = (int64_t)floor(pos);
+  double acc = 0.0;
+  for (int m = -a; m <= a; ++m) {
+    const int64_t i = fl - m;
+    if (i < 0 || i >= n_in) continue;
+    const double u = pos - (double)i;
+    if (u < -(double)a || u > (double)a) continue;
+    acc += (double)xs[i] * sinc_pi(u) * sinc_pi(u / (double)a);
+  }
+  y[b * y_stride + idx] = (T)acc;
+}
+
+// Per row: max |x| and its first index over [s0, s1), sum of squares over [n0, n1).  One block per row,
+// fixed association order (bit-reproducible).
+template <class T>
+__global__ void __launch_bounds__(256) k_window_stats(const T* __restrict__ x, int64_t stride, int64_t s0, int64_t s1,
+                                                      int64_t n0, int64_t n1, double* __restrict__ out) {
+  const T* r = x + (int64_t)blockIdx.x * stride;
+  double best = -1.0, ss = 0.0;
+  int64_t bi = -1;
+  bool nan_seen = false;
+  for (int64_t i = s0 + threadIdx.x; i < s1; i += 256) {
+    const double v = fabs((double)r[i]);
+    if (v != v) { if (!nan_seen) { nan_seen = true; best = v; bi = i; } continue; }
+    if (!nan_seen && v > best) { best = v; bi = i; }
+  }
+  for (int64_t i = n0 + threadIdx.x; i < n1; i += 256) { const double v = (double)r[i]; ss += v * v; }
+  __shared__ double sv[256], sq[256];
+  __shared__ int64_t si[256];
+  __shared__ int sn[256];
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi; sq[threadIdx.x] = ss; sn[threadIdx.x] = nan_seen ? 1 : 0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const int a = threadIdx.x, b = threadIdx.x + o;
+      sq[a] += sq[b];
+      bool take;
+      if (sn[a] != sn[b]) take = sn[b] > sn[a];
+      else if (sn[a]) take = si[b] >= 0 && (si[a] < 0 || si[b] < si[a]);
+      else take = si[b] >= 0 && (si[a] < 0 || sv[b] > sv[a] || (sv[b] == sv[a] && si[b] < si[a]));
+      if (take) { sv[a] = sv[b]; si[a] = si[b]; sn[a] = sn[b]; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* o = out + (int64_t)blockIdx.x * 3;
+    o[0] = sv[0];
+    o[1] = (double)si[0];
+    o[2] = sq[0];
+  }
+}
+
+int fail(cudaError_t e) { return e == cudaSuccess ? XCB_OK : XCB_ERR_CUDA; }
+
+}  // namespace
+
+extern "C" int xcb_phase_ramp(int32_t dtype, void* spec, int64_t stride, int64_t m, int32_t batch,
+                              const double* delay, double df, void* stream) {
+  if (!spec || !delay || m < 1 || batch < 1 || stride < m) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)batch);
+  if (dtype == XCB_F32) k_phase_ramp<float><<<grid, 256, 0, st>>>(static_cast<c2<float>*>(spec), stride, m, delay, df);
+  else if (dtype == XCB_F64) k_phase_ramp<double><<<grid, 256, 0, st>>>(static_cast<c2<double>*>(spec), stride, m, delay, df);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_resample_spectrum(int32_t dtype, const void* spec_in, int64_t in_stride, void* spec_out,
+                                     int64_t out_stride, int64_t npts, int64_t num, double df, double dlf,
+                                     int32_t window, int32_t batch, void* stream) {
+  if (!spec_in || !spec_out || npts < 2 || num < 1 || batch < 1 || window < 0 || window > 1) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((num / 2 + 1 + 255) / 256), (unsigned)batch);
+  if (dtype == XCB_F32)
+    k_resample_spectrum<float><<<grid, 256, 0, st>>>(static_cast<const c2<float>*>(spec_in), in_stride,
+                                                     static_cast<c2<float>*>(spec_out), out_stride, npts, num, df, dlf, window);
+  else if (dtype == XCB_F64)
+    k_resample_spectrum<double><<<grid, 256, 0, st>>>(static_cast<const c2<double>*>(spec_in), in_stride,
+                                                      static_cast<c2<double>*>(spec_out), out_stride, npts, num, df, dlf, window);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_lanczos(int32_t dtype, const void* x, int64_t x_stride, int64_t n_in, void* y, int64_t y_stride,
+                           int64_t n_out, double dt, double offset, int32_t a, int32_t batch, void* stream) {
+  if (!x || !y || n_in < 1 || n_out < 1 || a < 1 || batch < 1) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((n_out + 255) / 256), (unsigned)batch);
+  if (dtype == XCB_F32)
+    k_lanczos<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), x_stride, n_in, static_cast<float*>(y), y_stride, n_out, dt, offset, a);
+  else if (dtype == XCB_F64)
+    k_lanczos<double><<<grid, 256, 0, st>>>(static_cast<const double*>(x), x_stride, n_in, static_cast<double*>(y), y_stride, n_out, dt, offset, a);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_window_stats(int32_t dtype, const void* x, int64_t stride, int32_t n_rows, int64_t sig_begin,
+                                int64_t sig_end, int64_t noise_begin, int64_t noise_end, double* out, void* stream) {
+  if (!x || !out || n_rows < 1 || sig_begin < 0 || sig_end < sig_begin || noise_begin < 0 || noise_end < noise_begin)
+    return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == XCB_F32)
+    k_window_stats<float><<<(unsigned)n_rows, 256, 0, st>>>(static_cast<const float*>(x), stride, sig_begin, sig_end, noise_begin, noise_end, out);
+  else if (dtype == XCB_F64)
+    k_window_stats<double><<<(unsigned)n_rows, 256, 0, st>>>(static_cast<const double*>(x), stride, sig_begin, sig_end, noise_begin, noise_end, out);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}

@@ -27,10 +27,15 @@ fused: a detrend and/or taper directly in front of a filter become the filter's
 load prologue, consecutive causal filters become one cascade, and the
 ``[::factor]`` of ``decimate`` is the cascade's strided store.
 
+``resample`` (obspy's Fourier method: DFT of exactly ``npts`` points through
+Bluestein on the multi-pass FFT, Hann-windowed spectrum re-gridded, inverse DFT of
+``int(npts / factor)`` points) and ``interpolate`` with ``method='lanczos'`` are
+separate device steps (:mod:`xcorr_b200.stream.resample`).
+
 The remaining names of the reference's whitelist (``merge``, ``remove_response``,
-``rotate``, ``select``, ``interpolate``, ``resample``, ...) act on obspy objects
-or station metadata and stay with the reference's client
-(``stream/client.py:996``); they raise ``NotImplementedError`` here.
+``rotate``, ``select``, ...) act on obspy objects or station metadata and stay
+with the reference's client (``stream/client.py:996``); they raise
+``NotImplementedError`` here.
 """
 import ctypes
 import hashlib
@@ -48,8 +53,8 @@ __all__ = ['process', 'list_operations', 'is_operation', 'device_operations',
 # the reference's whitelist (stream/process.py:29-94); True = runs on the device
 _operations = {
     'attach_response': False, 'decimate': True, 'detrend': True, 'filter': True,
-    'interpolate': False, 'merge': False, 'normalize': False, 'remove_response': False,
-    'remove_sensitivity': False, 'resample': False, 'rotate': False, 'select': False,
+    'interpolate': True, 'merge': False, 'normalize': False, 'remove_response': False,
+    'remove_sensitivity': False, 'resample': True, 'rotate': False, 'select': False,
     'simulate': False, 'taper': True, 'trim': True, 'running_rms': False,
 }
 
@@ -237,7 +242,7 @@ class PreprocessProgram:
     def __init__(self, operations, npts, sampling_rate):
         self.npts_in = int(npts)
         self.fs_in = float(sampling_rate)
-        self.steps = []            # ('stage', _Stage) | ('trim', start, length)
+        self.steps = []            # ('stage', _Stage) | ('trim', start, length) | ('resample', ...) | ('interpolate', ...)
         n, fs = self.npts_in, self.fs_in
         cur = None
 
@@ -307,6 +312,57 @@ class PreprocessProgram:
                 n = (n + factor - 1) // factor
                 fs = fs / float(factor)
                 continue
+            elif op == 'resample':
+                # obspy Trace.resample(sampling_rate, window='hann', no_filter=True, strict_length=False)
+                new_fs = float(params.pop('sampling_rate'))
+                window = params.pop('window', 'hann')
+                no_filter = params.pop('no_filter', True)
+                params.pop('strict_length', None)
+                if params:
+                    raise TypeError(f"resample: unsupported arguments {sorted(params)}")
+                if window not in (None, 'hann'):
+                    raise NotImplementedError(f"resample window {window!r} (None or 'hann')")
+                factor = fs / new_fs
+                if not no_filter:
+                    if factor > 16:
+                        raise ArithmeticError('Automatic filter design is unstable for resampling factors above 16. '
+                                              'Manual resampling is necessary.')
+                    if cur is not None and (cur.decimate != 1 or cur.reverse):
+                        flush()
+                    cur = cur or _Stage()
+                    cur.sos.append(_cheby2_sos(fs, fs * 0.5 / float(factor)))
+                flush()
+                num = int(n / factor)
+                if num < 1:
+                    raise ValueError('resample: no samples left')
+                self.steps.append(('resample', n, fs, num, new_fs, window))
+                n, fs = num, new_fs
+            elif op == 'interpolate':
+                # obspy Trace.interpolate(sampling_rate, method, starttime=None, npts=None, time_shift=0.0, a=...)
+                new_fs = float(params.pop('sampling_rate'))
+                method = params.pop('method', 'weighted_average_slopes')
+                if method != 'lanczos':
+                    raise NotImplementedError(f"interpolate method {method!r} (only 'lanczos' runs on the device)")
+                a = int(params.pop('a'))
+                time_shift = float(params.pop('time_shift', 0.0))
+                start = float(params.pop('start_offset', 0.0))     # new start - old start, seconds (array input has no UTC)
+                npts_new = params.pop('npts', None)
+                if params:
+                    raise TypeError(f"interpolate: unsupported arguments {sorted(params)}")
+                flush()
+                old_dt, new_dt = 1.0 / fs, 1.0 / new_fs
+                # the shifted trace [time_shift, time_shift + (n-1) dt] is sampled from `start` (default: its own start)
+                start_rel = start
+                del time_shift                      # a pure relabelling of the time axis for array input
+                if start_rel < 0 or start_rel > (n - 1) * old_dt:
+                    raise ValueError("Can only interpolate between the start and end time of the trace.")
+                if npts_new is None:
+                    npts_new = int(np.floor(((n - 1) * old_dt - start_rel) / new_dt)) + 1
+                npts_new = int(npts_new)
+                if start_rel + (npts_new - 1) * new_dt > (n - 1) * old_dt + 1e-9 * old_dt:
+                    raise ValueError("The new array would extend past the end of the trace.")
+                self.steps.append(('interpolate', n, fs, npts_new, new_fs, a, start_rel))
+                n, fs = npts_new, new_fs
             elif op == 'trim':
                 flush()
                 start = int(params.get('start', 0))
@@ -323,6 +379,9 @@ class PreprocessProgram:
         for st in self.steps:
             if st[0] == 'trim':
                 n = st[2]
+                continue
+            if st[0] in ('resample', 'interpolate'):
+                n, fs = st[3], st[4]
                 continue
             s = st[1]
             s.npts, s.fs = n, fs
@@ -410,6 +469,14 @@ class PreprocessProgram:
         for st, b in zip(self.steps, bufs):
             if st[0] == 'trim':
                 cur = cur[:, st[1]:st[1] + st[2]]
+                continue
+            if st[0] == 'resample':
+                from .resample import resample_fourier
+                cur = resample_fourier(cur, st[1], st[2], st[3], st[4], st[5])
+                continue
+            if st[0] == 'interpolate':
+                from .resample import interpolate_lanczos
+                cur = interpolate_lanczos(cur, st[1], st[2], st[3], st[4], st[5], st[6])
                 continue
             s = st[1]
             i_stage += 1
