@@ -167,7 +167,7 @@ def timeshift(x, delay, sampling_rate, fast=True):
     plan = _plan(n, x2.dtype, x2.device, nsig)
     X = plan.rfft(x2[:, :n])
     d = np.broadcast_to(np.asarray(delay, dtype=np.float64), lead if lead else ()).reshape(-1)
-    dd = torch.from_numpy(np.ascontiguousarray(d)).to(x2.device)
+    dd = torch.from_numpy(np.array(d, dtype=np.float64)).to(x2.device)
     _lib.check(lib.xcb_phase_ramp(_CODE[x2.dtype], X.data_ptr(), X.stride(0), X.shape[1], nsig, dd.data_ptr(),
                                   float(df), _stream(x2)), 'xcb_phase_ramp')
     return plan.irfft(X).reshape(*lead, -1)
