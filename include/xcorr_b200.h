@@ -154,6 +154,10 @@ typedef struct xcb_sos {
   const double* carry_group; /* device, [2S][2S]: carry^256 (one carry group = 256 chunks) */
   const double* init_state;  /* device, [n_signals][2S] or NULL: sosfilt(..., zi=) state before the first processed
                               * sample (scipy layout zi[section][2]); used by sosfiltfilt (signal/filter.py:96) */
+  const double* zin_response; /* device, [chunk / decimate][2S] or NULL: zero-input response of the kept samples of a
+                              * chunk to unit start states.  Given (decimate >= 2, chunk % decimate == 0, forward), the
+                              * kept outputs are formed as zero-state output + response * start state instead of
+                              * rerunning the cascade over every input sample (exact by linearity). */
 } xcb_sos;
 
 /* stats[s] = {sum x, sum i*x, x[0], x[n-1]} (device double[n_signals][4]) */

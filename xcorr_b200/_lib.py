@@ -81,6 +81,7 @@ class xcb_sos(ctypes.Structure):
         ("carry", ctypes.POINTER(ctypes.c_double)),
         ("carry_group", ctypes.POINTER(ctypes.c_double)),
         ("init_state", ctypes.POINTER(ctypes.c_double)),
+        ("zin_response", ctypes.POINTER(ctypes.c_double)),
     ]
 
 

@@ -239,7 +239,6 @@ struct xcb_plan {
   Job* d_jobs = nullptr;
   // staged pair product: job groups per launch chunk (chunk c covers jobs [c*jobs_in_flight, ...))
   PairGroup* d_groups = nullptr;
-  unsigned long long* d_counter = nullptr;
   std::vector<int64_t> group_off;     // first group of chunk c; group_off[n_chunks] = total
   const PassLauncher* launch[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
   // measurement aid (xcb_profile_*): events around every pass launch
@@ -302,7 +301,6 @@ extern "C" int xcb_plan_destroy(xcb_plan* pl) {
   cudaFree(pl->d_inner2);
   cudaFree(pl->d_jobs);
   cudaFree(pl->d_groups);
-  cudaFree(pl->d_counter);
   delete pl;
   return XCB_OK;
 }
@@ -398,7 +396,7 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   const int C = pl->dtype == XCB_F32 ? tile_cols<float>() : tile_cols<double>();
   pl->tiles0 = pass0_tiles(pl->g, C);
   pl->partial_bytes = align_up((size_t)pl->g.n_blocks * pl->n_signals * pl->tiles0 * sizeof(double), 256);
-  pl->rnorm_bytes = align_up((size_t)pl->n_signals * sizeof(double), 256);
+  pl->rnorm_bytes = align_up((size_t)pl->n_signals * sizeof(double), 256) + 256;   // + the pair product's work counter
   const size_t per_job = (size_t)pl->g.M * (pl->dtype == XCB_F32 ? 8 : 16);
   size_t cap = d->max_work_bytes > 0 ? (size_t)d->max_work_bytes : ((size_t)16 << 30);
   int64_t fl = (int64_t)(cap / per_job);
@@ -420,7 +418,6 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
     }
     cudaError_t e = cudaMalloc(&pl->d_groups, all.size() * sizeof(PairGroup));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_groups, all.data(), all.size() * sizeof(PairGroup), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&pl->d_counter, sizeof(unsigned long long));
     if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "group table"); }
   }
   *out = pl;
@@ -454,6 +451,7 @@ template <class T> struct DeviceRunner {
   const xcb_plan* pl;
   cudaStream_t st;
   int64_t chunk = -1; // inverse passes: launch chunk (selects the job groups)
+  unsigned long long* counter = nullptr;   // work-item counter of the staged pair product (in the caller's workspace)
   int err = 0;        // cudaError_t of a failed launch, or -1 for an oversized grid
   bool operator()(const PassParams<T>& p0, bool row, int kind) {
     const int a = kind % pl->g.nd;
@@ -461,7 +459,7 @@ template <class T> struct DeviceRunner {
     if (row && p.load_mode == RL_PROLOGUE && pl->d_groups && chunk >= 0) {
       p.groups = pl->d_groups + pl->group_off[(size_t)chunk];
       p.n_groups = (int32_t)(pl->group_off[(size_t)chunk + 1] - pl->group_off[(size_t)chunk]);
-      p.work_counter = pl->d_counter;
+      p.work_counter = counter;
     }
     const int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
     if (nblocks >= 2147483647LL) { err = -1; return false; }
@@ -520,6 +518,8 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
     f.stack_spec_stride = pl->win_stride * g.M;
   }
   DeviceRunner<T> run{pl, st};
+  run.counter = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ws) + pl->partial_bytes +
+                                                      pl->rnorm_bytes - 256);
   for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
     int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
     run.chunk = j0 / pl->jobs_in_flight;

@@ -174,7 +174,8 @@ template <int S, class TI>
 __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
                                                   int chunk, int64_t n_chunks, const __grid_constant__ SosCoef<S> f,
                                                   PointwiseDev pw, const double* __restrict__ stats, int reverse,
-                                                  double* __restrict__ zstate) {
+                                                  double* __restrict__ zstate, double* __restrict__ yzs, int decim,
+                                                  int64_t n_out) {
   const int64_t per_sig = (n_chunks + kIlp - 1) / kIlp;
   const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (gid >= (int64_t)n_signals * per_sig) return;
@@ -210,7 +211,10 @@ __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int6
         const int64_t t = (cb + u) * chunk + j0 + b;
         if (j0 + b < chunk && t < n) {
           const int64_t i = reverse ? n - 1 - t : t;
-          cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
+          const double v = cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
+          // decimating cascades keep the zero-state output of the kept samples (chunk % decim == 0, so the
+          // kept local indices are the same in every chunk); phase 3 adds the zero-input response
+          if (yzs && (j0 + b) % decim == 0) yzs[(int64_t)sig * n_out + t / decim] = v;
         }
       }
 #pragma unroll
@@ -289,6 +293,47 @@ __global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int6
     for (int u = 0; u < kIlp; ++u)
 #pragma unroll
       for (int b = 0; b < kBatch; ++b) buf[u][b] = nxt[u][b];
+  }
+}
+
+// phase 3 of a DECIMATING cascade: by linearity the true output is the zero-state output phase 1
+// kept (yzs) plus the zero-input response of the chunk's start state, y[r] = yzs[r] + sum_k G[r][k] s0[k],
+// with G the response of the kept local samples to unit start states (host: scipy, like the carry
+// matrices).  d multiply-adds per kept sample instead of rerunning 5 S per input sample.  Thread q owns
+// chunk q; the block keeps G in shared memory and all lanes read the same row (broadcast).
+// A block takes kZinChunks consecutive chunks of one signal: their kept outputs are contiguous, so
+// the threads walk them coalesced; G (row pitch d + 1: conflict free) and the chunks' start states sit
+// in shared memory.
+constexpr int kZinChunks = 32;
+template <class TO>
+__global__ void __launch_bounds__(128) sos_phase3_zin(const double* __restrict__ yzs, TO* __restrict__ y, int64_t ys,
+                                                      int64_t n_out, int rows, int64_t n_chunks, int d,
+                                                      const double* __restrict__ G,
+                                                      const double* __restrict__ sstart) {
+  extern __shared__ double zin_sm[];                     // G [rows][d + 1], then s0 [kZinChunks][d]
+  double* g_sm = zin_sm;
+  double* s_sm = zin_sm + rows * (d + 1);
+  const int64_t blocks_per_sig = (n_chunks + kZinChunks - 1) / kZinChunks;
+  const int sig = (int)(blockIdx.x / blocks_per_sig);
+  const int64_t c0 = (blockIdx.x - (int64_t)sig * blocks_per_sig) * kZinChunks;
+  const int nc = (int)(n_chunks - c0 < kZinChunks ? n_chunks - c0 : kZinChunks);
+  for (int i = threadIdx.x; i < rows * d; i += 128) g_sm[(i / d) * (d + 1) + i % d] = G[i];
+  const double* in = sstart + ((int64_t)sig * n_chunks + c0) * d;
+  for (int i = threadIdx.x; i < nc * d; i += 128) s_sm[i] = in[i];
+  __syncthreads();
+  const double* src = yzs + (int64_t)sig * n_out;
+  TO* dst = y + (int64_t)sig * ys;
+  const int64_t o0 = c0 * rows;
+  const int count = nc * rows;
+  for (int o = threadIdx.x; o < count && o0 + o < n_out; o += 128) {
+    const int c = o / rows, r = o - c * rows;
+    const double* g = g_sm + r * (d + 1);
+    const double* s0 = s_sm + c * d;
+    double a0 = src[o0 + o], a1 = 0.0;
+    int k = 0;
+    for (; k + 1 < d; k += 2) { a0 = fma(g[k], s0[k], a0); a1 = fma(g[k + 1], s0[k + 1], a1); }
+    if (k < d) a0 = fma(g[k], s0[k], a0);
+    dst[o0 + o] = (TO)(a0 + a1);
   }
 }
 
@@ -385,6 +430,7 @@ struct SosArgs {
   const void* x; int64_t xs; void* y; int64_t ys; int64_t n; int n_signals;
   int chunk; int64_t n_chunks; PointwiseDev pw; const double* stats; int reverse, decim;
   double* zstate; double* sstart; const double (*coef)[5];
+  double* yzs; int64_t n_out; const double* zin;     // decimating fast path (see sos_phase3_zin)
 };
 
 template <int S, class TI> cudaError_t run_phase1(const SosArgs& a, cudaStream_t st) {
@@ -393,7 +439,7 @@ template <int S, class TI> cudaError_t run_phase1(const SosArgs& a, cudaStream_t
   const int64_t total = (int64_t)a.n_signals * ((a.n_chunks + kIlp - 1) / kIlp);
   sos_phase1<S, TI><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(static_cast<const TI*>(a.x), a.n, a.xs,
                                                                     a.n_signals, a.chunk, a.n_chunks, f, a.pw,
-                                                                    a.stats, a.reverse, a.zstate);
+                                                                    a.stats, a.reverse, a.zstate, a.yzs, a.decim, a.n_out);
   return cudaGetLastError();
 }
 
@@ -433,7 +479,7 @@ cudaError_t run_phase_s(int S, int phase, int dti, int dto, const SosArgs& a, cu
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
-struct SosLayout { int64_t n_chunks, n_groups; int d; size_t off_P, off_PG, off_z, off_s, off_g, total; };
+struct SosLayout { int64_t n_chunks, n_groups, n_out; int d; size_t off_P, off_PG, off_z, off_s, off_g, off_y, total; };
 
 SosLayout sos_layout(int64_t n, int n_signals, const xcb_sos* f) {
   SosLayout L;
@@ -446,6 +492,9 @@ SosLayout sos_layout(int64_t n, int n_signals, const xcb_sos* f) {
   L.off_z = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_chunks * L.d);
   L.off_s = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_chunks * L.d);
   L.off_g = o;  o += align256(sizeof(double) * (size_t)n_signals * L.n_groups * L.d);
+  L.n_out = (n + f->decimate - 1) / f->decimate;
+  L.off_y = o;
+  if (f->zin_response) o += align256(sizeof(double) * (size_t)n_signals * L.n_out);
   L.total = o;
   return L;
 }
@@ -549,12 +598,32 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   a.x = x; a.xs = x_stride; a.y = y; a.ys = y_stride; a.n = n; a.n_signals = n_signals;
   a.chunk = f->chunk; a.n_chunks = L.n_chunks; a.pw = to_dev(pre); a.stats = stats;
   a.reverse = f->reverse; a.decim = f->decimate; a.zstate = dz; a.sstart = ds; a.coef = f->coef;
+  if (f->zin_response && (f->decimate < 2 || f->chunk % f->decimate != 0 || f->reverse)) return XCB_ERR_ARG;
+  // the fast path keeps the response table in (default-sized) shared memory; else rerun the cascade
+  const bool zin = f->zin_response != nullptr &&
+                   sizeof(double) * ((size_t)(f->chunk / f->decimate) * (L.d + 1) + (size_t)kZinChunks * L.d) <= 48 * 1024;
+  a.yzs = zin ? reinterpret_cast<double*>(ws + L.off_y) : nullptr;
+  a.n_out = L.n_out;
+  a.zin = f->zin_response;
   if (run_phase_s(f->n_sections, 1, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
   const unsigned ng = (unsigned)((int64_t)n_signals * L.n_groups);
   sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 0, dg, ds);
   sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg, f->init_state);
   sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 2, dg, ds);
   if (cudaGetLastError() != cudaSuccess) return XCB_ERR_CUDA;
+  if (zin) {
+    const int rows = f->chunk / f->decimate;
+    const int64_t blocks_per_sig = (L.n_chunks + kZinChunks - 1) / kZinChunks;
+    const size_t smem = sizeof(double) * ((size_t)rows * (L.d + 1) + (size_t)kZinChunks * L.d);
+    const unsigned grid = (unsigned)((int64_t)n_signals * blocks_per_sig);
+    if (dtype_out == XCB_F32)
+      sos_phase3_zin<float><<<grid, 128, smem, st>>>(a.yzs, static_cast<float*>(y), y_stride, L.n_out, rows, L.n_chunks,
+                                                     L.d, a.zin, ds);
+    else
+      sos_phase3_zin<double><<<grid, 128, smem, st>>>(a.yzs, static_cast<double*>(y), y_stride, L.n_out, rows,
+                                                      L.n_chunks, L.d, a.zin, ds);
+    return cudaGetLastError() == cudaSuccess ? XCB_OK : XCB_ERR_CUDA;
+  }
   if (run_phase_s(f->n_sections, 3, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
   return XCB_OK;
 }

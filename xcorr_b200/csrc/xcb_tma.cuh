@@ -67,20 +67,26 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+#ifndef XCB_COL_MINB
+#define XCB_COL_MINB 3      // resident CTAs per SM the column pass is compiled for, where shared memory allows
+#endif
 template <class T, int R1, int R2> struct ColTma {
   using G = Cfg<T, R1, R2>;
   static constexpr int N = G::N, C = G::C, TJ = G::TJ, THREADS = G::THREADS;
   static constexpr int SLOT_BYTES = N * C * 2 * (int)sizeof(T);
   static constexpr int BOX_ROWS = N <= 256 ? N : N / 2;
   static constexpr int NBOX = N / BOX_ROWS;
-  static constexpr int NSLOT = (3 * SLOT_BYTES + 64 + THREADS * 8) * 2 <= 220 * 1024 ? 3 : 2;
+  static constexpr int SMEM_SM = 227 * 1024;                                  // per SM, 1 KB reserved per CTA
+  static constexpr int fits(int slots, int ctas) { return (slots * SLOT_BYTES + 64 + THREADS * 8 + 1024) * ctas <= SMEM_SM; }
+  static constexpr int MINB = (XCB_COL_MINB >= 3 && fits(2, 3)) ? 3 : 2;      // a 2-slot ring is the minimum
+  static constexpr int NSLOT = fits(3, MINB) ? 3 : 2;
   static constexpr int RED_OFF = NSLOT * SLOT_BYTES + 64;
   static constexpr int SMEM = RED_OFF + THREADS * 8;
   static_assert(N % BOX_ROWS == 0 && BOX_ROWS <= 256, "TMA box");
 };
 
 template <class T, int R1, int R2>
-__global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, 2)
+__global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, ColTma<T, R1, R2>::MINB)
 xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                  const int64_t split_col, const __grid_constant__ PassParams<T> p) {
   using K = ColTma<T, R1, R2>;

@@ -219,6 +219,22 @@ def _carry_matrices(sos, chunk):
     return np.ascontiguousarray(P), np.ascontiguousarray(np.linalg.matrix_power(P, _GROUP))
 
 
+def _zero_input_response(sos, chunk, decimate):
+    """Outputs at the kept samples (local index % decimate == 0) of a chunk fed with zeros,
+    per unit start state: shape (chunk // decimate, 2S)."""
+    from scipy import signal
+    S = sos.shape[0]
+    rows = chunk // decimate
+    G = np.zeros((rows, 2 * S))
+    zero = np.zeros(chunk)
+    for i in range(2 * S):
+        zi = np.zeros((S, 2))
+        zi[i // 2, i % 2] = 1.0
+        y, _ = signal.sosfilt(sos, zero, zi=zi)
+        G[:, i] = y[::decimate][:rows]
+    return np.ascontiguousarray(G)
+
+
 # -- program ------------------------------------------------------------------
 class _Stage:
     """One device launch group: optional pointwise prologue, optional cascade."""
@@ -406,12 +422,15 @@ class PreprocessProgram:
                 f.n_sections = len(sos)
                 f.decimate = s.decimate
                 f.reverse = int(s.reverse)
-                f.chunk = _SCAN_CHUNK
+                # decimating cascades: chunks of whole decimation periods enable the zero-input fast path
+                zin = s.decimate >= 2 and not s.reverse
+                f.chunk = (_SCAN_CHUNK // s.decimate) * s.decimate if zin else _SCAN_CHUNK
                 for k, sec in enumerate(sos):
                     a0 = sec[3]
                     for m, v in enumerate((sec[0] / a0, sec[1] / a0, sec[2] / a0, sec[4] / a0, sec[5] / a0)):
                         f.coef[k][m] = float(v)
-                s.P, s.PG = _carry_matrices(sos, _SCAN_CHUNK)
+                s.P, s.PG = _carry_matrices(sos, f.chunk)
+                s.G = _zero_input_response(sos, f.chunk, s.decimate) if zin else None
                 s.f = f
         self._designed = True
         self._dev_cache = {}
@@ -437,12 +456,15 @@ class PreprocessProgram:
                 b['stats_ws'] = torch.empty(nb.value, dtype=torch.uint8, device=dev)
                 b['stats'] = torch.empty((nsig, 4), dtype=torch.float64, device=dev)
             if s.f is not None:
+                b['P'] = torch.from_numpy(s.P).to(dev)
+                b['PG'] = torch.from_numpy(s.PG).to(dev)
+                if s.G is not None:      # (set before the size query: the fast path needs scratch for its zero-state outputs)
+                    b['G'] = torch.from_numpy(s.G).to(dev)
+                    s.f.zin_response = ctypes.cast(b['G'].data_ptr(), ctypes.POINTER(ctypes.c_double))
                 nb = ctypes.c_size_t()
                 _lib.check(lib.xcb_sosfilt_workspace_bytes(s.npts, nsig, ctypes.byref(s.f), ctypes.byref(nb)),
                            'xcb_sosfilt_workspace_bytes')
                 b['sos_ws'] = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-                b['P'] = torch.from_numpy(s.P).to(dev)
-                b['PG'] = torch.from_numpy(s.PG).to(dev)
             bufs.append(b)
         self._dev_cache[key] = bufs
         return bufs
@@ -499,6 +521,8 @@ class PreprocessProgram:
                 y = torch.empty((nsig, n_out), dtype=dt_out, device=dev)
                 s.f.carry = ctypes.cast(b['P'].data_ptr(), ctypes.POINTER(ctypes.c_double))
                 s.f.carry_group = ctypes.cast(b['PG'].data_ptr(), ctypes.POINTER(ctypes.c_double))
+                if s.G is not None:
+                    s.f.zin_response = ctypes.cast(b['G'].data_ptr(), ctypes.POINTER(ctypes.c_double))
                 _lib.check(lib.xcb_sosfilt(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), xcb[y.dtype], y.data_ptr(),
                                            y.stride(0), n, nsig, ctypes.byref(s.f),
                                            ctypes.byref(pw) if s.has_pointwise else None, stats_ptr,
