@@ -96,6 +96,20 @@ def cpu_reference(n_day, steps, warmup, cores=None, fraction=CPU_SAMPLE_FRACTION
                        "oracle port of xcorr/util/cc.py (numpy pocketfft, float32 in)")
 
 
+def measured_traffic(args, plan, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed
+    `ncu --set full` capture (profiles/ncu_r01_summary.md); only for the configuration that capture ran."""
+    captured = {("cfg3", "f32", (256, 150, 256), 2): {
+        "inv_pass2_N256": 3.618e9 + 9.386e9,      # xcb_pair_product_grouped: every spectrum once + one spectrum per pair
+        "inv_pass1_N150": 9.437e9 + 9.379e9,
+        "inv_pass0_N256": 9.437e9 + 3.862e9,
+        "fwd_pass1_N150": 3.775e9 + 3.717e9,
+        "fwd_pass2_N256": 3.776e9 + 3.717e9,
+    }}
+    key = (args.workload, args.dtype, tuple(plan.dims), plan.n_blocks)
+    return captured.get(key, {}).get(kernel)
+
+
 # ---------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------
@@ -141,7 +155,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.005)
 
     def result(self):
         self.stop_flag.set()
@@ -339,7 +353,8 @@ def run_gpu(args):
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": dom["achieved_gbs"] / peak, "traffic": None,
+                         "unit": "GB/s", "frac": dom["achieved_gbs"] / peak,
+                         "traffic": measured_traffic(args, plan, dom["kernel"]),
                          "peak_source": peak_src, "avg_launch_ms": dom["avg_ms"],
                          "alg_bytes_per_launch": dom["alg_bytes_per_launch"],
                          "share_of_step": dom["total_ms"] / sum(t["total_ms"] for t in table)},
