@@ -130,10 +130,13 @@ def _plan(K, dtype, device, batch):
     real = torch.float32 if dtype in (torch.float32, torch.complex64) else torch.float64
     key = (int(K), real, str(device))
     p = _cache.get(key)
-    if p is None or p.max_batch < min(batch, 16):
+    # signals per launch: the scratch is max_batch * (K + M) complex numbers -- keep it under 2 GiB
+    per_signal = (int(K) + good_length(max(2 * int(K) - 1, 1))) * (8 if real == torch.float32 else 16)
+    want = max(1, min(batch, 16, (2 << 30) // per_signal))
+    if p is None or p.max_batch < want:
         if len(_cache) >= 4:                      # plans hold O(M) device memory
             _cache.pop(next(iter(_cache)))
-        p = DFT(K, real, max_batch=max(1, min(batch, 16)), device=device)
+        p = DFT(K, real, max_batch=want, device=device)
         _cache[key] = p
     return p
 
