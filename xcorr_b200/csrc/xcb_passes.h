@@ -50,6 +50,8 @@ struct PairGroup {
   int64_t spec_i[kGroupJobs], spec_j[kGroupJobs];   // distinct spectrum bases (complex-element offsets)
   int32_t job[kGroupJobs];                          // index of the job within the launch
   uint8_t ji[kGroupJobs], jj[kGroupJobs];           // staged row used by each job
+  int64_t rows[2 * kGroupJobs];                     // staged rows in order: spec_i[0..n_i) then spec_j[0..n_j)
+  int32_t n_rows, pad2;
 };
 
 template <class T> struct PassParams {

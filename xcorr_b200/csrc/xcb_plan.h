@@ -491,6 +491,9 @@ inline void build_pair_groups(const Job* jobs, int n_jobs, int max_jobs, int max
       const int k = std::min<int>((int)mine.size(), std::min(max_jobs, max_rows - 1));
       for (int c = 0; c < k; ++c) add(g, mine[(size_t)c]);
     }
+    for (int a = 0; a < g.n_i; ++a) g.rows[a] = g.spec_i[a];
+    for (int b = 0; b < g.n_j; ++b) g.rows[g.n_i + b] = g.spec_j[b];
+    g.n_rows = g.n_i + g.n_j;
     out.push_back(g);
   }
 }

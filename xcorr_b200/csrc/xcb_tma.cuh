@@ -52,6 +52,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// same, for waits that can be long (a consumer waiting for its producer): back off between polls so
+// the spinning warps do not take issue slots from the warps that have work
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -283,44 +289,69 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   if (warp == K::WARPS) {
     // ---- producer warp: takes items in order from a global counter (so that the
     // CTAs of the grid stay on neighbouring row pairs and the spectra rows they share
-    // come from L2), lane l fetches staged row l/2, side l%2 ----
+    // come from L2); lane l fetches staged row l/2, side l%2.  The bookkeeping is a
+    // chain of dependent global accesses (counter -> group record -> twiddle tables),
+    // so it is software pipelined: while the copies of item k are issued, the record
+    // of item k+1 is in flight and the counter of item k+2 is being claimed. ----
+    struct Raw {                                        // loads issued, values not yet used
+      int64_t item, ra, rb, spec;
+      int32_t n_i, n_rows;
+      cx<T> hi, lo;
+    };
+    const int r = lane >> 1, sd = lane & 1;
+    auto claim = [&]() -> unsigned long long { return lane == 0 ? atomicAdd(p.work_counter, 1ULL) : 0ULL; };
+    auto start = [&](unsigned long long tok) {
+      Raw w;
+      w.item = (int64_t)__shfl_sync(0xffffffffu, tok, 0);
+      w.ra = w.rb = w.spec = 0; w.n_i = w.n_rows = 0;
+      w.hi.x = w.lo.x = T(1); w.hi.y = w.lo.y = T(0);
+      if (w.item < n_items) {
+        const int64_t q = w.item / p.n_groups;
+        const PairGroup& g = p.groups[w.item - q * p.n_groups];
+        RP::pair_rows(p, q, w.ra, w.rb);
+        w.n_i = g.n_i;
+        w.n_rows = g.n_rows;
+        w.spec = g.rows[r < 2 * kGroupJobs ? r : 0];
+        if (lane < 2) {
+          const uint32_t kl = RP::klow_of_row(p, lane ? w.rb : w.ra);
+          w.hi = ld_ro(p.tw2_hi + (kl >> p.tw_shift));
+          w.lo = ld_ro(p.tw2_lo + (kl & p.tw_mask));
+        }
+      }
+      return w;
+    };
     uint32_t step = 0;
+    Raw cur = start(claim());
+    unsigned long long tok = claim();
     for (;;) {
-      unsigned long long it = 0;
-      if (lane == 0) it = atomicAdd(p.work_counter, 1ULL);
-      const int64_t item = (int64_t)__shfl_sync(0xffffffffu, it, 0);
-      if (item >= n_items) {
+      if (cur.item >= n_items) {
         const int buf = (int)(step % NBUF);
         mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
         if (lane == 0) { mail[buf].item = -1; mbar_arrive(&full[buf]); }
         break;
       }
-      const int64_t q = item / p.n_groups;
-      const PairGroup& g = p.groups[item - q * p.n_groups];
-      int64_t ra, rb;
-      RP::pair_rows(p, q, ra, rb);
-      const int sides = ra == rb ? 1 : 2, n_i = g.n_i, rows = n_i + g.n_j;
-      const int r = lane >> 1, sd = lane & 1;
-      const bool mine = r < rows && sd < sides;
-      int64_t src = 0;
-      if (mine) src = (r < n_i ? g.spec_i[r] : g.spec_j[r - n_i]) + (sd ? rb : ra) * N;
-      cx<T> wr; wr.x = T(1); wr.y = T(0);
-      if (lane < 2) wr = W::row_twiddle(p, lane ? rb : ra);
+      const Raw nxt = start(tok);                       // its loads are in flight during this item's copies
+      tok = claim();
+      const int sides = cur.ra == cur.rb ? 1 : 2;
+      const bool mine = r < cur.n_rows && sd < sides;
+      const int64_t src = cur.spec + (sd ? cur.rb : cur.ra) * N;
+      const cx<T> wr = cmul(cur.hi, cur.lo);
       for (int w = 0; w < n_terms; ++w, ++step) {
         const int buf = (int)(step % NBUF);
         mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
         if (w == 0 && lane < 2) {
           mail[buf].wrow[lane] = wr;
-          if (lane == 0) { mail[buf].item = item; mail[buf].ra = ra; mail[buf].rb = rb; }
+          if (lane == 0) { mail[buf].item = cur.item; mail[buf].ra = cur.ra; mail[buf].rb = cur.rb; }
         }
         __syncwarp();
-        if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(rows * sides * K::ROW_BYTES));
+        if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(cur.n_rows * sides * K::ROW_BYTES));
         if (mine) {
-          const int64_t toff = p.use_blk_off ? (r < n_i ? p.blk_off_i[w] : p.blk_off_j[w]) : w * p.stack_spec_stride;
+          const int64_t toff = p.use_blk_off ? (r < cur.n_i ? p.blk_off_i[w] : p.blk_off_j[w]) : w * p.stack_spec_stride;
           bulk_load(smem_raw + buf * K::STAGE_BYTES + (r * 2 + sd) * K::ROW_BYTES, p.spec + src + toff, K::ROW_BYTES,
                     &full[buf]);
         }
       }
+      cur = nxt;
     }
     return;
   }
@@ -333,7 +364,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   const bool per_term = p.normalize && p.stack_sig_stride != 0;
   for (;;) {
     int buf = (int)(step % NBUF);
-    mbar_wait(&full[buf], (step / NBUF) & 1u);
+    mbar_wait_backoff(&full[buf], (step / NBUF) & 1u);
     const int64_t item = mail[buf].item;
     if (item < 0) break;
     const int64_t ra = mail[buf].ra, rb = mail[buf].rb;
@@ -362,7 +393,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     for (int w = 0; w < n_terms; ++w, ++step) {
       if (w > 0) {
         buf = (int)(step % NBUF);
-        mbar_wait(&full[buf], (step / NBUF) & 1u);
+        mbar_wait_backoff(&full[buf], (step / NBUF) & 1u);
       }
       if (lane_on) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
