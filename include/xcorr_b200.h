@@ -225,6 +225,15 @@ XCB_API int xcb_lanczos(int32_t dtype, const void* x, int64_t x_stride, int64_t 
 XCB_API int xcb_window_stats(int32_t dtype, const void* x, int64_t stride, int32_t n_rows, int64_t sig_begin,
                              int64_t sig_end, int64_t noise_begin, int64_t noise_end, double* out, void* stream);
 
+/* signal/spectrogram.py:125-145: scipy.signal.spectrogram(x, nperseg=win_len, noverlap=win_len-1, nfft, mode='psd',
+ * one-sided) of every row -- one segment per sample, each mean-detrended (detrend != 0), windowed and
+ * zero-padded to nfft -- placed `rint(win_len / 2)` samples in, zeros at the edges like the reference's np.pad.
+ *   window device double[win_len]; scale = 1/(fs * sum w^2) ('density') or 1/(sum w)^2 ('spectrum');
+ *   y device dtype[n_signals][nfft/2 + 1][n] */
+XCB_API int xcb_spectrogram(int32_t dtype, const void* x, int64_t x_stride, int64_t n, int32_t n_signals,
+                            const double* window, int32_t win_len, int32_t nfft, double scale, int32_t detrend,
+                            void* y, void* stream);
+
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
  * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not

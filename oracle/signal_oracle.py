@@ -13,6 +13,7 @@ arrays ``[..., lag]``:
 * ``filter``                   -- ``signal/filter.py:86-96`` (``butter`` + ``sosfiltfilt``)
 * ``snr``                      -- ``signal/snr.py:107-121`` (``rms``: ``signal/rms.py``)
 * ``postprocess``              -- ``core/postprocess.py:133-141``
+* ``spectrogram``              -- ``signal/spectrogram.py:116-145``
 
 Pinned by construction: every function is a direct call of the same numpy /
 scipy routine the reference calls, with the same arguments.
@@ -81,3 +82,14 @@ def postprocess(cc, weights, delay, lag0, sampling_rate, frequency=3.0, btype="h
     y = filter(y, sampling_rate, frequency, btype, order)
     y = taper(y, sampling_rate, max_length=3 / 2)
     return y
+
+
+def spectrogram(x, sampling_rate, duration, padding_factor=2, scaling="density", **kwargs):
+    """signal/spectrogram.py:116-145: scipy.signal.spectrogram, one segment per sample, padded to the lag axis."""
+    win_len = int(duration * sampling_rate)
+    nfft = int(win_len * padding_factor)
+    edge = int(np.rint(win_len / 2))
+    _f, _t, Sxx = scipy.signal.spectrogram(x=x, fs=sampling_rate, nperseg=win_len, noverlap=win_len - 1, nfft=nfft,
+                                           scaling=scaling, mode="psd", axis=-1, return_onesided=True, **kwargs)
+    npad = [(0, 0)] * (len(Sxx.shape) - 1) + [(edge, x.shape[-1] - Sxx.shape[-1] - edge)]
+    return np.pad(Sxx, pad_width=npad, mode="constant", constant_values=0), np.linspace(0.0, sampling_rate / 2, int(nfft / 2 + 1))

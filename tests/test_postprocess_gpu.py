@@ -123,3 +123,19 @@ def test_postprocess_chain_and_dataset_driver(env, dtype):
     assert got.shape == ref.shape and got.dtype == np.dtype(dtype)
     assert _max_rel(got, ref.astype(np.float64)) <= (1e-10 if dtype == np.float64 else 2e-5)
     assert out.variables["cc"].attrs["unbiased"] == 1 and "postprocess" in out.variables["cc"].attrs
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kw", [dict(duration=2.5, padding_factor=4), dict(duration=1.0, padding_factor=2, scaling="spectrum"),
+                                dict(duration=0.64, padding_factor=1)])
+def test_spectrogram(env, kw, dtype):
+    """signal/spectrogram.py (timelapse input): scipy.signal.spectrogram with one segment per lag sample."""
+    torch, sg, so = env
+    x = ccfs((2, 3, 3001), 21).astype(dtype)
+    got, f = sg.spectrogram(torch.from_numpy(x).cuda(), 50.0, **kw)
+    ref, f_ref = so.spectrogram(x.astype(np.float64), 50.0, **kw)
+    got = got.cpu().numpy()
+    assert got.shape == ref.shape and np.array_equal(f, f_ref)
+    assert np.max(np.abs(got - ref)) <= (1e-11 if dtype == np.float64 else 2e-5) * np.max(ref)
+    edge = int(np.rint(int(kw["duration"] * 50.0) / 2))
+    assert np.all(got[..., :edge] == 0) and np.all(got[..., -1] == 0)

@@ -142,6 +142,63 @@ __global__ void __launch_bounds__(256) k_window_stats(const T* __restrict__ x, i
   }
 }
 
+// scipy.signal.spectrogram with noverlap = nperseg - 1 (signal/spectrogram.py:125-139): one segment per
+// sample, each detrended (mean), windowed, zero-padded to nfft and transformed; |X|^2 * scale, one-sided.
+// A warp owns one frequency bin k and 32 consecutive segments: x[t + n] is read conflict free across
+// the lanes, the window and the twiddle of (k, n) are warp-uniform broadcasts, and the stores of a bin
+// are contiguous.  The mean is removed through the window's own transform: sum w (x - m) e = sum w x e - m W[k].
+constexpr int kSpecSeg = 128;                  // segments per block
+template <class T>
+__global__ void __launch_bounds__(256) k_spectrogram(const T* __restrict__ x, int64_t x_stride, int64_t n,
+                                                     const double* __restrict__ win, int win_len, int nfft,
+                                                     double scale, int detrend, int64_t edge, T* __restrict__ y) {
+  extern __shared__ unsigned char spec_sm_raw[];
+  T* xs = reinterpret_cast<T*>(spec_sm_raw);                       // [kSpecSeg + win_len]
+  T* ws = xs + kSpecSeg + win_len;                                 // [win_len]
+  T* tc = ws + win_len;                                            // [nfft] cos
+  T* tsn = tc + nfft;                                              // [nfft] -sin
+  const int64_t n_seg = n - win_len + 1;
+  const int64_t s0 = (int64_t)blockIdx.x * kSpecSeg;
+  const int64_t sig = blockIdx.y;
+  const T* xr = x + sig * x_stride;
+  for (int i = threadIdx.x; i < kSpecSeg + win_len; i += 256) xs[i] = (s0 + i < n) ? xr[s0 + i] : T(0);
+  for (int i = threadIdx.x; i < win_len; i += 256) ws[i] = (T)win[i];
+  for (int i = threadIdx.x; i < nfft; i += 256) {
+    double sn, cs;
+    sincospi(2.0 * (double)i / (double)nfft, &sn, &cs);
+    tc[i] = (T)cs; tsn[i] = (T)(-sn);
+  }
+  __syncthreads();
+  const int n_bins = nfft / 2 + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T* yo = y + sig * (int64_t)n_bins * n;
+  for (int seg_blk = 0; seg_blk < kSpecSeg; seg_blk += 32) {
+    const int sl = seg_blk + lane;                                 // local segment of this lane
+    const bool live = s0 + sl < n_seg;
+    T mean = T(0);
+    if (detrend) {
+      T a = T(0);
+      for (int m = 0; m < win_len; ++m) a += xs[sl + m];
+      mean = a / (T)win_len;
+    }
+    for (int k = warp; k < n_bins; k += 8) {
+      T re = T(0), im = T(0), wre = T(0), wim = T(0);
+      int idx = 0;
+      for (int m = 0; m < win_len; ++m) {
+        const T w = ws[m], c = w * tc[idx], sn = w * tsn[idx];
+        const T v = xs[sl + m];
+        re = fma(v, c, re); im = fma(v, sn, im);
+        wre += c; wim += sn;
+        idx += k; if (idx >= nfft) idx -= nfft;
+      }
+      re -= mean * wre; im -= mean * wim;
+      T p = (T)((double)(re * re + im * im) * scale);
+      if (k != 0 && !(nfft % 2 == 0 && k == nfft / 2)) p *= T(2);
+      if (live) yo[(int64_t)k * n + edge + s0 + sl] = p;
+    }
+  }
+}
+
 int fail(cudaError_t e) { return e == cudaSuccess ? XCB_OK : XCB_ERR_CUDA; }
 
 }  // namespace
@@ -196,5 +253,34 @@ extern "C" int xcb_window_stats(int32_t dtype, const void* x, int64_t stride, in
   else if (dtype == XCB_F64)
     k_window_stats<double><<<(unsigned)n_rows, 256, 0, st>>>(static_cast<const double*>(x), stride, sig_begin, sig_end, noise_begin, noise_end, out);
   else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_spectrogram(int32_t dtype, const void* x, int64_t x_stride, int64_t n, int32_t n_signals,
+                               const double* window, int32_t win_len, int32_t nfft, double scale, int32_t detrend,
+                               void* y, void* stream) {
+  if (!x || !window || !y || n < 1 || n_signals < 1 || win_len < 1 || win_len > n || nfft < win_len) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t b = dtype == XCB_F32 ? 4 : 8;
+  if (dtype != XCB_F32 && dtype != XCB_F64) return XCB_ERR_ARG;
+  const int n_bins = nfft / 2 + 1;
+  const int64_t n_seg = n - win_len + 1, edge = (int64_t)llrint((double)win_len / 2.0);
+  // zero frame: the reference pads `edge` columns on the left and the rest on the right (np.pad)
+  if (cudaMemsetAsync(y, 0, (size_t)n_signals * n_bins * n * b, st) != cudaSuccess) return XCB_ERR_CUDA;
+  const size_t smem = b * ((size_t)kSpecSeg + 2 * (size_t)win_len + 2 * (size_t)nfft);
+  if (smem > 200 * 1024) return XCB_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((n_seg + kSpecSeg - 1) / kSpecSeg), (unsigned)n_signals);
+  cudaError_t e;
+  if (dtype == XCB_F32) {
+    e = cudaFuncSetAttribute(k_spectrogram<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return XCB_ERR_CUDA;
+    k_spectrogram<float><<<grid, 256, smem, st>>>(static_cast<const float*>(x), x_stride, n, window, win_len, nfft, scale,
+                                                  detrend, edge, static_cast<float*>(y));
+  } else {
+    e = cudaFuncSetAttribute(k_spectrogram<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return XCB_ERR_CUDA;
+    k_spectrogram<double><<<grid, 256, smem, st>>>(static_cast<const double*>(x), x_stride, n, window, win_len, nfft,
+                                                   scale, detrend, edge, static_cast<double*>(y));
+  }
   return fail(cudaGetLastError());
 }

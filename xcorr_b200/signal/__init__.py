@@ -7,3 +7,4 @@ from .correlate import correlate1d, correlate2d, Correlate2dPlan  # noqa: F401
 from .normalize import norm1d, norm2d  # noqa: F401
 from .fft import DFT, fft, ifft, rfft, irfft  # noqa: F401
 from .postprocess_ops import (unbias, unbias_weights, demean, taper, window, timeshift, filter, snr)  # noqa: F401
+from .spectrogram import spectrogram  # noqa: F401
