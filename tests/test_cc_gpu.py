@@ -267,3 +267,51 @@ def test_block_mode_equals_classic_transform(xb, orc, dtype):
         for q, (i, j) in list(enumerate(pairs))[::4]:
             ref = orc.cc(rec[i, 0], rec[j, 0], unbiased=False)
             assert np.max(np.abs(got[q, 0] - ref[i0:i0 + K])) <= TOL[np.dtype(dtype)] * np.max(np.abs(ref)), (i0, q)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_staged_pair_product_chunks_stacking_and_groups(xb, orc, dtype):
+    """The staged / grouped pair product (16 x R2 row axes) in the roles the benchmark does not cover:
+    several launch chunks (small scratch), stacked windows with per-window norms, repeated and
+    auto pairs, a single-pass plan, and classic (full-lag) plans."""
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    tol = TOL[np.dtype(dtype)]
+    n, R, W = 30_000, 6, 3
+    pairs = xb.all_pairs(R, auto=True) + [(3, 1), (3, 1)]
+    rec = np.stack([orc.synthetic_receivers(R, n, seed=700 + w, delay=23) for w in range(W)], axis=1)   # [R, W, n]
+    x = torch.from_numpy(rec.astype(dtype)).cuda()
+    refs = {(i, j, w): orc.cc(rec[i, w].astype(dtype).astype(np.float64), rec[j, w].astype(dtype).astype(np.float64),
+                              unbiased=False) for (i, j) in set(pairs) for w in range(W)}
+    per_job = 128 * 256 * (8 if dtype == np.float32 else 16)
+    for kw in (dict(dims=(128, 256), max_work_bytes=5 * per_job),         # 69 jobs in chunks of 5
+               dict(dims=(128, 240)), dict(dims=(160, 192))):
+        plan = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, n_blocks=1, **kw)
+        assert plan.n_blocks == 1
+        got = plan(x).cpu().numpy()
+        for q, (i, j) in enumerate(pairs):
+            for w in range(W):
+                ref = refs[(i, j, w)]
+                assert np.max(np.abs(got[q, w] - ref)) <= tol * np.max(np.abs(ref)), (kw, q, w)
+    # stacking: sum over windows of the per-window normalised CCFs, one inverse per pair
+    plan = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, stack=True, dims=(128, 256))
+    got = plan(x).cpu().numpy()
+    for q, (i, j) in enumerate(pairs):
+        ref = sum(refs[(i, j, w)] for w in range(W))
+        assert np.max(np.abs(got[q] - ref)) <= tol * np.max(np.abs(ref)), q
+    # cropped window around zero lag through blocks (segments start before the signal) with groups
+    i0 = n - 1 - 2_000
+    plan = xb.CorrelationPlan(n, R, pairs, n_windows=W, dtype=tdt, index_min=i0, index_max=i0 + 6_001,
+                              dims=(80, 160), n_blocks=2, block_len=15_008)
+    got = plan(x).cpu().numpy()
+    for q, (i, j) in enumerate(pairs):
+        for w in range(W):
+            ref = refs[(i, j, w)]
+            assert np.max(np.abs(got[q, w] - ref[i0:i0 + 6_001])) <= tol * np.max(np.abs(ref)), (q, w)
+    # single-pass plan (one row): n = 120 -> 256 points
+    small = orc.synthetic_receivers(5, 120, seed=9, delay=3)
+    plan = xb.CorrelationPlan(120, 5, xb.all_pairs(5), dtype=tdt, dims=(256,))
+    got = plan(torch.from_numpy(small.astype(dtype)).cuda().unsqueeze(1)).cpu().numpy()
+    for q, (i, j) in enumerate(xb.all_pairs(5)):
+        ref = orc.cc(small[i].astype(dtype).astype(np.float64), small[j].astype(dtype).astype(np.float64), unbiased=False)
+        assert np.max(np.abs(got[q, 0] - ref)) <= tol * np.max(np.abs(ref))
