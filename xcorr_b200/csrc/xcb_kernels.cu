@@ -179,7 +179,8 @@ template <class T, int R1, int R2> int launch_row(const void* params, int64_t nb
     // worth it when the jobs share spectra (>= 3 jobs per group on average); a lone pair keeps
     // the plain warp kernel, which spreads its row pairs over all warps of a CTA
     if (K::kOk && staged && p.load_mode == RL_PROLOGUE && p.n_groups > 0 && p.work_counter &&
-        p.n_batch >= 3 * p.n_groups && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0) {
+        p.n_batch >= 3 * p.n_groups && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0 &&
+        p.n_pairs_rows * (int64_t)p.n_groups < 2147483647LL) {
       static int resident = 0;   // persistent grid
       if (!resident) resident = resident_ctas((const void*)xcb_pair_product_grouped<T, R1, R2>, K::THREADS, K::SMEM);
       const int64_t items = p.n_pairs_rows * (int64_t)p.n_groups;
