@@ -407,7 +407,7 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
 
   // job groups of the staged pair product (row axes 16 x R2 only; see launch_row)
   if (pl->n_jobs > 0 && menu_find(dims[nd - 1])->R1 == 16) {
-    const int warps = C / 2, max_rows = pl->dtype == XCB_F32 ? 6 : 4;     // PairGrouped::MAX_ROWS
+    const int warps = C / 2, max_rows = pl->dtype == XCB_F32 ? stage_rows<float>() : stage_rows<double>();
     std::vector<PairGroup> all, chunk;
     pl->group_off.push_back(0);
     for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += fl) {

@@ -45,6 +45,8 @@ struct Job {
 // the distinct first-role / second-role spectra are staged once per row pair in
 // shared memory and every job of the group (one warp each) reads them there.
 constexpr int kGroupJobs = 8;
+// distinct spectra a group may stage (shared-memory ring of the staged kernel: rows x 2 sides x N elements)
+template <class T> constexpr int stage_rows() { return sizeof(T) == 4 ? 6 : 4; }
 struct PairGroup {
   int32_t n_jobs, n_i, n_j, pad;
   int64_t spec_i[kGroupJobs], spec_j[kGroupJobs];   // distinct spectrum bases (complex-element offsets)

@@ -245,7 +245,7 @@ template <class T, int R1, int R2> struct PairGrouped {
   using W = RowWarp<T, R1, R2>;
   static constexpr int N = W::N, C = W::C, WARPS = W::THREADS / 32;      // consumer warps = jobs per group
   static constexpr int THREADS = W::THREADS + 32;                        // + one producer warp
-  static constexpr int MAX_ROWS = sizeof(T) == 4 ? 6 : 4;                // distinct spectra per group
+  static constexpr int MAX_ROWS = stage_rows<T>();                       // distinct spectra per group
   static constexpr int NBUF = sizeof(T) == 4 ? 3 : 2;                    // staging ring
   static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
   static constexpr int STAGE_BYTES = MAX_ROWS * 2 * ROW_BYTES;           // [row][side]
