@@ -49,32 +49,35 @@ xcb_col_pass(const __grid_constant__ PassParams<T> p) {
   P::phase_b(p, ctx, smem);
 }
 
-template <class T, int R1, int R2>
+// PRO: the pair product (first inverse pass); else the forward last pass / plain complex passes.  Compiled
+// separately so that neither role carries the other's registers.
+template <class T, int R1, int R2, bool PRO>
 __global__ void __launch_bounds__(Cfg<T, R1, R2>::THREADS)
 xcb_row_pass(const __grid_constant__ PassParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem[];
   if constexpr (R1 == 16) {
     // one warp per mirrored row pair, warp-synchronous (RowWarp in xcb_passes.h)
     using P = RowWarp<T, R1, R2>;
+    constexpr int MODE = PRO ? 2 : 1;
     typename P::Ctx ctx;
     ctx.tid = threadIdx.x;
     ctx.bid = blockIdx.x;
     const typename P::Slot slot = P::decode(p, ctx, smem);
-    P::phase_a(p, ctx, slot, smem);
+    P::template phase_a<MODE>(p, ctx, slot, smem);
     __syncwarp();
-    P::phase_b(p, ctx, slot);
+    P::template phase_b<MODE>(p, ctx, slot);
     __syncwarp();
-    P::phase_c(p, ctx, slot);
+    P::template phase_c<MODE>(p, ctx, slot);
     __syncwarp();
-    if (p.sumsq_partial && p.load_mode == RL_REAL) __syncthreads();   // single-pass plans: norms of the tile
-    P::phase_d(p, ctx, slot, smem);
+    if (!PRO && p.sumsq_partial && p.load_mode == RL_REAL) __syncthreads();   // single-pass plans: norms of the tile
+    P::template phase_d<MODE>(p, ctx, slot, smem);
   } else {
     using P = RowPass<T, R1, R2>;
     typename P::Ctx ctx;
     ctx.tid = threadIdx.x;
     ctx.bid = blockIdx.x;
     P::phase_info(p, ctx, smem);
-    if (p.load_mode != RL_PROLOGUE) __syncthreads();   // the pair product derives its rows itself
+    if (!PRO) __syncthreads();   // the pair product derives its rows itself
     P::phase_load(p, ctx, smem);
     __syncthreads();
     P::phase_s1_read(p, ctx, smem);
@@ -158,10 +161,21 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
         map_tail = map;
     }
     if (rc == 0) {
-      static int resident = 0;   // persistent grid: as many CTAs as stay resident
-      if (!resident) resident = resident_ctas((const void*)xcb_col_pass_tma<T, R1, R2>, K::THREADS, K::SMEM);
-      int64_t grid = nblocks < resident ? nblocks : resident;
-      xcb_col_pass_tma<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
+      // the first forward pass (real input, norms) and the last inverse pass (lag epilogue) have their own
+      // kernels; the middle passes share the run-time-moded one (measured: specialising them is slower)
+      const int role = p.load_mode == CL_REAL ? COL_FWD_REAL : p.store_mode == CS_EPI ? COL_INV_EPI : COL_ANY;
+      static int resident[5] = {0, 0, 0, 0, 0};   // persistent grid: as many CTAs as stay resident
+      const void* fn = role == COL_FWD_REAL ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL>
+                       : role == COL_INV_EPI ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_INV_EPI>
+                                             : (const void*)xcb_col_pass_tma<T, R1, R2, COL_ANY>;
+      if (!resident[role]) resident[role] = resident_ctas(fn, K::THREADS, K::SMEM);
+      const int64_t grid = nblocks < resident[role] ? nblocks : resident[role];
+      if (role == COL_FWD_REAL)
+        xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
+      else if (role == COL_INV_EPI)
+        xcb_col_pass_tma<T, R1, R2, COL_INV_EPI><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
+      else
+        xcb_col_pass_tma<T, R1, R2, COL_ANY><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       return (int)cudaGetLastError();
     }
   }
@@ -191,7 +205,8 @@ template <class T, int R1, int R2> int launch_row(const void* params, int64_t nb
       return (int)cudaGetLastError();
     }
   }
-  xcb_row_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
+  if (p.load_mode == RL_PROLOGUE) xcb_row_pass<T, R1, R2, true><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
+  else xcb_row_pass<T, R1, R2, false><<<(unsigned)nblocks, G::THREADS, G::ROW_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -199,10 +214,16 @@ template <class T, int R1, int R2> int prepare() {
   using G = Cfg<T, R1, R2>;
   cudaError_t e = cudaFuncSetAttribute(xcb_col_pass<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::COL_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(xcb_row_pass<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROW_SMEM);
+  e = cudaFuncSetAttribute(xcb_row_pass<T, R1, R2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROW_SMEM);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           ColTma<T, R1, R2>::SMEM);
+  e = cudaFuncSetAttribute(xcb_row_pass<T, R1, R2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::ROW_SMEM);
+  if (e != cudaSuccess) return (int)e;
+  constexpr int kTmaSmem = ColTma<T, R1, R2>::SMEM;
+  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_INV_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
   if (e != cudaSuccess) return (int)e;
   if constexpr (R1 == 16)
     e = cudaFuncSetAttribute(xcb_pair_product_grouped<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -759,6 +759,12 @@ template <class T, int R1, int R2> struct RowWarp {
   static constexpr int SMEM = C * COLBUF * 2 * (int)sizeof(T) + THREADS * 8;
   static_assert(SMEM <= G::ROW_SMEM, "fits the row-pass allocation");
 
+  // MODE 0: the role is read from p.load_mode (emulator); 1: forward pass only; 2: pair product only --
+  // the kernels are compiled per role so that neither carries the other's registers and code
+  template <int MODE> static XCB_HD bool is_pro(const PassParams<T>& p) {
+    return MODE == 0 ? p.load_mode == RL_PROLOGUE : MODE == 2;
+  }
+
   struct Slot {
     int64_t batch, row;
     cx<T>* buf;        // this half's row buffer
@@ -811,7 +817,8 @@ template <class T, int R1, int R2> struct RowWarp {
   // v[r] += sw * a[r R2] * conj(b[r R2]), r < R1: this lane's share of one term
   // (block / stacked window) of the cross-spectrum; a, b point at the lane's first
   // element of the two rows (global memory, or rows staged in shared memory)
-  static XCB_HD void accumulate(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw) {
+  template <bool SCALED>
+  static XCB_HD void accumulate_t(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw) {
     constexpr int H = R1 / 2;                       // two batches of loads bound the registers
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -820,11 +827,16 @@ template <class T, int R1, int R2> struct RowWarp {
       for (int r = 0; r < H; ++r) { a[r] = a_row[(h * H + r) * R2]; b[r] = b_row[(h * H + r) * R2]; }
 #pragma unroll
       for (int r = 0; r < H; ++r) {
-        const T ax = a[r].x * sw, ay = a[r].y * sw;
+        const T ax = SCALED ? a[r].x * sw : a[r].x, ay = SCALED ? a[r].y * sw : a[r].y;
         v[h * H + r].x += ax * b[r].x + ay * b[r].y;
         v[h * H + r].y += ay * b[r].x - ax * b[r].y;
       }
     }
+  }
+  // `scaled`: per-term norms (stacked windows); else the single scale is applied after the sum
+  static XCB_HD void accumulate(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw, bool scaled = true) {
+    if (scaled) accumulate_t<true>(v, a_row, b_row, sw);
+    else accumulate_t<false>(v, a_row, b_row, sw);
   }
 
   // slot 0 of a spectrum holds (X[0], X[M]), both real: C[0] and C[M] are plain products
@@ -842,11 +854,12 @@ template <class T, int R1, int R2> struct RowWarp {
     return r;
   }
 
+  template <int MODE = 0>
   static XCB_HD void phase_a(const PassParams<T>& p, Ctx& ctx, const Slot& s, unsigned char* smem_raw) {
     cx<T>* v = ctx.v;
     ctx.ss = 0.0;
     if (s.active && s.j < R2) {
-      if (p.load_mode == RL_PROLOGUE) {
+      if (is_pro<MODE>(p)) {
         const Job jb = p.jobs[s.batch];
         const bool per_term = p.normalize && p.stack_sig_stride != 0;
         const cx<T>* z = p.spec + s.row * N + s.j;
@@ -856,7 +869,7 @@ template <class T, int R1, int R2> struct RowWarp {
           int64_t oi, oj;
           T sw;
           term(p, jb, w, per_term, oi, oj, sw);
-          accumulate(v, z + oi, z + oj, sw);
+          accumulate(v, z + oi, z + oj, sw, per_term);
         }
         if (s.row0 && s.j == 0) v[0] = packed_dc(p, jb, per_term);
 #pragma unroll
@@ -876,7 +889,7 @@ template <class T, int R1, int R2> struct RowWarp {
         for (int r = 0; r < R1; ++r) s.buf[s.j * P1 + r] = v[r];       // stage layout
       }
     }
-    if (p.sumsq_partial && p.load_mode == RL_REAL) red_ptr(smem_raw)[ctx.tid] = ctx.ss;
+    if (MODE != 2 && p.sumsq_partial && p.load_mode == RL_REAL) red_ptr(smem_raw)[ctx.tid] = ctx.ss;
   }
 
   // stage 2: read the stage layout, inner twiddles, radix-R2 -> v[r] = element j + R1 r
@@ -887,10 +900,11 @@ template <class T, int R1, int R2> struct RowWarp {
     fft_reg<R2>(v);
   }
 
+  template <int MODE = 0>
   static XCB_HD void phase_b(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
     cx<T>* v = ctx.v;
     if (!s.active) return;
-    if (p.load_mode == RL_PROLOGUE) {
+    if (is_pro<MODE>(p)) {
       if (s.j >= R2) return;
       const Job jb = p.jobs[s.batch];
       const bool per_term = p.normalize && p.stack_sig_stride != 0;
@@ -920,10 +934,11 @@ template <class T, int R1, int R2> struct RowWarp {
     }
   }
 
+  template <int MODE = 0>
   static XCB_HD void phase_c(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
     const cx<T>* v = ctx.v;
     if (!s.active) return;
-    if (p.load_mode == RL_PROLOGUE) {
+    if (is_pro<MODE>(p)) {
       if (s.j >= R2) return;
 #pragma unroll
       for (int r = 0; r < R1; ++r) s.buf[s.j * P1 + r] = v[r];         // stage layout
@@ -933,10 +948,11 @@ template <class T, int R1, int R2> struct RowWarp {
     }
   }
 
+  template <int MODE = 0>
   static XCB_HD void phase_d(const PassParams<T>& p, Ctx& ctx, const Slot& s, unsigned char* smem_raw) {
     cx<T>* v = ctx.v;
     if (s.active) {
-      if (p.load_mode == RL_PROLOGUE) {
+      if (is_pro<MODE>(p)) {
         stage2(p, s, v);
         if (p.store_mode == RS_EPI) {
           T* outp = p.ccf + p.jobs[s.batch].out_off;
@@ -979,7 +995,7 @@ template <class T, int R1, int R2> struct RowWarp {
         }
       }
     }
-    if (p.sumsq_partial && p.load_mode == RL_REAL)
+    if (MODE != 2 && p.sumsq_partial && p.load_mode == RL_REAL)
       block_sumsq<THREADS>(p.sumsq_partial + ctx.bid, red_ptr(smem_raw), ctx.tid);
   }
 };

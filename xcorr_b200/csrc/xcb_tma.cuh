@@ -91,10 +91,18 @@ template <class T, int R1, int R2> struct ColTma {
   static_assert(N % BOX_ROWS == 0 && BOX_ROWS <= 256, "TMA box");
 };
 
-template <class T, int R1, int R2>
+// ROLE: 1 forward first pass (real input, norms), 2 forward middle, 3 inverse middle, 4 inverse last (lag
+// epilogue).  One kernel per role: the middle passes do not carry the epilogue's code and registers.
+enum ColRole : int { COL_ANY = 0, COL_FWD_REAL = 1, COL_FWD = 2, COL_INV = 3, COL_INV_EPI = 4 };
+
+template <class T, int R1, int R2, int ROLE>
 __global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, ColTma<T, R1, R2>::MINB)
 xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                  const int64_t split_col, const __grid_constant__ PassParams<T> p) {
+  // (ROLE 0 = COL_ANY reads the modes at run time)
+  const int kLoad = ROLE == COL_ANY ? p.load_mode : ROLE == COL_FWD_REAL ? CL_REAL : (ROLE == COL_FWD ? CL_CPLX : CL_CPLX_INV);
+  const int kStore = ROLE == COL_ANY ? p.store_mode : ROLE <= COL_FWD ? CS_TW : (ROLE == COL_INV ? CS_CONJ : CS_EPI);
+  const bool kSumsq = ROLE == COL_ANY || ROLE == COL_FWD_REAL;
   using K = ColTma<T, R1, R2>;
   constexpr int N = K::N, C = K::C;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -157,7 +165,7 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
 #pragma unroll
       for (int r = 0; r < R1; ++r) v[r] = sm[(j + r * R2) * C + c];
     }
-    if (p.sumsq_partial) {          // real-input first pass: sum of squares of this tile (rows past n are zero)
+    if (kSumsq && p.sumsq_partial) {          // real-input first pass: sum of squares of this tile (rows past n are zero)
       T ssq = T(0);
       if (j < R2) {
 #pragma unroll
@@ -166,9 +174,9 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       red[tid] = (double)ssq;
     }
     __syncthreads();
-    if (p.sumsq_partial) block_sumsq<K::THREADS>(p.sumsq_partial + tile, red, tid);
+    if (kSumsq && p.sumsq_partial) block_sumsq<K::THREADS>(p.sumsq_partial + tile, red, tid);
     if (j < R2) {
-      if (p.load_mode == CL_CPLX_INV) twiddle_chain<R1, true>(p, colscale * (uint32_t)j, colscale * (uint32_t)R2, v);
+      if (kLoad == CL_CPLX_INV) twiddle_chain<R1, true>(p, colscale * (uint32_t)j, colscale * (uint32_t)R2, v);
       fft_reg<R1>(v);
 #pragma unroll
       for (int r = 0; r < R1; ++r) sm[(j * R1 + r) * C + c] = v[r];
@@ -187,12 +195,12 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     if (j < R1 && col_ok) {
       twiddle_powers<R2>(w_inner, v);
       fft_reg<R2>(v);
-      if (p.store_mode == CS_TW) {
+      if (kStore == CS_TW) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
         twiddle_chain<R2, false>(p, colscale * (uint32_t)j, colscale * (uint32_t)R1, v);
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[(int64_t)(j + r * R1) * p.inner] = v[r];
-      } else if (p.store_mode == CS_CONJ) {
+      } else if (kStore == CS_CONJ) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[(int64_t)(j + r * R1) * p.inner] = cconj(v[r]);
@@ -399,7 +407,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
         T sw = T(1);
         if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
-        W::accumulate(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw);
+        W::accumulate(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw, per_term);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[buf]);       // this warp is done with the buffer (and its mail)
@@ -410,11 +418,11 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];           // publish C (linear index)
     }
     __syncwarp();
-    W::phase_b(p, ctx, s);
+    W::template phase_b<2>(p, ctx, s);
     __syncwarp();
-    W::phase_c(p, ctx, s);
+    W::template phase_c<2>(p, ctx, s);
     __syncwarp();
-    W::phase_d(p, ctx, s, smem_raw);
+    W::template phase_d<2>(p, ctx, s, smem_raw);
     __syncwarp();                    // the exchange buffers are reused by the next item
   }
 }
