@@ -76,9 +76,10 @@ xcb_row_pass(const __grid_constant__ PassParams<T> p) {
     typename P::Ctx ctx;
     ctx.tid = threadIdx.x;
     ctx.bid = blockIdx.x;
+    constexpr int MODE = PRO ? 2 : 1;
     P::phase_info(p, ctx, smem);
     if (!PRO) __syncthreads();   // the pair product derives its rows itself
-    P::phase_load(p, ctx, smem);
+    P::template phase_load<MODE>(p, ctx, smem);
     __syncthreads();
     P::phase_s1_read(p, ctx, smem);
     __syncthreads();
@@ -86,7 +87,7 @@ xcb_row_pass(const __grid_constant__ PassParams<T> p) {
     __syncthreads();
     P::phase_s2(p, ctx, smem);
     __syncthreads();
-    P::phase_store(p, ctx, smem);
+    P::template phase_store<MODE>(p, ctx, smem);
   }
 }
 

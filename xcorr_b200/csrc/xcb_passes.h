@@ -512,13 +512,16 @@ template <class T, int R1, int R2> struct RowPass {
   static constexpr int UB = 8;
 
   // phase 1: global -> shared (transposed)
+  // MODE 0: role from p.load_mode (emulator); 1: forward / plain complex pass; 2: pair product.  The kernels
+  // are compiled per role.
+  template <int MODE = 0>
   static XCB_HD void phase_load(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
     cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
     const RowInfo<T>* info = info_ptr(smem_raw);
     int64_t batch, tile_;
     decode(p, ctx.bid, batch, tile_);
     ctx.ss = 0.0;
-    if (p.load_mode == RL_PROLOGUE) {
+    if (MODE == 2 || (MODE == 0 && p.load_mode == RL_PROLOGUE)) {
       // Pair slot lp (rows ra, rb) is owned by 2*TJ threads; nothing here reads
       // `info`, so the kernel does not wait for phase_info before loading.
       constexpr int TS = 2 * TJ;
@@ -600,7 +603,7 @@ template <class T, int R1, int R2> struct RowPass {
         cx<T> v0; v0.x = fs * (c0 + cm); v0.y = -fs * (c0 - cm);
         smem[2 * lp] = v0;
       }
-    } else if (p.load_mode == RL_REAL) {
+    } else if (MODE != 2 && p.load_mode == RL_REAL) {
       const T* x = reinterpret_cast<const T*>(p.in) + batch * p.in_stride;
       for (int idx = ctx.tid; idx < C * N; idx += G::THREADS) {
         int c = idx / N, e = idx - c * N;
@@ -662,14 +665,13 @@ template <class T, int R1, int R2> struct RowPass {
     }
   }
 
+  template <int MODE = 0>
   static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw) {
-    phase_store(p, ctx, smem_raw, info_ptr(smem_raw));
-  }
-  static XCB_HD void phase_store(const PassParams<T>& p, Ctx& ctx, unsigned char* smem_raw, const RowInfo<T>* info) {
+    const RowInfo<T>* info = info_ptr(smem_raw);
     const cx<T>* smem = reinterpret_cast<const cx<T>*>(smem_raw);
     int64_t batch, tile_;
     decode(p, ctx.bid, batch, tile_);
-    if (p.store_mode == RS_HALF) {
+    if (MODE != 2 && p.store_mode == RS_HALF) {
       // forward last pass: packed transform Z of the pair tile -> half spectrum X
       const int lp = ctx.tid / (2 * TJ), t = ctx.tid - lp * (2 * TJ);
       const RowInfo<T> ia = info[2 * lp];
@@ -724,7 +726,7 @@ template <class T, int R1, int R2> struct RowPass {
         }
       }
     }
-    if (p.sumsq_partial && p.load_mode == RL_REAL)
+    if (MODE != 2 && p.sumsq_partial && p.load_mode == RL_REAL)
       block_sumsq<G::THREADS>(p.sumsq_partial + ctx.bid, red_ptr(smem_raw), ctx.tid);
   }
 };
