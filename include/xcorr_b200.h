@@ -234,6 +234,11 @@ XCB_API int xcb_spectrogram(int32_t dtype, const void* x, int64_t x_stride, int6
                             const double* window, int32_t win_len, int32_t nfft, double scale, int32_t detrend,
                             void* y, void* stream);
 
+/* stream/running_rms.py:73-113 (op 'running_rms'): out[s][k] = sqrt(mean(x[s][k*step : k*step + win]^2)),
+ * k < n_windows; out device double[n_signals][n_windows]. */
+XCB_API int xcb_running_rms(int32_t dtype, const void* x, int64_t stride, int64_t n, int32_t n_signals, int64_t win,
+                            int64_t step, int64_t n_windows, double* out, void* stream);
+
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
  * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not

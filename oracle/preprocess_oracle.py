@@ -17,7 +17,7 @@ import numpy as np
 from scipy import signal
 
 __all__ = ["detrend", "cosine_taper", "taper_window", "taper", "butter_sos", "filter_",
-           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "process"]
+           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "running_rms", "process"]
 
 
 def detrend(x, type="simple"):
@@ -218,6 +218,21 @@ def interpolate_lanczos(x, sampling_rate, new_sampling_rate, a, time_shift=0.0, 
     return y, float(new_sampling_rate)
 
 
+def running_rms(x, sampling_rate, window=1.0):
+    """``stream/running_rms.py:73-113``: ``int(int(endtime - starttime) / window)`` output samples, each the
+    root-mean-square of one obspy ``Trace.slide(window_length=window, step=window)`` window (both end samples
+    included: ``window * fs + 1`` samples).  Returns (data, new_sampling_rate = 1 / window)."""
+    x = np.asarray(x, dtype=np.float64)
+    duration = (len(x) - 1) / sampling_rate
+    npts = int(int(duration) / window)
+    step = int(round(window * sampling_rate))
+    out = np.zeros(npts)
+    for k in range(npts):
+        w = x[k * step:k * step + step + 1]
+        out[k] = np.sqrt(np.sum(np.power(w, 2)) / len(w))
+    return out, 1.0 / window
+
+
 def trim(x, start=0, length=None):
     """Array form of the time-based trims (``stream/client.py:1017`` and
     ``core/process.py:156-157``): samples ``[start, start+length)``."""
@@ -241,6 +256,8 @@ def process(x, sampling_rate, operations):
             y, fs = decimate(y, fs, **params)
         elif name == "trim":
             y = trim(y, **params)
+        elif name == "running_rms":
+            y, fs = running_rms(y, fs, **params)
         elif name == "resample":
             params = dict(params)
             y, fs = resample(y, fs, params.pop("sampling_rate"), **params)

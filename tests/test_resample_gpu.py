@@ -80,3 +80,16 @@ def test_unsupported_variants_raise(env):
         sp.process(x, [("interpolate", {"sampling_rate": 10.0, "method": "cubic"})], sampling_rate=20.0, raise_error=True)
     with pytest.raises(RuntimeError):
         sp.process(x, [("resample", {"sampling_rate": 10.0, "window": "blackman"})], sampling_rate=20.0, raise_error=True)
+
+
+@pytest.mark.parametrize("npts,fs,window", [(30_001, 50.0, 1.0), (30_000, 50.0, 10.0), (7_777, 40.0, 2.5)])
+def test_running_rms_matches_oracle(env, npts, fs, window):
+    torch, sp, pre = env
+    x = traces(3, npts, fs, seed=int(window * 10))
+    for dtype in (np.float32, np.float64):
+        got, fs_out = sp.process(torch.from_numpy(x.astype(dtype)).cuda(), [("running_rms", {"window": window})],
+                                 sampling_rate=fs, raise_error=True, out_dtype=torch.float64)
+        assert fs_out == 1.0 / window
+        for s in range(3):
+            ref, _ = pre.running_rms(x[s].astype(dtype).astype(np.float64), fs, window)
+            assert got[s].shape == ref.shape and np.allclose(got[s].cpu().numpy(), ref, rtol=1e-13)

@@ -199,6 +199,23 @@ __global__ void __launch_bounds__(256) k_spectrogram(const T* __restrict__ x, in
   }
 }
 
+// stream/running_rms.py:73-113: root-mean-square over consecutive windows of `win` samples starting every
+// `step` samples (obspy Trace.slide: both window ends included).  One warp per (trace, window), fixed order.
+template <class T>
+__global__ void __launch_bounds__(256) k_running_rms(const T* __restrict__ x, int64_t stride, int64_t win, int64_t step,
+                                                     int64_t n_windows, int32_t n_signals, double* __restrict__ out) {
+  const int64_t w = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_windows * n_signals) return;
+  const int64_t sig = w / n_windows, k = w - sig * n_windows;
+  const T* p = x + sig * stride + k * step;
+  double a = 0.0;
+  for (int64_t i = lane; i < win; i += 32) { const double v = (double)p[i]; a = fma(v, v, a); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if (lane == 0) out[w] = sqrt(a / (double)win);
+}
+
 int fail(cudaError_t e) { return e == cudaSuccess ? XCB_OK : XCB_ERR_CUDA; }
 
 }  // namespace
@@ -282,5 +299,20 @@ extern "C" int xcb_spectrogram(int32_t dtype, const void* x, int64_t x_stride, i
     k_spectrogram<double><<<grid, 256, smem, st>>>(static_cast<const double*>(x), x_stride, n, window, win_len, nfft,
                                                    scale, detrend, edge, static_cast<double*>(y));
   }
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_running_rms(int32_t dtype, const void* x, int64_t stride, int64_t n, int32_t n_signals, int64_t win,
+                               int64_t step, int64_t n_windows, double* out, void* stream) {
+  if (!x || !out || n < 1 || n_signals < 1 || win < 1 || step < 1 || n_windows < 1) return XCB_ERR_ARG;
+  if ((n_windows - 1) * step + win > n) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t warps = n_windows * n_signals;
+  const unsigned grid = (unsigned)((warps * 32 + 255) / 256);
+  if (dtype == XCB_F32)
+    k_running_rms<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), stride, win, step, n_windows, n_signals, out);
+  else if (dtype == XCB_F64)
+    k_running_rms<double><<<grid, 256, 0, st>>>(static_cast<const double*>(x), stride, win, step, n_windows, n_signals, out);
+  else return XCB_ERR_ARG;
   return fail(cudaGetLastError());
 }

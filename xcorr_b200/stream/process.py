@@ -18,6 +18,7 @@ Operations with array semantics run on the device through the C ABI
 ``decimate``  ``factor`` (<= 16), ``no_filter`` -- Chebyshev-II low-pass + ``[::factor]``
 ``trim``      sample-based: ``start``, ``length`` (the time-based trim of the
               reference is resolved to samples by the caller)
+``running_rms``  ``window`` seconds (``stream/running_rms.py``): rms of consecutive windows
 ============  ===============================================================
 
 Filter *design* (``scipy.signal.iirfilter`` / ``cheb2ord`` / ``cheby2`` /
@@ -55,7 +56,7 @@ _operations = {
     'attach_response': False, 'decimate': True, 'detrend': True, 'filter': True,
     'interpolate': True, 'merge': False, 'normalize': False, 'remove_response': False,
     'remove_sensitivity': False, 'resample': True, 'rotate': False, 'select': False,
-    'simulate': False, 'taper': True, 'trim': True, 'running_rms': False,
+    'simulate': False, 'taper': True, 'trim': True, 'running_rms': True,
 }
 
 _DETREND = {'demean': 1, 'constant': 1, 'linear': 2, 'simple': 3}
@@ -379,6 +380,20 @@ class PreprocessProgram:
                     raise ValueError("The new array would extend past the end of the trace.")
                 self.steps.append(('interpolate', n, fs, npts_new, new_fs, a, start_rel))
                 n, fs = npts_new, new_fs
+            elif op == 'running_rms':
+                # stream/running_rms.py:73-113: rms over consecutive windows (obspy Trace.slide, both ends included)
+                window = float(params.pop('window', 1.))
+                if params:
+                    raise TypeError(f"running_rms: unsupported arguments {sorted(params)}")
+                flush()
+                duration = (n - 1) / fs
+                n_win = int(int(duration) / window)
+                step = int(round(window * fs))
+                if n_win < 1 or step < 1:
+                    raise ValueError('running_rms: trace shorter than one window')
+                win = min(step + 1, n - (n_win - 1) * step)
+                self.steps.append(('running_rms', n, fs, n_win, 1.0 / window, win, step))
+                n, fs = n_win, 1.0 / window
             elif op == 'trim':
                 flush()
                 start = int(params.get('start', 0))
@@ -396,7 +411,7 @@ class PreprocessProgram:
             if st[0] == 'trim':
                 n = st[2]
                 continue
-            if st[0] in ('resample', 'interpolate'):
+            if st[0] in ('resample', 'interpolate', 'running_rms'):
                 n, fs = st[3], st[4]
                 continue
             s = st[1]
@@ -499,6 +514,14 @@ class PreprocessProgram:
             if st[0] == 'interpolate':
                 from .resample import interpolate_lanczos
                 cur = interpolate_lanczos(cur, st[1], st[2], st[3], st[4], st[5], st[6])
+                continue
+            if st[0] == 'running_rms':
+                if cur.stride(1) != 1:
+                    cur = cur.contiguous()
+                y = torch.empty((nsig, st[3]), dtype=torch.float64, device=dev)
+                _lib.check(lib.xcb_running_rms(xcb[cur.dtype], cur.data_ptr(), cur.stride(0), st[1], nsig, st[5], st[6],
+                                               st[3], y.data_ptr(), stream), 'xcb_running_rms')
+                cur = y
                 continue
             s = st[1]
             i_stage += 1
