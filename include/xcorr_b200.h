@@ -239,6 +239,11 @@ XCB_API int xcb_spectrogram(int32_t dtype, const void* x, int64_t x_stride, int6
 XCB_API int xcb_running_rms(int32_t dtype, const void* x, int64_t stride, int64_t n, int32_t n_signals, int64_t win,
                             int64_t step, int64_t n_windows, double* out, void* stream);
 
+/* obspy Trace.normalize (op 'normalize'): x[s] /= max |x[s]| with window_stats = the output of xcb_window_stats over
+ * the whole trace (in place), or x /= |norm| when window_stats is NULL. */
+XCB_API int xcb_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_t n, int32_t n_signals,
+                               const double* window_stats, double norm, void* stream);
+
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
  * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not

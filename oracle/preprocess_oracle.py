@@ -17,7 +17,7 @@ import numpy as np
 from scipy import signal
 
 __all__ = ["detrend", "cosine_taper", "taper_window", "taper", "butter_sos", "filter_",
-           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "running_rms", "process"]
+           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "running_rms", "normalize", "process"]
 
 
 def detrend(x, type="simple"):
@@ -233,6 +233,14 @@ def running_rms(x, sampling_rate, window=1.0):
     return out, 1.0 / window
 
 
+def normalize(x, norm=None):
+    """obspy ``Trace.normalize``: divide by ``abs(norm)``; ``norm=None`` -> the trace's largest absolute value."""
+    x = np.asarray(x, dtype=np.float64)
+    if norm is None:
+        norm = np.max(np.abs(x))
+    return x / abs(norm)
+
+
 def trim(x, start=0, length=None):
     """Array form of the time-based trims (``stream/client.py:1017`` and
     ``core/process.py:156-157``): samples ``[start, start+length)``."""
@@ -258,6 +266,8 @@ def process(x, sampling_rate, operations):
             y = trim(y, **params)
         elif name == "running_rms":
             y, fs = running_rms(y, fs, **params)
+        elif name == "normalize":
+            y = normalize(y, **params)
         elif name == "resample":
             params = dict(params)
             y, fs = resample(y, fs, params.pop("sampling_rate"), **params)

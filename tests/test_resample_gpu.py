@@ -93,3 +93,15 @@ def test_running_rms_matches_oracle(env, npts, fs, window):
         for s in range(3):
             ref, _ = pre.running_rms(x[s].astype(dtype).astype(np.float64), fs, window)
             assert got[s].shape == ref.shape and np.allclose(got[s].cpu().numpy(), ref, rtol=1e-13)
+
+
+def test_normalize_matches_oracle(env):
+    torch, sp, pre = env
+    x = traces(3, 5000, 50.0, seed=4) * np.array([[1.0], [-7.5], [1e-3]])
+    ops = [("detrend", {"type": "demean"}), ("normalize", {}), ("taper", {"type": "hann", "max_percentage": 0.05})]
+    got, _ = sp.process(torch.from_numpy(x).cuda(), ops, sampling_rate=50.0, raise_error=True)
+    for s in range(3):
+        ref, _ = pre.process(x[s], 50.0, ops)
+        assert np.max(np.abs(got[s].cpu().numpy() - ref)) <= 1e-13
+    got, _ = sp.process(torch.from_numpy(x).cuda(), [("normalize", {"norm": -4.0})], sampling_rate=50.0, raise_error=True)
+    assert np.allclose(got.cpu().numpy(), x / 4.0, rtol=1e-15)

@@ -124,6 +124,7 @@ SYMBOLS = {
     "xcb_window_stats": (ctypes.c_int, [_i32, _vp, _i64, _i32, _i64, _i64, _i64, _i64, _vp, _vp]),
     "xcb_spectrogram": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _i32, _i32, ctypes.c_double, _i32, _vp, _vp]),
     "xcb_running_rms": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "xcb_normalize_rows": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, ctypes.c_double, _vp]),
     "xcb_cc_host": (ctypes.c_int, [_i32, _i64, _vp, _vp, _i32, _i32, _i64, _i64, _vp]),
 }
 

@@ -216,6 +216,17 @@ __global__ void __launch_bounds__(256) k_running_rms(const T* __restrict__ x, in
   if (lane == 0) out[w] = sqrt(a / (double)win);
 }
 
+// obspy Trace.normalize(norm=None): x /= max |x| of the trace (stats[s][0] from k_window_stats); norm given: x /= |norm|
+template <class T>
+__global__ void k_normalize_rows(T* __restrict__ x, int64_t stride, int64_t n, const double* __restrict__ stats,
+                                 double norm) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t s = blockIdx.y;
+  const double d = stats ? stats[s * 3] : fabs(norm);
+  x[s * stride + i] = (T)((double)x[s * stride + i] / d);
+}
+
 int fail(cudaError_t e) { return e == cudaSuccess ? XCB_OK : XCB_ERR_CUDA; }
 
 }  // namespace
@@ -313,6 +324,17 @@ extern "C" int xcb_running_rms(int32_t dtype, const void* x, int64_t stride, int
     k_running_rms<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), stride, win, step, n_windows, n_signals, out);
   else if (dtype == XCB_F64)
     k_running_rms<double><<<grid, 256, 0, st>>>(static_cast<const double*>(x), stride, win, step, n_windows, n_signals, out);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+extern "C" int xcb_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_t n, int32_t n_signals,
+                                  const double* window_stats, double norm, void* stream) {
+  if (!x || n < 1 || n_signals < 1) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_signals);
+  if (dtype == XCB_F32) k_normalize_rows<float><<<grid, 256, 0, st>>>(static_cast<float*>(x), stride, n, window_stats, norm);
+  else if (dtype == XCB_F64) k_normalize_rows<double><<<grid, 256, 0, st>>>(static_cast<double*>(x), stride, n, window_stats, norm);
   else return XCB_ERR_ARG;
   return fail(cudaGetLastError());
 }

@@ -19,6 +19,7 @@ Operations with array semantics run on the device through the C ABI
 ``trim``      sample-based: ``start``, ``length`` (the time-based trim of the
               reference is resolved to samples by the caller)
 ``running_rms``  ``window`` seconds (``stream/running_rms.py``): rms of consecutive windows
+``normalize``  obspy ``Trace.normalize``: divide by max |x| (or by ``norm``)
 ============  ===============================================================
 
 Filter *design* (``scipy.signal.iirfilter`` / ``cheb2ord`` / ``cheby2`` /
@@ -54,7 +55,7 @@ __all__ = ['process', 'list_operations', 'is_operation', 'device_operations',
 # the reference's whitelist (stream/process.py:29-94); True = runs on the device
 _operations = {
     'attach_response': False, 'decimate': True, 'detrend': True, 'filter': True,
-    'interpolate': True, 'merge': False, 'normalize': False, 'remove_response': False,
+    'interpolate': True, 'merge': False, 'normalize': True, 'remove_response': False,
     'remove_sensitivity': False, 'resample': True, 'rotate': False, 'select': False,
     'simulate': False, 'taper': True, 'trim': True, 'running_rms': True,
 }
@@ -380,6 +381,13 @@ class PreprocessProgram:
                     raise ValueError("The new array would extend past the end of the trace.")
                 self.steps.append(('interpolate', n, fs, npts_new, new_fs, a, start_rel))
                 n, fs = npts_new, new_fs
+            elif op == 'normalize':
+                # obspy Trace.normalize(norm=None): divide by the trace's max |x| (or by |norm|)
+                norm = params.pop('norm', None)
+                if params:
+                    raise TypeError(f"normalize: unsupported arguments {sorted(params)}")
+                flush()
+                self.steps.append(('normalize', n, fs, n, fs, None if norm is None else float(norm)))
             elif op == 'running_rms':
                 # stream/running_rms.py:73-113: rms over consecutive windows (obspy Trace.slide, both ends included)
                 window = float(params.pop('window', 1.))
@@ -411,7 +419,7 @@ class PreprocessProgram:
             if st[0] == 'trim':
                 n = st[2]
                 continue
-            if st[0] in ('resample', 'interpolate', 'running_rms'):
+            if st[0] in ('resample', 'interpolate', 'running_rms', 'normalize'):
                 n, fs = st[3], st[4]
                 continue
             s = st[1]
@@ -514,6 +522,19 @@ class PreprocessProgram:
             if st[0] == 'interpolate':
                 from .resample import interpolate_lanczos
                 cur = interpolate_lanczos(cur, st[1], st[2], st[3], st[4], st[5], st[6])
+                continue
+            if st[0] == 'normalize':
+                y = cur.clone() if (cur is x or cur.stride(1) != 1 or cur._base is not None) else cur
+                y = y.contiguous()
+                stats_ptr = None
+                if st[5] is None:
+                    ws = torch.empty((nsig, 3), dtype=torch.float64, device=dev)
+                    _lib.check(lib.xcb_window_stats(xcb[y.dtype], y.data_ptr(), y.stride(0), nsig, 0, st[1], 0, 1,
+                                                    ws.data_ptr(), stream), 'xcb_window_stats')
+                    stats_ptr = ws.data_ptr()
+                _lib.check(lib.xcb_normalize_rows(xcb[y.dtype], y.data_ptr(), y.stride(0), st[1], nsig, stats_ptr,
+                                                  0.0 if st[5] is None else st[5], stream), 'xcb_normalize_rows')
+                cur = y
                 continue
             if st[0] == 'running_rms':
                 if cur.stride(1) != 1:
