@@ -139,3 +139,19 @@ def test_spectrogram(env, kw, dtype):
     assert np.max(np.abs(got - ref)) <= (1e-11 if dtype == np.float64 else 2e-5) * np.max(ref)
     edge = int(np.rint(int(kw["duration"] * 50.0) / 2))
     assert np.all(got[..., :edge] == 0) and np.all(got[..., -1] == 0)
+
+
+def test_linear_detrend_and_rms(env):
+    """signal/detrend.py (scipy.stats.linregress line) and signal/rms.py."""
+    import scipy.stats
+    torch, sg, so = env
+    x = ccfs((2, 4, 3000), 33) + 1e-3 * np.arange(3000)
+    lag = np.arange(3000) / 50.0 - 7.0
+    got = sg.detrend(torch.from_numpy(x).cuda(), type="linear").cpu().numpy()
+    ref = np.empty_like(x)
+    for idx in np.ndindex(x.shape[:-1]):
+        m, b, *_ = scipy.stats.linregress(lag, x[idx])
+        ref[idx] = x[idx] - (m * lag + b)
+    assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+    assert np.max(np.abs(sg.detrend(torch.from_numpy(x).cuda()).cpu().numpy() - so.demean(x))) <= 1e-12
+    assert np.allclose(sg.rms(torch.from_numpy(x).cuda()), np.sqrt(np.mean(x * x, axis=-1)), rtol=1e-13)

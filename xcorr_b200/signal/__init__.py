@@ -6,5 +6,6 @@ wrappers (``signal/fft.py``) and the CCF post-processing operators chained by
 from .correlate import correlate1d, correlate2d, Correlate2dPlan  # noqa: F401
 from .normalize import norm1d, norm2d  # noqa: F401
 from .fft import DFT, fft, ifft, rfft, irfft  # noqa: F401
-from .postprocess_ops import (unbias, unbias_weights, demean, taper, window, timeshift, filter, snr)  # noqa: F401
+from .postprocess_ops import (unbias, unbias_weights, demean, detrend, rms, taper, window, timeshift, filter,  # noqa: F401
+                              snr)
 from .spectrogram import spectrogram  # noqa: F401

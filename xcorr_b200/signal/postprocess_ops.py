@@ -37,7 +37,7 @@ from ..stream.process import _carry_matrices, _SCAN_CHUNK
 from ..util.cc import weight
 from .fft import _plan
 
-__all__ = ['unbias', 'unbias_weights', 'demean', 'taper', 'window', 'timeshift', 'filter', 'snr']
+__all__ = ['unbias', 'unbias_weights', 'demean', 'detrend', 'rms', 'taper', 'window', 'timeshift', 'filter', 'snr']
 
 _CODE = {torch.float32: _lib.XCB_F32, torch.float64: _lib.XCB_F64}
 
@@ -109,6 +109,26 @@ def demean(x):
     """``x - x.mean(dim)`` (``signal/detrend.py:113``)."""
     x2, lead = _rows(x)
     return _pointwise(x2, detrend=1).reshape(*lead, -1)
+
+
+def detrend(x, type=None):
+    """``signal/detrend.py:30-111``: ``type='constant'`` (default) removes the mean, ``'linear'`` the
+    least-squares line over the (regularly spaced) last axis -- what ``scipy.stats.linregress`` fits there."""
+    type = type or 'constant'
+    if type not in ('constant', 'linear'):
+        raise KeyError('type should be any of "constant|linear"')
+    x2, lead = _rows(x)
+    return _pointwise(x2, detrend=1 if type == 'constant' else 2).reshape(*lead, -1)
+
+
+def rms(x):
+    """``signal/rms.py``: root-mean-square along the last axis (host array, float64)."""
+    x2, lead = _rows(x)
+    out = torch.empty((x2.shape[0], 3), dtype=torch.float64, device=x2.device)
+    n = x2.shape[1]
+    _lib.check(_lib.load().xcb_window_stats(_CODE[x2.dtype], x2.data_ptr(), x2.stride(0), x2.shape[0], 0, 1, 0, n,
+                                            out.data_ptr(), _stream(x2)), 'xcb_window_stats')
+    return np.sqrt(out.cpu().numpy()[:, 2] / float(n)).reshape(lead)
 
 
 def window(n, sampling_rate, wtype=None, max_percentage=None, max_length=None, side=None):
