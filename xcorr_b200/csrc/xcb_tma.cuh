@@ -56,7 +56,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // the spinning warps do not take issue slots from the warps that have work
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  uint32_t ns = 32;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 512) ns *= 2;
+  }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile(
@@ -334,7 +338,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     for (;;) {
       if (cur.item >= n_items) {
         const int buf = (int)(step % NBUF);
-        mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
+        mbar_wait_backoff(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
         if (lane == 0) { mail[buf].item = -1; mbar_arrive(&full[buf]); }
         break;
       }
@@ -346,7 +350,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       const cx<T> wr = cmul(cur.hi, cur.lo);
       for (int w = 0; w < n_terms; ++w, ++step) {
         const int buf = (int)(step % NBUF);
-        mbar_wait(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
+        mbar_wait_backoff(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
         if (w == 0 && lane < 2) {
           mail[buf].wrow[lane] = wr;
           if (lane == 0) { mail[buf].item = cur.item; mail[buf].ra = cur.ra; mail[buf].rb = cur.rb; }
