@@ -491,10 +491,52 @@ inline void build_pair_groups(const Job* jobs, int n_jobs, int max_jobs, int max
       const int k = std::min<int>((int)mine.size(), std::min(max_jobs, max_rows - 1));
       for (int c = 0; c < k; ++c) add(g, mine[(size_t)c]);
     }
+    out.push_back(g);
+  }
+  // second pass: merge the leftovers (partial blocks at the edge of the pair triangle, lone pairs) into
+  // neighbouring groups while the union still fits -- every group costs a full CTA pass per row pair
+  // whatever its size, so fewer, fuller groups are faster
+  auto try_merge = [&](PairGroup& a, const PairGroup& b) {
+    if (a.n_jobs + b.n_jobs > max_jobs) return false;
+    PairGroup u = a;
+    for (int w = 0; w < b.n_jobs; ++w) {
+      const int64_t si = b.spec_i[b.ji[w]], sj = b.spec_j[b.jj[w]];
+      int x = 0, y = 0;
+      while (x < u.n_i && u.spec_i[x] != si) ++x;
+      if (x == u.n_i) { if (u.n_i == kGroupJobs) return false; u.spec_i[u.n_i++] = si; }
+      while (y < u.n_j && u.spec_j[y] != sj) ++y;
+      if (y == u.n_j) { if (u.n_j == kGroupJobs) return false; u.spec_j[u.n_j++] = sj; }
+      if (u.n_i + u.n_j > max_rows) return false;
+      u.job[u.n_jobs] = b.job[w];
+      u.ji[u.n_jobs] = (uint8_t)x;
+      u.jj[u.n_jobs] = (uint8_t)y;
+      ++u.n_jobs;
+    }
+    a = u;
+    return true;
+  };
+  std::vector<char> dead(out.size(), 0);
+  const int kWindow = 48;                                 // groups of one window are neighbours
+  for (size_t b = 0; b < out.size(); ++b) {
+    if (out[b].n_jobs >= max_jobs) continue;
+    // best fit: the fullest neighbour that still takes this group
+    int best = -1;
+    const size_t lo = b > (size_t)kWindow ? b - kWindow : 0, hi = std::min(out.size(), b + kWindow + 1);
+    for (size_t a = lo; a < hi; ++a) {
+      if (a == b || dead[a] || out[a].n_jobs >= max_jobs || out[a].n_jobs + out[b].n_jobs > max_jobs) continue;
+      PairGroup trial = out[a];
+      if (!try_merge(trial, out[b])) continue;
+      if (best < 0 || out[a].n_jobs > out[(size_t)best].n_jobs) best = (int)a;
+    }
+    if (best >= 0) { try_merge(out[(size_t)best], out[b]); dead[b] = 1; }
+  }
+  size_t k = 0;
+  for (size_t a = 0; a < out.size(); ++a) if (!dead[a]) out[k++] = out[a];
+  out.resize(k);
+  for (PairGroup& g : out) {
     for (int a = 0; a < g.n_i; ++a) g.rows[a] = g.spec_i[a];
     for (int b = 0; b < g.n_j; ++b) g.rows[g.n_i + b] = g.spec_j[b];
     g.n_rows = g.n_i + g.n_j;
-    out.push_back(g);
   }
 }
 
