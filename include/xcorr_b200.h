@@ -85,6 +85,8 @@ typedef struct xcb_plan_info {
   int32_t dtype;
   int32_t n_blocks;        /* 1 = classic */
   int64_t block_len;
+  int32_t n_groups;        /* job groups per launch of the staged pair product (0: the plain row kernel runs) */
+  int32_t reserved;
 } xcb_plan_info;
 
 XCB_API const char* xcb_strerror(int status);
@@ -244,6 +246,11 @@ XCB_API int xcb_running_rms(int32_t dtype, const void* x, int64_t stride, int64_
 XCB_API int xcb_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_t n, int32_t n_signals,
                                const double* window_stats, double norm, void* stream);
 
+/* signal/normalize.py:33-155 (norm1d, norm2d; used by correlate1d/2d): every row divided by its 2-norm in place,
+ * the norm being sqrt(window_stats[s][2]) from xcb_window_stats over the whole row (fixed-order float64 sum). */
+XCB_API int xcb_l2_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_t n, int32_t n_signals,
+                                  const double* window_stats, void* stream);
+
 /* Measurement aid (bench.py): when enabled, every pass kernel this plan launches
  * is bracketed by CUDA events on its stream.  Kinds 0..nd-1 are the forward
  * passes (axis order), nd..2nd-1 the inverse passes of the same axes.  Not
@@ -258,6 +265,10 @@ XCB_API int xcb_profile_read(xcb_plan* plan, int32_t* n_kinds, double* total_ms,
  * (lag_index_max - lag_index_min) elements (both 0 -> 2n-1). */
 XCB_API int xcb_cc_host(int32_t dtype, int64_t n, const void* x, const void* y, int32_t normalize,
                 int32_t unbiased, int64_t lag_index_min, int64_t lag_index_max, void* out);
+/* xcb_cc_host keeps the plan, device buffers and stream of the last few (device, dtype, n, crop, flags)
+ * it was called with (the reference calls cc() once per pair and window with the same shape,
+ * core/process.py:155-162); this frees them. */
+XCB_API int xcb_cc_host_clear_cache(void);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ import numpy as np
 from scipy import signal
 
 __all__ = ["detrend", "cosine_taper", "taper_window", "taper", "butter_sos", "filter_",
-           "cheby2_lowpass_sos", "decimate", "trim", "resample", "interpolate_lanczos", "running_rms", "normalize", "process"]
+           "cheby2_lowpass_sos", "decimate", "trim", "trim_time", "resample", "interpolate_lanczos", "running_rms", "normalize", "process"]
 
 
 def detrend(x, type="simple"):
@@ -247,13 +247,40 @@ def trim(x, start=0, length=None):
     return x[start:] if length is None else x[start:start + length]
 
 
-def process(x, sampling_rate, operations):
+def trim_time(x, sampling_rate, trace_start, starttime=None, endtime=None):
+    """obspy ``Trace.trim(starttime, endtime, pad=False, nearest_sample=True)`` on an
+    array whose first sample sits at `trace_start` seconds (what ``('trim', {})`` becomes once
+    ``stream/process.py:153-196`` injected the window, and ``stream/client.py:1017``).
+    Follows ``Trace._ltrim`` then ``Trace._rtrim``.  Returns ``(y, new_trace_start)``."""
+    def round_away(v):                      # obspy.core.compatibility.round_away
+        return int(np.sign(v) * np.floor(np.abs(v) + 0.5))
+    y = np.asarray(x)
+    if starttime is not None:               # _ltrim
+        delta = round_away((starttime - trace_start) * sampling_rate)
+        if delta > 0:
+            y = y[delta:]
+            trace_start = trace_start + delta / sampling_rate
+    if endtime is not None:                 # _rtrim
+        if endtime < trace_start:           # "endtime < starttime": obspy leaves an empty trace
+            return y[:0], trace_start
+        delta = round_away((endtime - trace_start) * sampling_rate) - len(y) + 1
+        if delta < 0:
+            y = y[:len(y) - abs(delta)]
+    return y, trace_start
+
+
+def process(x, sampling_rate, operations, trace_start=0.0, starttime=None, endtime=None, return_start=False):
     """Apply an op-list ``[(name, params), ...]`` to one trace.  Returns
-    ``(y, sampling_rate)``."""
+    ``(y, sampling_rate)`` (and the time of the first output sample with `return_start`).
+    ``('trim', {})`` receives `starttime` / `endtime` like ``stream/process.py:153-196``."""
     y = np.asarray(x, dtype=np.float64)
     fs = float(sampling_rate)
+    t0 = float(trace_start)
     for name, params in operations:
         params = dict(params)
+        if name == "trim" and "start" not in params and "length" not in params:
+            y, t0 = trim_time(y, fs, t0, params.get("starttime", starttime), params.get("endtime", endtime))
+            continue
         if name == "detrend":
             y = detrend(y, params.get("type", "simple"))
         elif name == "taper":
@@ -278,4 +305,4 @@ def process(x, sampling_rate, operations):
             y, fs = interpolate_lanczos(y, fs, params.pop("sampling_rate"), **params)
         else:
             raise NotImplementedError(f"operation {name!r} is outside the array-valued hot path")
-    return y, fs
+    return (y, fs, t0) if return_start else (y, fs)

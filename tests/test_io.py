@@ -59,7 +59,9 @@ def test_write_protocol_and_round_trip(tmp_path):
     assert ds.attrs["sha256_hash_metadata"] == hash_dataset(ds)
     assert len(ds.attrs["sha256_hash"]) == 64
     back = read(path)
-    assert back.attrs["Conventions"] == "CF-1.9" and back.attrs["sha256_hash"] == ds.attrs["sha256_hash"]
+    # read() verifies the stored data hash and drops it (io/read.py:184-185)
+    assert back.attrs["Conventions"] == "CF-1.9" and "sha256_hash" not in back.attrs
+    assert hash_dataset(back, metadata_only=False) == ds.attrs["sha256_hash"]
     for name in ("cc", "status", "pair_offset", "time_offset", "distance"):
         a, b = ds.variables[name], back.variables[name]
         assert tuple(a.dims) == tuple(b.dims) and np.array_equal(a.data, b.data, equal_nan=True)
@@ -75,3 +77,54 @@ def test_write_protocol_and_round_trip(tmp_path):
         assert write(empty, os.path.join(tmp_path, "empty.nc"), verb=0) is None
     assert any("no data" in str(x.message) for x in w) and not os.path.exists(os.path.join(tmp_path, "empty.nc"))
     assert write(empty, os.path.join(tmp_path, "empty.nc"), force_write=True, verb=0)
+
+
+def test_hashes_equal_the_reference_hasher_golden():
+    """tests/golden/hash_golden.json was produced by executing the reference's util/hasher.py
+    (hash_Dataset) on the same variable set (tests/golden/make_golden_hash.py)."""
+    import json
+    from tests.golden.make_golden_hash import golden_dataset
+    from xcorr_b200.io import hash_dataset, to_json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hash_golden.json")))
+    ds = golden_dataset()
+    assert hash_dataset(ds, metadata_only=True) == gold["metadata"]
+    assert hash_dataset(ds, metadata_only=False) == gold["data"]
+    assert to_json({"b": np.int8(1), "a": np.float32(0.5), "sha256_hash": "x", "scale_factor": 1.0}) == gold["to_json_sample"]
+    # util/hasher.py:22-35: stored hashes and packing attributes never enter a hash
+    ds.attrs["sha256_hash"] = "anything"
+    ds.attrs["sha256_hash_metadata"] = gold["metadata"]
+    assert hash_dataset(ds, metadata_only=False) == gold["data"]
+
+
+def test_stored_hashes_survive_write_read_and_rewrite(tmp_path):
+    """the stored sha256_hash must equal the hash recomputed after write() and after read(),
+    writing twice must store the same hash, and read() must give back a set process() can resume."""
+    from xcorr_b200.io import write, read, hash_dataset
+    ds = _dataset()
+    p1, p2 = os.path.join(tmp_path, "a.nc"), os.path.join(tmp_path, "b.nc")
+    write(ds, p1, verb=0)
+    h_data, h_meta = ds.attrs["sha256_hash"], ds.attrs["sha256_hash_metadata"]
+    assert hash_dataset(ds, metadata_only=False) == h_data and hash_dataset(ds) == h_meta
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                       # no "metadata hash is updated" on an unchanged set
+        write(ds, p2, verb=0)
+    assert ds.attrs["sha256_hash"] == h_data and ds.attrs["sha256_hash_metadata"] == h_meta
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                       # metadata hash consistent after the round trip
+        back = read(p1)
+    assert "sha256_hash" not in back.attrs                    # io/read.py:184-185
+    assert hash_dataset(back, metadata_only=False) == h_data
+    assert hash_dataset(back) == h_meta == back.attrs["sha256_hash_metadata"]
+    ops = back.coords["pair"].attrs["preprocess"]
+    assert isinstance(ops, dict) and "HHZ" in ops and [o[0] for o in ops["HHZ"]] == ["detrend"]
+    assert back.coords["time"].attrs["closed"] == ds.coords["time"].attrs["closed"]
+    # a corrupted file is detected by the data hash
+    raw = bytearray(open(p1, "rb").read())
+    raw[-40] ^= 0xFF
+    open(p1, "wb").write(bytes(raw))
+    with pytest.raises(ValueError):
+        read(p1)
+    # int64 data that does not fit NetCDF-3 raises instead of being truncated
+    ds.variables["big"] = type(ds.variables["cc"])(("pair",), np.array([2**40, 1], dtype=np.int64))
+    with pytest.raises(OverflowError):
+        write(ds, os.path.join(tmp_path, "c.nc"), verb=0)

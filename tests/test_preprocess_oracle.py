@@ -1,5 +1,6 @@
 """Known-answer tests pinning the (otherwise unpinned) obspy restatement."""
 import numpy as np
+import pytest
 from scipy import signal
 
 from oracle import preprocess_oracle as pre
@@ -136,3 +137,32 @@ def test_signal_oracle_known_answers():
     r, s, nn, idx = so.snr(np.r_[np.ones(10), [-7.0], np.ones(9)], np.r_[np.zeros(8, bool), np.ones(12, bool)],
                            np.r_[np.ones(8, bool), np.zeros(12, bool)])
     assert s == 7.0 and nn == 1.0 and idx == 10 and r == 7.0
+
+
+def test_time_based_trim_matches_the_obspy_restatement():
+    """Host arithmetic of ('trim', {starttime, endtime}) in the op compiler against the oracle's
+    Trace._ltrim / _rtrim restatement, incl. the buffered-window case of stream/client.py:499-519."""
+    from xcorr_b200.stream.process import PreprocessProgram, trim_samples, inject_dynamic_parameters
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n = int(rng.integers(5, 400))
+        fs = float(rng.choice([1.0, 10.0, 50.0, 250.0]))
+        t0 = float(rng.uniform(-20, 20))
+        a = t0 + float(rng.uniform(-5, 0.9 * n / fs))
+        b = a + float(rng.uniform(0.01, 1.5 * n / fs))
+        x = np.arange(n, dtype=np.float64)
+        y, t1 = pre.trim_time(x, fs, t0, a, b)
+        if len(y) < 1:
+            with pytest.raises(ValueError):
+                trim_samples(n, fs, t0, a, b)
+            continue
+        s, k = trim_samples(n, fs, t0, a, b)
+        assert (s, k) == (int(y[0]), len(y)) and abs(t1 - (t0 + s / fs)) < 1e-12
+    # the reference's window: 24 h + 5 % buffer on both sides at 250 Hz, decimated by 5, then ('trim', {})
+    wl, fs = 86400.0, 250.0
+    n_raw = int(1.1 * wl * fs) + 1
+    ops = [("decimate", {"factor": 5}), ("trim", {})]
+    ops = [(o, inject_dynamic_parameters(o, p, starttime=0.0, endtime=wl)) for o, p in ops]
+    prog = PreprocessProgram(ops, n_raw, fs, trace_start=-0.05 * wl)
+    assert (prog.npts_out, prog.fs_out, prog.trace_start_out) == (int(wl * 50) + 1, 50.0, 0.0)
+    assert inject_dynamic_parameters("trim", {"start": 3}, starttime=0.0, endtime=1.0) == {"start": 3}

@@ -57,6 +57,8 @@ class xcb_plan_info(ctypes.Structure):
         ("dtype", ctypes.c_int32),
         ("n_blocks", ctypes.c_int32),
         ("block_len", ctypes.c_int64),
+        ("n_groups", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -125,7 +127,9 @@ SYMBOLS = {
     "xcb_spectrogram": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _i32, _i32, ctypes.c_double, _i32, _vp, _vp]),
     "xcb_running_rms": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _i64, _i64, _i64, _vp, _vp]),
     "xcb_normalize_rows": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, ctypes.c_double, _vp]),
+    "xcb_l2_normalize_rows": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _vp]),
     "xcb_cc_host": (ctypes.c_int, [_i32, _i64, _vp, _vp, _i32, _i32, _i64, _i64, _vp]),
+    "xcb_cc_host_clear_cache": (ctypes.c_int, []),
 }
 
 _lib = None

@@ -72,6 +72,22 @@ class CCDataset:
         return ds
 
 
+def _zeros_maybe_pinned(shape, dtype, pin_memory):
+    """Zero-filled host array; page-locked when asked for (or by default with a CUDA device), so
+    device-to-host copies into it run at full PCIe speed without a staging copy."""
+    if pin_memory is None or pin_memory:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.zeros(shape, dtype=torch.float32 if np.dtype(dtype) == np.float32 else torch.float64,
+                                pin_memory=True)
+                return t.numpy()
+        except Exception:
+            if pin_memory:
+                raise
+    return np.zeros(shape, dtype=dtype)
+
+
 def _json_attrs(attrs):
     return {k: (json.dumps(v) if isinstance(v, dict) else v) for k, v in attrs.items()}
 
@@ -82,6 +98,7 @@ def init(
     window_length: float = 86400., window_overlap: float = 0.875,
     clip_lag=None, unbiased_cc: bool = False, closed: str = 'left',
     dtype: np.dtype = np.float32, distance=None, hash_waveforms: bool = False,
+    pin_memory=None,
 ):
     """
     Initiate the cross-correlation variable set (``core/init.py:25``).
@@ -90,7 +107,9 @@ def init(
     list of ``'{net}.{sta}.{loc}.{cha}-{net}.{sta}.{loc}.{cha}'`` strings (one
     dataset for all pairs) and the geodetic distance, which the reference
     derives from an obspy inventory with pyproj, is passed in (`distance`, km
-    per pair, default NaN).
+    per pair, default NaN).  `pin_memory` (default: when a CUDA device is present) places the
+    ``cc`` array in page-locked host memory so that :func:`xcorr_b200.core.process` copies the
+    correlation functions from the device straight into it.
     """
     if not isinstance(attrs, dict):
         raise TypeError('attrs should be a dictionary')
@@ -140,7 +159,7 @@ def init(
     inclusive = {None: 'both', 'left': 'left', 'right': 'right'}[closed]
     times = pd.date_range(start=starttime, end=endtime,
                           freq='{0:.0f}s'.format(window_length * (1 - window_overlap)), inclusive=inclusive)
-    ds.coords['time'] = Variable(('time',), times.values, {
+    ds.coords['time'] = Variable(('time',), times.values.astype('datetime64[ns]'), {
         'window_length': window_length,
         'window_overlap': window_overlap,
         'closed': closed,
@@ -211,7 +230,7 @@ def init(
         'units': 's',
         'description': 'offset = receiver[0].starttime - time + window_length/2',
     }, encoding)
-    ds.variables['cc'] = Variable(('pair', 'time', 'lag'), np.zeros((P, W, K), dtype=dtype), {
+    ds.variables['cc'] = Variable(('pair', 'time', 'lag'), _zeros_maybe_pinned((P, W, K), dtype, pin_memory), {
         'long_name': 'Cross-correlation Estimate',
         'standard_name': 'cross-correlation_estimate',
         'units': '-',
@@ -222,4 +241,7 @@ def init(
         'bias_correct': np.byte(unbiased_cc),
         'unbiased': np.byte(0),
     }, encoding)
+    # add metadata hash (core/init.py:323)
+    from ..io.hasher import hash_dataset
+    ds.attrs['sha256_hash_metadata'] = hash_dataset(ds, metadata_only=True)
     return ds

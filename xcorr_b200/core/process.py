@@ -7,6 +7,19 @@ Batched replacement of the reference's serial ``pair x time`` loop
 transforms both receivers again for every pair and every window; here every
 (receiver, window) trace is fetched once, preprocessed on the GPU as one batch
 per channel, transformed once, and reused by all the pairs it belongs to.
+
+Windowing follows the reference's client (``stream/client.py:499-519, 996-1050``):
+a trace may start before the nominal window (the client's 5 % buffer); the op-list
+runs on the buffered trace with the window's start / end injected into ``trim``
+(``stream/process.py:86-89,153-196``); the result is trimmed to the window
+(``client.py:1017``), checked for sampling rate and strict duration (``:1020-1050``)
+and its first ``npts`` samples are correlated (``core/process.py:156-157``).
+
+Host <-> device traffic is pipelined: the raw traces of batch ``b+1`` are gathered
+into page-locked staging buffers and copied in while batch ``b`` computes, and the
+correlation functions of batch ``b`` are copied out (straight into ``dataset.cc``
+when :func:`xcorr_b200.core.init` placed it in page-locked memory) while batch
+``b+1`` runs.
 """
 import numpy as np
 import pandas as pd
@@ -14,11 +27,63 @@ import pandas as pd
 from . import init as _init  # noqa: F401
 from ..stream import process as stream_process
 
-__all__ = ['process']
+__all__ = ['process', 'compile_operations']
 
 
 def _channel(receiver):
     return receiver.split('.')[-1]
+
+
+def compile_operations(ops, channels, window_length):
+    """Validate every channel's op-list ONCE, before any window is touched
+    (``stream/process.py:29-94`` whitelist, argument checks of the compiler): a
+    configuration error raises here instead of turning every cell into "missing data".
+    Returns ``{channel: [(op, params), ...]}`` with ``trim`` completed by the window
+    (``inject_dynamic_parameters``)."""
+    out = {}
+    for chan in channels:
+        if chan not in ops:
+            raise KeyError(f"preprocess operations for channel '{chan}' are missing")
+        lst = []
+        for item in ops[chan]:
+            if not isinstance(item, (tuple, list)) or len(item) != 2:
+                raise TypeError('Provided operation should be a tuple or list with length 2 (method:str,params:dict).')
+            op, params = item
+            if not stream_process.is_operation(op):
+                raise ValueError(f'Provided operation "{op}" is invalid.')
+            if op not in stream_process.device_operations():
+                raise NotImplementedError(
+                    f'operation "{op}" acts on obspy objects / station metadata and is not part of the '
+                    'array-valued GPU path; apply it with the reference client before the hand-off')
+            if not isinstance(params, dict):
+                raise TypeError(f'parameters of operation "{op}" should be a dictionary')
+            lst.append((op, stream_process.inject_dynamic_parameters(op, params, starttime=0.0,
+                                                                     endtime=float(window_length))))
+        out[chan] = lst
+    return out
+
+
+class _Stager:
+    """Two page-locked host buffers (+ device twins) reused round-robin."""
+
+    def __init__(self, torch, dev):
+        self.torch, self.dev = torch, dev
+        self.host, self.device, self.free_ev = {}, {}, {}
+
+    def get(self, slot, key, shape, dtype, host=True, device=True):
+        torch = self.torch
+        k = (slot, key)
+        n = int(np.prod(shape))
+        h = d = None
+        if device:
+            if k not in self.device or self.device[k].numel() < n or self.device[k].dtype != dtype:
+                self.device[k] = torch.empty(n, dtype=dtype, device=self.dev)
+            d = self.device[k][:n].view(*shape)
+        if host:
+            if k not in self.host or self.host[k].numel() < n or self.host[k].dtype != dtype:
+                self.host[k] = torch.empty(n, dtype=dtype, pin_memory=True)
+            h = self.host[k][:n].view(*shape)
+        return h, d
 
 
 def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = False,
@@ -32,12 +97,14 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         Filled in place: ``cc``, ``status``, ``pair_offset``, ``time_offset``.
 
     waveforms : callable ``(receiver: str, time: pd.Timestamp) -> (data, sampling_rate, start_offset) | None``
-        Raw trace covering the window centred on `time` (length
-        ``window_length``), as a 1-D float array, with its sampling rate and the
-        offset in seconds of its first sample from the nominal window start.
-        ``None`` marks missing data -- the cell gets status -1 and its ``cc``
-        stays zero, as ``core/process.py:122-132`` does.  (The reference gets
-        this from ``client.get_pair_processed_waveforms``; I/O stays on the host.)
+        Raw trace for the window centred on `time` (length ``window_length``) as a
+        1-D float array, its sampling rate, and the offset in seconds of its first
+        sample from the nominal window start -- negative when the trace carries a
+        buffer in front of the window like the reference client's 5 %
+        (``stream/client.py:499-519``).  ``None`` marks missing data: the cell gets
+        status -1 and its ``cc`` stays zero (``core/process.py:122-132``).  (The
+        reference gets this from ``client.get_pair_processed_waveforms``; I/O stays
+        on the host.)
 
     retry_missing : `bool`
         Also process cells with status -1 (``core/process.py:93-104``).
@@ -47,6 +114,7 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
     """
     import torch
     from ..plan import CorrelationPlan
+    from ..io.hasher import hash_dataset
 
     dataset.attrs['history'] += f", Process started @ {pd.Timestamp.now()}"
     lag = dataset.coords['lag']
@@ -57,81 +125,179 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
     i0 = int(round((lag.data[0] + lag_max) * fs))
     i1 = int(round((lag.data[-1] + lag_max) * fs + 1))
     lag.attrs['index_min'], lag.attrs['index_max'] = i0, i1
+    K = i1 - i0
 
     pairs = [str(p) for p in dataset.coords['pair'].data]
     times = pd.DatetimeIndex(dataset.coords['time'].data)
-    ops = dataset.coords['pair'].attrs['preprocess']
-    window_length = dataset.coords['time'].attrs['window_length']
+    window_length = float(dataset.coords['time'].attrs['window_length'])
     cc = dataset.variables['cc']
     status = dataset.variables['status'].data
     receivers = sorted({r for p in pairs for r in p.split('-')})
     ridx = {r: k for k, r in enumerate(receivers)}
     pair_idx = [(ridx[p.split('-')[0]], ridx[p.split('-')[1]]) for p in pairs]
+    R, P = len(receivers), len(pairs)
+    # configuration errors raise before the loop (they are not "missing data")
+    ops = compile_operations(dataset.coords['pair'].attrs['preprocess'], sorted({_channel(r) for r in receivers}),
+                             window_length)
     dtype = torch.float32 if cc.data.dtype == np.float32 else torch.float64
     dev = torch.device(device or 'cuda')
     if dev.index is None:
         dev = torch.device('cuda', torch.cuda.current_device())
+    cc_t = torch.from_numpy(cc.data)
+    cc_pinned = cc_t.is_pinned() and cc_t.is_contiguous()
 
     todo = [w for w in range(len(times))
-            if any(status[q, w] == 0 or (retry_missing and status[q, w] == -1) for q in range(len(pairs)))]
+            if any(status[q, w] == 0 or (retry_missing and status[q, w] == -1) for q in range(P))]
     if test_run:
         todo = todo[:1]
-    plans = {}
-    for b0 in range(0, len(todo), windows_per_batch):
-        batch = todo[b0:b0 + windows_per_batch]
-        W = len(batch)
-        # ---- gather: every (receiver, window) once ----
-        raw, offsets = {}, np.full((len(receivers), W), np.nan)
-        for k, r in enumerate(receivers):
-            for j, w in enumerate(batch):
-                got = waveforms(r, times[w])
-                if got is None:
+    batches = [todo[b:b + windows_per_batch] for b in range(0, len(todo), windows_per_batch)]
+
+    plans, programs = {}, {}
+    with torch.cuda.device(dev):
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        stager = _Stager(torch, dev)
+        x_dev = [None, None]
+        ccf_dev = [None, None]
+        ev_run = [None, None]                 # compute of the batch that last used slot s
+        ev_out = [None, None]                 # its device -> host copy
+
+        def program_for(chan, n_raw, rate, off):
+            key = (chan, n_raw, rate, off)
+            if key not in programs:
+                try:
+                    programs[key] = stream_process.PreprocessProgram(ops[chan], n_raw, rate, trace_start=off)
+                except ValueError as error:   # the trace does not cover the window / cannot take the ops: missing data
+                    if verb > 0:
+                        print(f'{chan}: {n_raw} samples at {rate} Hz cannot be processed ({error})')
+                    programs[key] = None      # (TypeError / NotImplementedError / ArithmeticError = configuration: raise)
+            return programs[key]
+
+        def launch(slot, batch):
+            """Gather + async H2D + preprocess + correlate + async D2H of one batch."""
+            W = len(batch)
+            raw, offsets = {}, np.full((R, W), np.nan)
+            for k, r in enumerate(receivers):
+                for j, w in enumerate(batch):
+                    got = waveforms(r, times[w])
+                    if got is None:
+                        continue
+                    data, rate, off = got
+                    data = np.asarray(data)
+                    if data.dtype not in (np.float32, np.float64):
+                        data = data.astype(np.float64)            # obspy promotes integer data to float64
+                    raw[(k, j)] = (data, float(rate), float(off))
+            if x_dev[slot] is None or x_dev[slot].shape[1] != W:
+                x_dev[slot] = torch.zeros((R, W, npts), dtype=dtype, device=dev)
+                ccf_dev[slot] = torch.empty((P, W, K), dtype=dtype, device=dev)
+            x = x_dev[slot]
+            ok = np.zeros((R, W), dtype=bool)
+            groups = {}
+            for (k, j), (data, rate, off) in raw.items():
+                groups.setdefault((_channel(receivers[k]), len(data), rate, off, data.dtype), []).append((k, j))
+            if ev_run[slot] is not None:
+                s_in.wait_event(ev_run[slot])                     # x_dev[slot] and the staging twins are free again
+                ev_run[slot].synchronize()                        # ... and so are the page-locked buffers on the host
+            staged = []
+            for gi, ((chan, n_raw, rate, off, ndt), members) in enumerate(groups.items()):
+                prog = program_for(chan, n_raw, rate, off)
+                if prog is None:
                     continue
-                data, rate, off = got
-                raw[(k, j)] = (np.asarray(data), float(rate))
-                offsets[k, j] = off
-        # ---- preprocess on the GPU, one batch per (channel, length, rate) ----
-        x = torch.zeros((len(receivers), W, npts), dtype=dtype, device=dev)
-        ok = np.zeros((len(receivers), W), dtype=bool)
-        groups = {}
-        for (k, j), (data, rate) in raw.items():
-            groups.setdefault((_channel(receivers[k]), len(data), rate), []).append((k, j))
-        for (chan, n_raw, rate), members in groups.items():
-            if chan not in ops:
-                continue
-            stack = torch.from_numpy(np.stack([raw[m][0] for m in members]).astype(np.float64)).to(dev)
-            out = stream_process.process(stack, [tuple(o) for o in ops[chan]], sampling_rate=rate,
-                                         out_dtype=dtype)
-            if out is None:
-                continue
-            y, rate_out = out
-            # sampling-rate and strict duration checks of stream/client.py:1020-1050
-            if abs(rate_out - fs) > 1e-9 * fs or y.shape[1] < npts:
-                continue
-            for m, (k, j) in enumerate(members):
-                x[k, j] = y[m, :npts]               # core/process.py:156-157 slices [:npts]
-                ok[k, j] = True
-        # ---- correlate all pairs of the batch ----
-        if W not in plans:
-            plans[W] = CorrelationPlan(npts, len(receivers), pair_idx, n_windows=W, dtype=dtype,
-                                       index_min=i0, index_max=i1,
-                                       normalize=cc.attrs['normalize'] == 1,
-                                       unbiased=cc.attrs['bias_correct'] == 1, device=dev)
-        ccf = plans[W](x).cpu().numpy()
-        # ---- scatter ----
-        for q, (a, b) in enumerate(pair_idx):
-            for j, w in enumerate(batch):
-                if not (status[q, w] == 0 or (retry_missing and status[q, w] == -1)):
+                # client.py:1017: trim the processed trace to the window, then the checks of :1020-1050
+                skip, keep = stream_process.trim_samples(prog.npts_out, prog.fs_out, prog.trace_start_out,
+                                                         0.0, window_length)
+                if not np.isclose(prog.fs_out, fs, atol=0.0) or window_length * prog.fs_out - keep > 0:
                     continue
-                if not (ok[a, j] and ok[b, j]):
+                start_final = prog.trace_start_out + skip / prog.fs_out
+                tdt = torch.float32 if ndt == np.float32 else torch.float64
+                srcs = [torch.from_numpy(raw[m][0]) for m in members]
+                if all(t.is_pinned() and t.is_contiguous() for t in srcs):
+                    # the caller's I/O layer already reads into page-locked memory: DMA straight from it
+                    _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
+                    with torch.cuda.stream(s_in):
+                        for m, t in enumerate(srcs):
+                            devbuf[m].copy_(t, non_blocking=True)
+                else:
+                    host, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt)
+                    hnp = host.numpy()
+                    for m, (k, j) in enumerate(members):
+                        hnp[m] = raw[(k, j)][0]
+                    with torch.cuda.stream(s_in):
+                        devbuf.copy_(host, non_blocking=True)
+                staged.append((prog, devbuf, members, skip, start_final))
+            ev_in = torch.cuda.Event()
+            ev_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                if ev_out[slot] is not None:
+                    s_run.wait_event(ev_out[slot])                # ccf_dev[slot] drained
+                for prog, devbuf, members, skip, start_final in staged:
+                    y = prog.run(devbuf, out_dtype=dtype)
+                    ks = torch.tensor([k for k, _ in members], device=dev)
+                    js = torch.tensor([j for _, j in members], device=dev)
+                    x[ks, js] = y[:, skip:skip + npts]            # core/process.py:156-157 slices [:npts]
+                    for (k, j) in members:
+                        ok[k, j] = True
+                        offsets[k, j] = start_final
+                if W not in plans:
+                    plans[W] = CorrelationPlan(npts, R, pair_idx, n_windows=W, dtype=dtype, index_min=i0, index_max=i1,
+                                               normalize=cc.attrs['normalize'] == 1,
+                                               unbiased=cc.attrs['bias_correct'] == 1, device=dev)
+                plans[W](x, out=ccf_dev[slot])
+                ev_run[slot] = torch.cuda.Event()
+                ev_run[slot].record(s_run)
+            # cells of this batch that get a result
+            cells = []
+            for q, (a, b) in enumerate(pair_idx):
+                for j, w in enumerate(batch):
+                    if not (status[q, w] == 0 or (retry_missing and status[q, w] == -1)):
+                        continue
+                    cells.append((q, j, w, bool(ok[a, j] and ok[b, j])))
+            direct = cc_pinned and all(good for *_, good in cells) and len(cells) == P * W and \
+                batch == list(range(batch[0], batch[0] + W))
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[slot])
+                if direct:
+                    # rows of the page-locked dataset array are contiguous per pair: one DMA per pair
+                    if W == cc_t.shape[1]:
+                        cc_t.copy_(ccf_dev[slot], non_blocking=True)
+                    else:
+                        for q in range(P):
+                            cc_t[q, batch[0]:batch[0] + W].copy_(ccf_dev[slot][q], non_blocking=True)
+                    host_out = None
+                else:
+                    host_out, _ = stager.get(slot, 'out', (P, W, K), dtype, device=False)
+                    host_out.copy_(ccf_dev[slot], non_blocking=True)
+                ev_out[slot] = torch.cuda.Event()
+                ev_out[slot].record(s_out)
+            return batch, cells, offsets, host_out, ev_out[slot]
+
+        def finish(pending):
+            batch, cells, offsets, host_out, ev = pending
+            ev.synchronize()
+            out_np = host_out.numpy() if host_out is not None else None
+            for q, j, w, good in cells:
+                a, b = pair_idx[q]
+                if not good:
                     status[q, w] = -1
                     if verb > 0:
                         print(pairs[q], str(times[w])[:19], 'Missing data. Set status "-1" and skip.')
                     continue
-                cc.data[q, w] = ccf[q, j]
+                if out_np is not None:
+                    cc.data[q, w] = out_np[q, j]
                 dataset.variables['pair_offset'].data[q, w] = offsets[a, j] - offsets[b, j]
                 dataset.variables['time_offset'].data[q, w] = offsets[a, j]      # start(receiver 0) - (time - window_length/2)
                 status[q, w] = 1
+
+        pending = None
+        for b, batch in enumerate(batches):
+            nxt = launch(b % 2, batch)
+            if pending is not None:
+                finish(pending)
+            pending = nxt
+        if pending is not None:
+            finish(pending)
+        torch.cuda.synchronize(dev)
+
     dataset.attrs['history'] += f", Process ended @ {pd.Timestamp.now()}"
     if cc.attrs['bias_correct'] == 1 and cc.attrs['unbiased'] == 0:
         # fused into the inverse transform's epilogue (signal/unbias.py:85)
@@ -139,4 +305,6 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         cc.attrs['long_name'] = 'Unbiased ' + cc.attrs['long_name']
         cc.attrs['standard_name'] = 'unbiased_' + cc.attrs['standard_name']
         dataset.attrs['history'] += f", Unbiased CC @ {pd.Timestamp.now()}"
+    # update metadata hash (core/process.py:183)
+    dataset.attrs['sha256_hash_metadata'] = hash_dataset(dataset, metadata_only=True)
     return dataset

@@ -89,6 +89,21 @@ static int cuda_fail(cudaError_t e, const char* where) {
     if (e_ != cudaSuccess) return cuda_fail(e_, #call);        \
   } while (0)
 
+// Runs the enclosed launches on the plan's device whatever the caller's current device is
+// (a plan created for cuda:1 may be used while cuda:0 is current).
+namespace {
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = err == cudaSuccess; }
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+}  // namespace
+
 extern "C" const char* xcb_strerror(int status) {
   switch (status) {
     case XCB_OK: return "ok";
@@ -440,6 +455,13 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
   info->nd = pl->g.nd;
   for (int a = 0; a < kMaxDims; ++a) info->dims[a] = pl->g.dims[a];
   info->dtype = pl->dtype;
+  // staged / grouped pair product: job groups of the first launch chunk (0 = the plain row kernel runs)
+  info->n_groups = 0;
+  if (pl->d_groups && pl->group_off.size() > 1) {
+    const int64_t ng = pl->group_off[1] - pl->group_off[0];
+    const int64_t nj = std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs);
+    if (nj >= 3 * ng) info->n_groups = (int32_t)ng;
+  }
   return XCB_OK;
 }
 
@@ -492,6 +514,8 @@ static int forward_t(const xcb_plan* pl, const void* x, int64_t x_stride, void* 
 extern "C" int xcb_forward(const xcb_plan* pl, const void* x, int64_t x_stride, void* spec, double* sumsq,
                            void* workspace, void* stream) {
   if (!pl || !x || !spec || !sumsq || !workspace || x_stride < pl->g.n) return XCB_ERR_ARG;
+  DeviceGuard guard(pl->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return pl->dtype == XCB_F32 ? forward_t<float>(pl, x, x_stride, spec, sumsq, workspace, st)
                               : forward_t<double>(pl, x, x_stride, spec, sumsq, workspace, st);
@@ -533,6 +557,8 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
 extern "C" int xcb_correlate(const xcb_plan* pl, const void* spec, const double* sumsq, void* ccf, void* workspace,
                              void* stream) {
   if (!pl || !spec || !sumsq || !ccf || !workspace) return XCB_ERR_ARG;
+  DeviceGuard guard(pl->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return pl->dtype == XCB_F32 ? correlate_t<float>(pl, spec, sumsq, ccf, workspace, st)
                               : correlate_t<double>(pl, spec, sumsq, ccf, workspace, st);
@@ -863,53 +889,114 @@ extern "C" int xcb_dft_bluestein(const xcb_fft* f, int64_t K, int32_t sign, cons
 // ---------------------------------------------------------------------------
 // cc() with host buffers
 // ---------------------------------------------------------------------------
+// The reference calls cc() once per (pair, window) with the same n, dtype and flags
+// (core/process.py:155-162), so the plan (twiddle tables, job table), the device
+// buffers and a private stream are cached per (device, dtype, n, crop, flags): a call
+// is two host->device copies, the kernels and one device->host copy.  The host
+// buffers are the caller's pageable numpy arrays; the driver stages such copies through
+// its own pinned buffers in pipelined chunks, which is what a hand-made pinned staging
+// copy would do with an extra pass over the data.
+namespace {
+struct CcHostEntry {
+  int device, dtype, normalize, unbiased;
+  int64_t n, i0, i1;
+  xcb_plan* pl = nullptr;
+  unsigned char* buf = nullptr;
+  cudaStream_t st = nullptr;
+  size_t x_bytes = 0, spec_bytes = 0, ccf_bytes = 0;
+  int64_t stride = 0, n_lags = 0;
+  uint64_t last_use = 0;
+};
+constexpr int kCcHostSlots = 4;
+std::mutex g_cc_mu;                  // one cc() at a time per process: the cached buffers are shared
+CcHostEntry g_cc_cache[kCcHostSlots];
+uint64_t g_cc_clock = 0;
+
+void cc_entry_release(CcHostEntry& e) {
+  if (e.pl) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != e.device) cudaSetDevice(e.device);
+    if (e.st) cudaStreamDestroy(e.st);
+    cudaFree(e.buf);
+    xcb_plan_destroy(e.pl);
+    if (prev != e.device && prev >= 0) cudaSetDevice(prev);
+  }
+  e = CcHostEntry();
+}
+}  // namespace
+
+extern "C" int xcb_cc_host_clear_cache(void) {
+  std::lock_guard<std::mutex> lock(g_cc_mu);
+  for (auto& e : g_cc_cache) cc_entry_release(e);
+  return XCB_OK;
+}
+
 extern "C" int xcb_cc_host(int32_t dtype, int64_t n, const void* x, const void* y, int32_t normalize,
                            int32_t unbiased, int64_t i0, int64_t i1, void* out) {
   if (!x || !y || !out || n < 1) return XCB_ERR_ARG;
   if (dtype != XCB_F32 && dtype != XCB_F64) return XCB_ERR_ARG;
   const size_t b = dtype == XCB_F32 ? 4 : 8;
-  int32_t pr[2] = {0, 1};
-  xcb_desc d;
-  memset(&d, 0, sizeof(d));
-  d.n = n;
-  d.dtype = dtype;
-  d.n_receivers = 2;
-  d.n_windows = 1;
-  d.n_pairs = 1;
-  d.pairs = pr;
-  d.normalize = normalize;
-  d.unbiased = unbiased;
-  d.lag_index_min = i0;
-  d.lag_index_max = i1;
-  xcb_plan* pl = nullptr;
-  int rc = xcb_plan_create(&pl, &d);
-  if (rc) return rc;
-  xcb_plan_info info;
-  xcb_plan_get_info(pl, &info);
-  const int64_t stride = (n + 1) / 2 * 2;     // even stride keeps both signals vector-aligned
-  unsigned char* buf = nullptr;
-  const size_t x_bytes = align_up((size_t)2 * stride * b, 256);
-  const size_t spec_bytes = align_up((size_t)2 * info.spectrum_elems * 2 * b, 256);
-  const size_t ccf_bytes = align_up((size_t)info.n_lags * b, 256);
-  const size_t total = x_bytes + spec_bytes + 256 + ccf_bytes + info.workspace_bytes;
-  cudaError_t e = cudaMalloc(&buf, total);
-  if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "cudaMalloc(cc_host)"); }
-  unsigned char* dx = buf;
-  unsigned char* dspec = dx + x_bytes;
-  double* dss = reinterpret_cast<double*>(dspec + spec_bytes);
-  unsigned char* dccf = dspec + spec_bytes + 256;
-  unsigned char* dws = dccf + ccf_bytes;
-  rc = XCB_OK;
+  int device = 0;
+  XCB_CUDA(cudaGetDevice(&device));
+  std::lock_guard<std::mutex> lock(g_cc_mu);
+  CcHostEntry* e = nullptr;
+  for (auto& c : g_cc_cache)
+    if (c.pl && c.device == device && c.dtype == dtype && c.n == n && c.i0 == i0 && c.i1 == i1 &&
+        c.normalize == (normalize != 0) && c.unbiased == (unbiased != 0)) { e = &c; break; }
+  if (!e) {
+    CcHostEntry* victim = &g_cc_cache[0];                 // an empty slot, else the least recently used
+    for (auto& c : g_cc_cache) {
+      if (!c.pl) { victim = &c; break; }
+      if (c.last_use < victim->last_use) victim = &c;
+    }
+    cc_entry_release(*victim);
+    e = victim;
+    int32_t pr[2] = {0, 1};
+    xcb_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n = n;
+    d.dtype = dtype;
+    d.n_receivers = 2;
+    d.n_windows = 1;
+    d.n_pairs = 1;
+    d.pairs = pr;
+    d.normalize = normalize;
+    d.unbiased = unbiased;
+    d.lag_index_min = i0;
+    d.lag_index_max = i1;
+    int rc = xcb_plan_create(&e->pl, &d);
+    if (rc) { *e = CcHostEntry(); return rc; }
+    xcb_plan_info info;
+    xcb_plan_get_info(e->pl, &info);
+    e->device = device; e->dtype = dtype; e->n = n; e->i0 = i0; e->i1 = i1;
+    e->normalize = normalize != 0; e->unbiased = unbiased != 0;
+    e->stride = (n + 1) / 2 * 2;             // even stride keeps both signals vector-aligned
+    e->n_lags = info.n_lags;
+    e->x_bytes = align_up((size_t)2 * e->stride * b, 256);
+    e->spec_bytes = align_up((size_t)2 * info.spectrum_elems * 2 * b, 256);
+    e->ccf_bytes = align_up((size_t)info.n_lags * b, 256);
+    cudaError_t ce = cudaMalloc(&e->buf, e->x_bytes + e->spec_bytes + 256 + e->ccf_bytes + info.workspace_bytes);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { cc_entry_release(*e); return cuda_fail(ce, "cudaMalloc(cc_host)"); }
+  }
+  e->last_use = ++g_cc_clock;
+  unsigned char* dx = e->buf;
+  unsigned char* dspec = dx + e->x_bytes;
+  double* dss = reinterpret_cast<double*>(dspec + e->spec_bytes);
+  unsigned char* dccf = dspec + e->spec_bytes + 256;
+  unsigned char* dws = dccf + e->ccf_bytes;
+  int rc = XCB_OK;
+  cudaError_t ce = cudaSuccess;
   do {
-    if ((e = cudaMemcpy(dx, x, n * b, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-    if ((e = cudaMemcpy(dx + stride * b, y, n * b, cudaMemcpyHostToDevice)) != cudaSuccess) break;
-    if ((rc = xcb_forward(pl, dx, stride, dspec, dss, dws, nullptr)) != XCB_OK) break;
-    if ((rc = xcb_correlate(pl, dspec, dss, dccf, dws, nullptr)) != XCB_OK) break;
-    if ((e = cudaMemcpy(out, dccf, (size_t)info.n_lags * b, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    if ((ce = cudaMemcpyAsync(dx, x, n * b, cudaMemcpyHostToDevice, e->st)) != cudaSuccess) break;
+    if ((ce = cudaMemcpyAsync(dx + e->stride * b, y, n * b, cudaMemcpyHostToDevice, e->st)) != cudaSuccess) break;
+    if ((rc = xcb_forward(e->pl, dx, e->stride, dspec, dss, dws, e->st)) != XCB_OK) break;
+    if ((rc = xcb_correlate(e->pl, dspec, dss, dccf, dws, e->st)) != XCB_OK) break;
+    if ((ce = cudaMemcpyAsync(out, dccf, (size_t)e->n_lags * b, cudaMemcpyDeviceToHost, e->st)) != cudaSuccess) break;
+    ce = cudaStreamSynchronize(e->st);
   } while (0);
-  cudaFree(buf);
-  xcb_plan_destroy(pl);
   if (rc) return rc;
-  if (e != cudaSuccess) return cuda_fail(e, "xcb_cc_host");
+  if (ce != cudaSuccess) return cuda_fail(ce, "xcb_cc_host");
   return XCB_OK;
 }

@@ -91,13 +91,20 @@ xcb_row_pass(const __grid_constant__ PassParams<T> p) {
   }
 }
 
-static int resident_ctas(const void* kernel, int threads, int smem) {
+// CTAs of `kernel` that stay resident on the CURRENT device; cached per (device, slot) by the callers
+// (slots of one template instantiation; a box may hold different GPUs).
+constexpr int kMaxDev = 64;
+static int resident_ctas(const void* kernel, int threads, int smem, int* cache) {
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
+  int* slot = (dev >= 0 && dev < kMaxDev) ? cache + dev : nullptr;
+  if (slot && *slot) return *slot;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  return per_sm * (sms > 0 ? sms : 148);
+  const int r = per_sm * (sms > 0 ? sms : 148);
+  if (slot) *slot = r;
+  return r;
 }
 
 // TMA path: the pass input viewed as [batch][rows][128-byte column tiles] with
@@ -165,12 +172,12 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
       // the first forward pass (real input, norms) and the last inverse pass (lag epilogue) have their own
       // kernels; the middle passes share the run-time-moded one (measured: specialising them is slower)
       const int role = p.load_mode == CL_REAL ? COL_FWD_REAL : p.store_mode == CS_EPI ? COL_INV_EPI : COL_ANY;
-      static int resident[5] = {0, 0, 0, 0, 0};   // persistent grid: as many CTAs as stay resident
+      static int resident[5][kMaxDev];            // persistent grid: as many CTAs as stay resident (per device)
       const void* fn = role == COL_FWD_REAL ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL>
                        : role == COL_INV_EPI ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_INV_EPI>
                                              : (const void*)xcb_col_pass_tma<T, R1, R2, COL_ANY>;
-      if (!resident[role]) resident[role] = resident_ctas(fn, K::THREADS, K::SMEM);
-      const int64_t grid = nblocks < resident[role] ? nblocks : resident[role];
+      const int res = resident_ctas(fn, K::THREADS, K::SMEM, resident[role]);
+      const int64_t grid = nblocks < res ? nblocks : res;
       if (role == COL_FWD_REAL)
         xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       else if (role == COL_INV_EPI)
@@ -196,8 +203,8 @@ template <class T, int R1, int R2> int launch_row(const void* params, int64_t nb
     if (K::kOk && staged && p.load_mode == RL_PROLOGUE && p.n_groups > 0 && p.work_counter &&
         p.n_batch >= 3 * p.n_groups && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0 &&
         p.n_pairs_rows * (int64_t)p.n_groups < 2147483647LL) {
-      static int resident = 0;   // persistent grid
-      if (!resident) resident = resident_ctas((const void*)xcb_pair_product_grouped<T, R1, R2>, K::THREADS, K::SMEM);
+      static int resident_dev[kMaxDev];   // persistent grid (per device)
+      const int resident = resident_ctas((const void*)xcb_pair_product_grouped<T, R1, R2>, K::THREADS, K::SMEM, resident_dev);
       const int64_t items = p.n_pairs_rows * (int64_t)p.n_groups;
       const int64_t grid = items < resident ? items : resident;
       cudaError_t ce = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);

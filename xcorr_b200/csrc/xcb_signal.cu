@@ -217,13 +217,14 @@ __global__ void __launch_bounds__(256) k_running_rms(const T* __restrict__ x, in
 }
 
 // obspy Trace.normalize(norm=None): x /= max |x| of the trace (stats[s][0] from k_window_stats); norm given: x /= |norm|
-template <class T>
+// L2: x /= sqrt(stats[s][2]) (sum of squares of the row, fixed-order reduction of k_window_stats) = np.linalg.norm
+template <class T, bool L2 = false>
 __global__ void k_normalize_rows(T* __restrict__ x, int64_t stride, int64_t n, const double* __restrict__ stats,
                                  double norm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t s = blockIdx.y;
-  const double d = stats ? stats[s * 3] : fabs(norm);
+  const double d = L2 ? sqrt(stats[s * 3 + 2]) : (stats ? stats[s * 3] : fabs(norm));
   x[s * stride + i] = (T)((double)x[s * stride + i] / d);
 }
 
@@ -335,6 +336,19 @@ extern "C" int xcb_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_
   dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_signals);
   if (dtype == XCB_F32) k_normalize_rows<float><<<grid, 256, 0, st>>>(static_cast<float*>(x), stride, n, window_stats, norm);
   else if (dtype == XCB_F64) k_normalize_rows<double><<<grid, 256, 0, st>>>(static_cast<double*>(x), stride, n, window_stats, norm);
+  else return XCB_ERR_ARG;
+  return fail(cudaGetLastError());
+}
+
+// signal/normalize.py:33-155 (norm1d / norm2d): every row divided by its 2-norm, sqrt of the row's sum of
+// squares in window_stats[s][2] (xcb_window_stats with the noise window [0, n)).
+extern "C" int xcb_l2_normalize_rows(int32_t dtype, void* x, int64_t stride, int64_t n, int32_t n_signals,
+                                     const double* window_stats, void* stream) {
+  if (!x || !window_stats || n < 1 || n_signals < 1) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_signals);
+  if (dtype == XCB_F32) k_normalize_rows<float, true><<<grid, 256, 0, st>>>(static_cast<float*>(x), stride, n, window_stats, 0.0);
+  else if (dtype == XCB_F64) k_normalize_rows<double, true><<<grid, 256, 0, st>>>(static_cast<double*>(x), stride, n, window_stats, 0.0);
   else return XCB_ERR_ARG;
   return fail(cudaGetLastError());
 }

@@ -15,6 +15,10 @@ __all__ = ['to_json', 'hash_variable', 'hash_dataset']
 
 _enc = 'utf-8'
 
+# util/hasher.py:22-35: attributes that never enter a hash -- the hashes themselves (else the data hash
+# would depend on the previous one) and the packing attributes xarray moves into `encoding` on read
+_ignore_keys = ('sha256_hash', 'sha256_hash_metadata', 'add_offset', 'scale_factor')
+
 
 def _to_serializable(obj):
     if isinstance(obj, (np.int8, np.int16, np.int32, np.int64)):
@@ -25,7 +29,9 @@ def _to_serializable(obj):
 
 
 def to_json(obj):
-    """``util/hasher.py:38-48``."""
+    """``util/hasher.py:30-48``: JSON of a dictionary without the ``_ignore_keys``."""
+    if isinstance(obj, dict):
+        obj = {k: v for k, v in obj.items() if k not in _ignore_keys}
     return json.dumps(obj, separators=(',', ':'), sort_keys=True, indent=4, skipkeys=False, default=_to_serializable)
 
 

@@ -48,6 +48,8 @@ def _attr_value(v):
         return np.int8(v)
     if isinstance(v, (int, np.integer)):
         return np.int32(v) if -2**31 <= int(v) < 2**31 else np.float64(v)
+    if isinstance(v, float):
+        return np.float64(v)                 # scipy's writer would store a Python float as NC_FLOAT (32 bit)
     if isinstance(v, (list, tuple)):
         return np.asarray(v)
     if v is None:
@@ -83,6 +85,9 @@ def _write_netcdf3(ds, path):
                 attrs.setdefault('calendar', 'proleptic_gregorian')
             else:
                 if data.dtype == np.int64:
+                    if data.size and (data.min() < -2**31 or data.max() >= 2**31):
+                        raise OverflowError(f'variable {name!r}: int64 values do not fit NetCDF-3 (no 64-bit integers); '
+                                            'write through xarray + netCDF4 instead')
                     data = data.astype(np.int32)
                 code = {'float32': 'f', 'float64': 'd', 'int8': 'b', 'int16': 'h', 'int32': 'i'}[data.dtype.name]
                 v = f.createVariable(name, code, tuple(var.dims))
@@ -125,15 +130,33 @@ def write(data: CCDataset, path: str, force_write: bool = False, hash_data: bool
     return os.path.join(abspath, file)
 
 
-def read(path: str):
-    """Read a file written by :func:`write` with the NetCDF-3 fallback back into a :class:`CCDataset`."""
+def _attr_back(v):
+    """Inverse of :func:`_attr_value` as far as NetCDF-3 keeps the information: text, native-endian
+    arrays, scalars as numpy scalars (JSON-serialised like the Python numbers they were)."""
+    if isinstance(v, bytes):
+        v = v.decode()
+    if isinstance(v, str):
+        return None if v == 'None' else v
+    a = np.asarray(v)
+    if a.dtype.kind in 'fiu' and not a.dtype.isnative:
+        a = a.astype(a.dtype.newbyteorder('='))
+    if a.ndim == 0 or a.size == 1 and not isinstance(v, np.ndarray):
+        return a.reshape(-1)[0]
+    return a
+
+
+def read(path: str, fast: bool = False):
+    """Read a file written by :func:`write` with the NetCDF-3 fallback back into a :class:`CCDataset`
+    (``io/read.py:32-205``): the ``preprocess`` attribute becomes the operations dictionary again and its
+    hash is verified, the stored ``sha256_hash`` is checked against the data (unless `fast`) and removed."""
     from scipy.io import netcdf_file
+    from ..stream.process import operations_to_dict, check_operations_hash
     ds = CCDataset()
     with netcdf_file(path, 'r', mmap=False) as f:
         for k, v in f._attributes.items():
-            ds.attrs[k] = v.decode() if isinstance(v, bytes) else v
+            ds.attrs[k] = _attr_back(v)
         for name, var in f.variables.items():
-            attrs = {k: (a.decode() if isinstance(a, bytes) else a) for k, a in var._attributes.items()}
+            attrs = {k: _attr_back(a) for k, a in var._attributes.items()}
             data = var.data.copy()
             if data.dtype.kind in 'fiu' and not data.dtype.isnative:
                 data = data.astype(data.dtype.newbyteorder('='))     # NetCDF-3 is big-endian on disk
@@ -147,4 +170,15 @@ def read(path: str):
                 attrs.pop('units'), attrs.pop('calendar', None)
             target = ds.coords if (len(dims) == 1 and dims[0] == name) else ds.variables
             target[name] = Variable(dims, data, attrs)
+    if 'pair' in ds.coords and isinstance(ds.coords['pair'].attrs.get('preprocess'), str):
+        ops = operations_to_dict(ds.coords['pair'].attrs['preprocess'])
+        check_operations_hash(ops, raise_error=True)
+        ds.coords['pair'].attrs['preprocess'] = ops
+    stored = ds.attrs.pop('sha256_hash', None)          # io/read.py:184-185
+    if stored is not None and not fast:
+        if hash_dataset(ds, metadata_only=False) != stored:
+            raise ValueError(f'{path}: sha256 data hash does not match the stored sha256_hash')
+    if ds.attrs.get('sha256_hash_metadata') is not None:
+        if hash_dataset(ds, metadata_only=True) != ds.attrs['sha256_hash_metadata']:
+            warnings.warn('Dataset metadata sha256 hash is inconsistent.', UserWarning)
     return ds

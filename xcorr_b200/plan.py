@@ -108,6 +108,7 @@ class CorrelationPlan:
         self.jobs_in_flight = int(info.jobs_in_flight)
         self.dims = tuple(int(info.dims[a]) for a in range(info.nd))
         self.n_blocks, self.block_len = int(info.n_blocks), int(info.block_len)
+        self.n_groups = int(info.n_groups)
         self.n_receivers, self.n_windows = int(n_receivers), int(n_windows)
         self.stack = bool(stack)
         self.index_min = int(index_min)

@@ -16,8 +16,11 @@ Operations with array semantics run on the device through the C ABI
 ``filter``    ``type`` in bandpass / highpass / lowpass / lowpass_cheby_2,
               ``corners=4``, ``zerophase=False`` -- causal ``sosfilt`` like obspy
 ``decimate``  ``factor`` (<= 16), ``no_filter`` -- Chebyshev-II low-pass + ``[::factor]``
-``trim``      sample-based: ``start``, ``length`` (the time-based trim of the
-              reference is resolved to samples by the caller)
+``trim``      time-based like obspy ``Trace.trim(starttime, endtime)`` (nearest sample, no
+              padding) with ``starttime`` / ``endtime`` INJECTED by :func:`process` as the reference
+              does (``stream/process.py:86-89,153-196``); times are seconds on the axis on which
+              the first sample of the input sits at ``trace_start``.  Also sample-based:
+              ``start``, ``length``
 ``running_rms``  ``window`` seconds (``stream/running_rms.py``): rms of consecutive windows
 ``normalize``  obspy ``Trace.normalize``: divide by max |x| (or by ``norm``)
 ============  ===============================================================
@@ -48,7 +51,7 @@ import numpy as np
 
 from .. import _lib
 
-__all__ = ['process', 'list_operations', 'is_operation', 'device_operations',
+__all__ = ['process', 'inject_dynamic_parameters', 'trim_samples', 'list_operations', 'is_operation', 'device_operations',
            'hash_operations', 'check_operations_hash', 'operations_to_dict',
            'operations_to_json', 'PreprocessProgram']
 
@@ -253,15 +256,47 @@ class _Stage:
         return self.detrend != 0 or self.taper is not None
 
 
+def _round_away(v):
+    """Round half away from zero (obspy.core.compatibility.round_away)."""
+    return int(np.floor(abs(v) + 0.5) * (1 if v >= 0 else -1))
+
+
+def trim_samples(npts, fs, trace_start, starttime=None, endtime=None):
+    """obspy ``Trace.trim(starttime, endtime)`` with its defaults (``pad=False``,
+    ``nearest_sample=True``) resolved to ``(first sample, number of samples)``:
+    ``_ltrim`` drops ``round((starttime - trace_start) * fs)`` samples when that is positive,
+    ``_rtrim`` then keeps the samples up to ``round((endtime - new_start) * fs)`` inclusive when
+    that is inside the trace.  Times in seconds on one axis."""
+    start = 0
+    if starttime is not None:
+        d = _round_away((float(starttime) - trace_start) * fs)
+        if d > 0:
+            start = d
+    n = npts - start
+    if n < 1:
+        raise ValueError('trim: no samples left (starttime after the end of the trace)')
+    if endtime is not None:
+        new_start = trace_start + start / fs
+        d = _round_away((float(endtime) - new_start) * fs) - n + 1
+        if d < 0:
+            n += d
+        if n < 1:
+            raise ValueError('trim: no samples left (endtime before the start of the trace)')
+    return start, n
+
+
 class PreprocessProgram:
     """An op-list compiled into fused device stages for traces of a given
-    length and sampling rate."""
+    length and sampling rate.  `trace_start` is the time in seconds of the first input
+    sample on the axis the time-based ``trim`` parameters refer to; ``trace_start_out``
+    is the time of the first output sample."""
 
-    def __init__(self, operations, npts, sampling_rate):
+    def __init__(self, operations, npts, sampling_rate, trace_start=0.0):
         self.npts_in = int(npts)
         self.fs_in = float(sampling_rate)
         self.steps = []            # ('stage', _Stage) | ('trim', start, length) | ('resample', ...) | ('interpolate', ...)
         n, fs = self.npts_in, self.fs_in
+        t0 = float(trace_start)
         cur = None
 
         def flush():
@@ -371,7 +406,7 @@ class PreprocessProgram:
                 old_dt, new_dt = 1.0 / fs, 1.0 / new_fs
                 # the shifted trace [time_shift, time_shift + (n-1) dt] is sampled from `start` (default: its own start)
                 start_rel = start
-                del time_shift                      # a pure relabelling of the time axis for array input
+                t0 += time_shift + start_rel        # obspy: stats.starttime += time_shift; new start = that (+ offset)
                 if start_rel < 0 or start_rel > (n - 1) * old_dt:
                     raise ValueError("Can only interpolate between the start and end time of the trace.")
                 if npts_new is None:
@@ -404,15 +439,23 @@ class PreprocessProgram:
                 n, fs = n_win, 1.0 / window
             elif op == 'trim':
                 flush()
-                start = int(params.get('start', 0))
-                length = params.get('length')
-                length = n - start if length is None else int(length)
+                if 'start' in params or 'length' in params:
+                    start = int(params.get('start', 0))
+                    length = params.get('length')
+                    length = n - start if length is None else int(length)
+                else:
+                    extra = set(params) - {'starttime', 'endtime'}
+                    if extra:
+                        raise TypeError(f"trim: unsupported arguments {sorted(extra)}")
+                    start, length = trim_samples(n, fs, t0, params.get('starttime'), params.get('endtime'))
                 if start < 0 or length < 1 or start + length > n:
                     raise ValueError('trim outside the trace')
                 self.steps.append(('trim', start, length))
+                t0 += start / fs
                 n = length
         flush()
         self.npts_out, self.fs_out = n, fs
+        self.trace_start_out = t0
         # resolve lengths per stage
         n, fs = self.npts_in, self.fs_in
         for st in self.steps:
@@ -590,6 +633,23 @@ class PreprocessProgram:
         return cur
 
 
+# operations whose parameters are completed at run time (stream/process.py:29-94, key 'inject')
+_inject = {'trim': ('starttime', 'endtime')}
+
+
+def inject_dynamic_parameters(operation, parameters, inventory=None, starttime=None, endtime=None, verb=0):
+    """``stream/process.py:153-196``: the window's start / end time are added to the static
+    parameters of the operations that need them (``trim``).  Times are seconds on the axis of
+    `trace_start` (array input carries no UTC).  A ``trim`` given in samples is left alone."""
+    params = dict(parameters)
+    if operation in _inject and 'start' not in params and 'length' not in params:
+        if 'starttime' in _inject[operation] and starttime is not None:
+            params['starttime'] = float(starttime)
+        if 'endtime' in _inject[operation] and endtime is not None:
+            params['endtime'] = float(endtime)
+    return params
+
+
 def process(waveforms, operations: list, sampling_rate: float = None, inventory=None,
             starttime=None, endtime=None, raise_error: bool = False, verb: int = 0, **kwargs):
     r"""Process a batch of traces given a list of operations.
@@ -605,6 +665,11 @@ def process(waveforms, operations: list, sampling_rate: float = None, inventory=
         ``[('operation', {parameters}), ...]``.
     sampling_rate : `float`
         Sampling rate of `waveforms` in Hz (obspy keeps it in ``Trace.stats``).
+    starttime, endtime : `float`, optional
+        Window start / end in seconds, injected into ``trim`` (the reference injects UTC times,
+        ``stream/process.py:86-89``); `trace_start` (keyword, default 0) is the time of the
+        first sample of `waveforms` on the same axis, e.g. ``-0.05 * duration`` for the
+        client's 5 % buffer (``stream/client.py:499-519``).
 
     Returns
     -------
@@ -614,6 +679,7 @@ def process(waveforms, operations: list, sampling_rate: float = None, inventory=
         raise TypeError('``sampling_rate`` is required for array input')
     if not isinstance(raise_error, bool):
         raise TypeError('``raise_error`` is not of type `bool`')
+    trace_start = float(kwargs.pop('trace_start', 0.0))
     ops = []
     for operation_params in operations:
         if not isinstance(operation_params, (tuple, list)) or len(operation_params) != 2:
@@ -629,9 +695,10 @@ def process(waveforms, operations: list, sampling_rate: float = None, inventory=
                 raise ValueError(msg)
             warnings.warn(msg, UserWarning)
             continue
-        ops.append((operation, parameters))
+        ops.append((operation, inject_dynamic_parameters(operation, parameters, starttime=starttime,
+                                                         endtime=endtime)))
     try:
-        prog = PreprocessProgram(ops, waveforms.shape[-1], sampling_rate)
+        prog = PreprocessProgram(ops, waveforms.shape[-1], sampling_rate, trace_start)
         if verb > 0:
             print('Apply processing operations:', [o for o, _ in ops])
         return prog.run(waveforms, **kwargs), prog.fs_out
