@@ -119,6 +119,22 @@ XCB_API int xcb_forward(const xcb_plan* plan, const void* x, int64_t x_stride, v
 XCB_API int xcb_correlate(const xcb_plan* plan, const void* spec, const double* sumsq, void* ccf,
                   void* workspace, void* stream);
 
+/* Like xcb_correlate, for callers that keep only the maximum of every correlation function: the kept lags
+ * [lag_index_min, lag_index_max) are reduced inside the last inverse pass and never stored.  Replaces
+ * `cc2.argmax()` + the value look-up of scripts/timelapse.py:255-268 (and util/cc.py:144-206 for 1-D).
+ *   mask   NULL, or the 2-D validity of a row-embedded image correlation (signal/correlate.py:228-244 run on
+ *          1-D kernels): lag = dF * row_width + dT is kept iff |dT| < half_width and |dF| < n_rows
+ *   index  device int64[n_jobs]: first maximal index within the kept lags (np.argmax: a NaN wins), job = w*n_pairs + p
+ *   value  device dtype[n_jobs] or NULL
+ * Plans with at least two passes, no stacking. */
+typedef struct xcb_lag_mask {
+  int64_t row_width;   /* W: samples per embedded image row (>= 2*half_width - 1) */
+  int64_t half_width;  /* T: image columns */
+  int64_t n_rows;      /* F: image rows; n = F * W */
+} xcb_lag_mask;
+XCB_API int xcb_correlate_argmax(const xcb_plan* plan, const void* spec, const double* sumsq, const xcb_lag_mask* mask,
+                                 int64_t* index, void* value, void* workspace, void* stream);
+
 /* First index of the maximum of each row (np.argmax semantics, util/cc.py:144-206).
  *   rows   device, dtype[n_rows][row_len];  index device int64[n_rows];  value device dtype[n_rows] or NULL */
 XCB_API int xcb_argmax(int32_t dtype, const void* rows, int64_t n_rows, int64_t row_len, int64_t* index,

@@ -62,6 +62,10 @@ class xcb_plan_info(ctypes.Structure):
     ]
 
 
+class xcb_lag_mask(ctypes.Structure):
+    _fields_ = [("row_width", ctypes.c_int64), ("half_width", ctypes.c_int64), ("n_rows", ctypes.c_int64)]
+
+
 class xcb_pointwise(ctypes.Structure):
     _fields_ = [
         ("detrend", ctypes.c_int32),
@@ -99,6 +103,7 @@ SYMBOLS = {
     "xcb_plan_get_info": (ctypes.c_int, [_vp, ctypes.POINTER(xcb_plan_info)]),
     "xcb_forward": (ctypes.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "xcb_correlate": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "xcb_correlate_argmax": (ctypes.c_int, [_vp, _vp, _vp, ctypes.POINTER(xcb_lag_mask), _vp, _vp, _vp, _vp]),
     "xcb_argmax": (ctypes.c_int, [_i32, _vp, _i64, _i64, _vp, _vp, _vp]),
     "xcb_stats_workspace_bytes": (ctypes.c_int, [_i64, _i32, ctypes.POINTER(ctypes.c_size_t)]),
     "xcb_stats": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _vp, _vp]),

@@ -554,6 +554,68 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
   return XCB_OK;
 }
 
+// Fused variant for callers that keep only the maximum of every correlation function
+// (scripts/timelapse.py:255-268): the last inverse pass reduces its tile instead of storing it.
+template <class T>
+static int correlate_argmax_t(const xcb_plan* pl, const void* spec, const double* sumsq, const xcb_lag_mask* mask,
+                              int64_t* index, void* value, void* ws, cudaStream_t st) {
+  DevTables<T> tb = dev_tables<T>(pl);
+  const PlanGeom& g = pl->g;
+  if (g.nd < 2 || pl->desc.stack) return XCB_ERR_UNSUPPORTED;
+  double* rnorm = reinterpret_cast<double*>(static_cast<unsigned char*>(ws) + pl->partial_bytes);
+  cx<T>* work = reinterpret_cast<cx<T>*>(static_cast<unsigned char*>(ws) + pl->partial_bytes + pl->rnorm_bytes);
+  xcb_rnorm<<<(unsigned)((pl->n_signals + 255) / 256), 256, 0, st>>>(sumsq, pl->n_signals, rnorm);
+  XCB_CUDA(cudaGetLastError());
+  const int C = tile_cols<T>();
+  const int64_t tiles = (g.M / g.S[0]) * ((g.S[1] + C - 1) / C);          // tiles per job of the last inverse pass
+  const int64_t fl = std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs);
+  T* pval = nullptr;
+  int64_t* pidx = nullptr;
+  XCB_CUDA(cudaMallocAsync(&pval, sizeof(T) * fl * tiles, st));
+  XCB_CUDA(cudaMallocAsync(&pidx, sizeof(int64_t) * fl * tiles, st));
+  CorrFlags f;
+  f.i0 = pl->i0;
+  f.i1 = pl->i1;
+  f.normalize = pl->desc.normalize;
+  f.unbiased = pl->desc.unbiased;
+  f.amax_val = pval;
+  f.amax_idx = pidx;
+  if (mask) { f.mask_w = (int32_t)mask->row_width; f.mask_t = (int32_t)mask->half_width; f.mask_f = (int32_t)mask->n_rows; }
+  DeviceRunner<T> run{pl, st};
+  run.counter = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ws) + pl->partial_bytes +
+                                                      pl->rnorm_bytes - 256);
+  int rc = XCB_OK;
+  for (int64_t j0 = 0; j0 < pl->n_jobs && rc == XCB_OK; j0 += pl->jobs_in_flight) {
+    const int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
+    run.chunk = j0 / pl->jobs_in_flight;
+    if (!run_inverse<T>(g, tb, static_cast<const cx<T>*>(spec), rnorm, pl->d_jobs + j0, nj, work, (T*)nullptr, f, run)) {
+      rc = run.err < 0 || run.err == (int)cudaErrorNotSupported ? XCB_ERR_UNSUPPORTED
+                                                                : cuda_fail((cudaError_t)run.err, "inverse pass launch");
+      break;
+    }
+    xcb_argmax_final_rows<T><<<(unsigned)nj, 32, 0, st>>>(pval, pidx, (int)tiles, nj, index + j0,
+                                                          value ? static_cast<T*>(value) + j0 : nullptr);
+    if (cudaGetLastError() != cudaSuccess) rc = XCB_ERR_CUDA;
+  }
+  cudaFreeAsync(pval, st);
+  cudaFreeAsync(pidx, st);
+  return rc;
+}
+
+extern "C" int xcb_correlate_argmax(const xcb_plan* pl, const void* spec, const double* sumsq, const xcb_lag_mask* mask,
+                                    int64_t* index, void* value, void* workspace, void* stream) {
+  if (!pl || !spec || !sumsq || !index || !workspace) return XCB_ERR_ARG;
+  if (mask && (mask->row_width < 1 || mask->half_width < 1 || mask->n_rows < 1 ||
+               2 * mask->half_width - 1 > mask->row_width || mask->row_width * mask->n_rows > pl->g.n ||
+               mask->row_width * (2 * mask->n_rows) >= 2147483647LL))
+    return XCB_ERR_ARG;
+  DeviceGuard guard(pl->device);
+  if (guard.err != cudaSuccess) return cuda_fail(guard.err, "cudaSetDevice");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return pl->dtype == XCB_F32 ? correlate_argmax_t<float>(pl, spec, sumsq, mask, index, value, workspace, st)
+                              : correlate_argmax_t<double>(pl, spec, sumsq, mask, index, value, workspace, st);
+}
+
 extern "C" int xcb_correlate(const xcb_plan* pl, const void* spec, const double* sumsq, void* ccf, void* workspace,
                              void* stream) {
   if (!pl || !spec || !sumsq || !ccf || !workspace) return XCB_ERR_ARG;

@@ -171,10 +171,12 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
     if (rc == 0) {
       // the first forward pass (real input, norms) and the last inverse pass (lag epilogue) have their own
       // kernels; the middle passes share the run-time-moded one (measured: specialising them is slower)
-      const int role = p.load_mode == CL_REAL ? COL_FWD_REAL : p.store_mode == CS_EPI ? COL_INV_EPI : COL_ANY;
-      static int resident[5][kMaxDev];            // persistent grid: as many CTAs as stay resident (per device)
+      const int role = p.load_mode == CL_REAL ? COL_FWD_REAL : p.store_mode == CS_EPI ? COL_INV_EPI
+                       : p.store_mode == CS_AMAX ? COL_INV_AMAX : COL_ANY;
+      static int resident[6][kMaxDev];            // persistent grid: as many CTAs as stay resident (per device)
       const void* fn = role == COL_FWD_REAL ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL>
                        : role == COL_INV_EPI ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_INV_EPI>
+                       : role == COL_INV_AMAX ? (const void*)xcb_col_pass_tma<T, R1, R2, COL_INV_AMAX>
                                              : (const void*)xcb_col_pass_tma<T, R1, R2, COL_ANY>;
       const int res = resident_ctas(fn, K::THREADS, K::SMEM, resident[role]);
       const int64_t grid = nblocks < res ? nblocks : res;
@@ -182,11 +184,14 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
         xcb_col_pass_tma<T, R1, R2, COL_FWD_REAL><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       else if (role == COL_INV_EPI)
         xcb_col_pass_tma<T, R1, R2, COL_INV_EPI><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
+      else if (role == COL_INV_AMAX)
+        xcb_col_pass_tma<T, R1, R2, COL_INV_AMAX><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       else
         xcb_col_pass_tma<T, R1, R2, COL_ANY><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(map, map_tail, tg.split_col, p);
       return (int)cudaGetLastError();
     }
   }
+  if (p.store_mode == CS_AMAX) return (int)cudaErrorNotSupported;   // the fused arg-max lives in the TMA kernel only
   xcb_col_pass<T, R1, R2><<<(unsigned)nblocks, G::THREADS, G::COL_SMEM, s>>>(p);
   return (int)cudaGetLastError();
 }
@@ -232,6 +237,8 @@ template <class T, int R1, int R2> int prepare() {
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_INV_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_INV_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
   if (e != cudaSuccess) return (int)e;
   if constexpr (R1 == 16)
     e = cudaFuncSetAttribute(xcb_pair_product_grouped<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,

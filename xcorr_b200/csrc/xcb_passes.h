@@ -27,7 +27,7 @@
 namespace xcb {
 
 enum ColLoad : int32_t { CL_REAL = 0, CL_CPLX = 1, CL_CPLX_INV = 2 };
-enum ColStore : int32_t { CS_TW = 0, CS_CONJ = 1, CS_EPI = 2 };
+enum ColStore : int32_t { CS_TW = 0, CS_CONJ = 1, CS_EPI = 2, CS_AMAX = 3 };
 enum RowLoad : int32_t { RL_CPLX = 0, RL_REAL = 1, RL_PROLOGUE = 2 };
 enum RowStore : int32_t { RS_CPLX = 0, RS_CONJ = 1, RS_EPI = 2, RS_HALF = 3 };
 
@@ -132,6 +132,15 @@ template <class T> struct PassParams {
   // major).  For the pair product all pairs of a frequency tile then run
   // together and the spectra rows they share are served by L2 instead of HBM.
   int32_t tile_major;
+  // ---- fused arg-max epilogue (CS_AMAX: the kept lags are reduced, not stored) ----
+  // per tile: the first maximal kept output index (np.argmax order: a NaN wins, ties -> lowest index) and its
+  // value; -1 when the tile holds no kept lag.  A second kernel reduces the tiles of a job.
+  void* amax_val;            // T[n_batch][tiles_per_batch]
+  int64_t* amax_idx;         // [n_batch][tiles_per_batch]
+  // 2-D validity of lag = dF * mask_w + dT (row-embedded images, signal/correlate.py): kept iff |dT| < mask_t
+  // and |dF| < mask_f; mask_w == 0 keeps every lag of [i0, i1)
+  int32_t mask_w, mask_t, mask_f;
+  int32_t mask_shift;        // log2(mask_w) when mask_w is a power of two, else -1
 };
 
 template <class T, int R1_, int R2_> struct Cfg {
@@ -231,6 +240,52 @@ template <class T> XCB_HD void epilogue_store_fast(const PassParams<T>& p, T* ou
     *reinterpret_cast<cx<T>*>(outp + l) = v;           // l even, rows start 2*sizeof(T)-aligned (K even or job 0)
   } else if (l < K) {
     outp[l] = re * p.escale;
+  }
+}
+
+// ---- fused arg-max (CS_AMAX) ----
+constexpr uint32_t kAmaxNone = 0xffffffffu;
+// np.argmax order on (value, output index) candidates: a NaN beats any number, then the larger value, then the lower index
+template <class T> XCB_HD bool amax_better(T vb, uint32_t ob, T va, uint32_t oa) {
+  if (ob == kAmaxNone) return false;
+  if (oa == kAmaxNone) return true;
+  const bool nb = vb != vb, na = va != va;
+  if (nb != na) return nb;
+  if (nb) return ob < oa;
+  return vb > va || (vb == va && ob < oa);
+}
+// final packed element m = (r[2m], r[2m+1]): offer its kept, unmasked lags to the running candidate (bv, bo)
+template <class T> XCB_HD void amax_consider(const PassParams<T>& p, uint32_t m, T re, T im, T& bv, uint32_t& bo) {
+  const uint32_t n = (uint32_t)p.n, L = (uint32_t)p.L;
+  const uint32_t i0 = (uint32_t)p.i0, K = (uint32_t)(p.i1 - p.i0);
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t l = 2u * m + (uint32_t)h;
+    uint32_t i, o;
+    if (p.epi_direct) {
+      o = l;
+      i = l + i0;
+    } else {
+      if (l < n) i = l + (n - 1u);
+      else if (l > L - n) i = l - (L - n + 1u);
+      else continue;
+      o = i - i0;
+    }
+    if (o >= K) continue;
+    if (p.mask_w) {
+      // lag = i - (n-1) = dF * W + dT;  t = lag + (T-1) + F*W > 0  ->  dF + F = t / W,  dT + T-1 = t % W
+      const uint32_t W = (uint32_t)p.mask_w, Tm = (uint32_t)p.mask_t, F = (uint32_t)p.mask_f;
+      const uint32_t t = i + (Tm - 1u) + F * W - (n - 1u);
+      const uint32_t q = p.mask_shift >= 0 ? (t >> p.mask_shift) : t / W;
+      const uint32_t dt = t - q * W;
+      if (dt >= 2u * Tm - 1u || q < 1u || q > 2u * F - 1u) continue;
+    }
+    T val = (h ? im : re) * p.escale;
+    if (p.unbiased) {
+      const uint32_t k = i >= n - 1u ? i - (n - 1u) : (n - 1u) - i;
+      val *= T((double)n / (double)(n - k));
+    }
+    if (amax_better(val, o, bv, bo)) { bv = val; bo = o; }
   }
 }
 

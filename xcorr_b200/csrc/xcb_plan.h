@@ -284,6 +284,10 @@ struct CorrFlags {
   int normalize = 1, unbiased = 0, accumulate = 0;
   int n_stack = 1, stack_sig_stride = 0;       // spectral stacking over windows
   int64_t stack_spec_stride = 0;
+  // fused arg-max instead of the lag store (last inverse pass, column kernels only)
+  void* amax_val = nullptr;
+  int64_t* amax_idx = nullptr;
+  int32_t mask_w = 0, mask_t = 0, mask_f = 0;
   int use_blk_off = 0;                          // block mode: explicit per-block offsets
   int64_t blk_off_i[8] = {0, 0, 0, 0, 0, 0, 0, 0}, blk_off_j[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -343,6 +347,14 @@ inline PassParams<T> make_inverse_pass(const PlanGeom& g, const DevTables<T>& tb
   } else {
     p.load_mode = CL_CPLX_INV;
     p.store_mode = (a == 0) ? CS_EPI : CS_CONJ;
+    if (a == 0 && f.amax_idx) {
+      p.store_mode = CS_AMAX;
+      p.amax_val = f.amax_val;
+      p.amax_idx = f.amax_idx;
+      p.mask_w = f.mask_w; p.mask_t = f.mask_t; p.mask_f = f.mask_f;
+      p.mask_shift = -1;
+      if (f.mask_w > 0 && (f.mask_w & (f.mask_w - 1)) == 0) { int sh = 0; while ((1 << sh) < f.mask_w) ++sh; p.mask_shift = sh; }
+    }
   }
   return p;
 }

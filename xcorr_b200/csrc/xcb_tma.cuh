@@ -97,7 +97,7 @@ template <class T, int R1, int R2> struct ColTma {
 
 // ROLE: 1 forward first pass (real input, norms), 2 forward middle, 3 inverse middle, 4 inverse last (lag
 // epilogue).  One kernel per role: the middle passes do not carry the epilogue's code and registers.
-enum ColRole : int { COL_ANY = 0, COL_FWD_REAL = 1, COL_FWD = 2, COL_INV = 3, COL_INV_EPI = 4 };
+enum ColRole : int { COL_ANY = 0, COL_FWD_REAL = 1, COL_FWD = 2, COL_INV = 3, COL_INV_EPI = 4, COL_INV_AMAX = 5 };
 
 template <class T, int R1, int R2, int ROLE>
 __global__ void __launch_bounds__(ColTma<T, R1, R2>::THREADS, ColTma<T, R1, R2>::MINB)
@@ -105,7 +105,8 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
                  const int64_t split_col, const __grid_constant__ PassParams<T> p) {
   // (ROLE 0 = COL_ANY reads the modes at run time)
   const int kLoad = ROLE == COL_ANY ? p.load_mode : ROLE == COL_FWD_REAL ? CL_REAL : (ROLE == COL_FWD ? CL_CPLX : CL_CPLX_INV);
-  const int kStore = ROLE == COL_ANY ? p.store_mode : ROLE <= COL_FWD ? CS_TW : (ROLE == COL_INV ? CS_CONJ : CS_EPI);
+  const int kStore = ROLE == COL_ANY ? p.store_mode : ROLE <= COL_FWD ? CS_TW
+                     : (ROLE == COL_INV ? CS_CONJ : (ROLE == COL_INV_AMAX ? CS_AMAX : CS_EPI));
   const bool kSumsq = ROLE == COL_ANY || ROLE == COL_FWD_REAL;
   using K = ColTma<T, R1, R2>;
   constexpr int N = K::N, C = K::C;
@@ -196,10 +197,21 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const int64_t next = tile + K::NSLOT * stride_tiles;
       if (next < ntiles) issue(next, s);
     }
+    T amax_v = T(0);
+    uint32_t amax_o = kAmaxNone;
     if (j < R1 && col_ok) {
       twiddle_powers<R2>(w_inner, v);
       fft_reg<R2>(v);
-      if (kStore == CS_TW) {
+      if (ROLE == COL_INV_AMAX) {
+        // fused arg-max: the lags of this tile are offered to a per-thread candidate, nothing is stored
+        const uint32_t m0 = (uint32_t)(base + c), inner = (uint32_t)p.inner;
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          const int k = j + r * R1;
+          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+            amax_consider(p, m0 + (uint32_t)k * inner, v[r].x, -v[r].y, amax_v, amax_o);
+        }
+      } else if (kStore == CS_TW) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
         twiddle_chain<R2, false>(p, colscale * (uint32_t)j, colscale * (uint32_t)R1, v);
 #pragma unroll
@@ -225,6 +237,36 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
             if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
               epilogue_store(p, outp, m0 + (uint32_t)k * inner, v[r].x, -v[r].y);
           }
+        }
+      }
+    }
+    if (ROLE == COL_INV_AMAX) {
+      // tile candidate: warp shuffles, then one slot per warp in `red` (free in this role), then warp 0
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const T ov = __shfl_down_sync(0xffffffffu, amax_v, o);
+        const uint32_t oo = __shfl_down_sync(0xffffffffu, amax_o, o);
+        if (amax_better(ov, oo, amax_v, amax_o)) { amax_v = ov; amax_o = oo; }
+      }
+      struct Cand { T v; uint32_t o; uint32_t pad; };
+      Cand* cand = reinterpret_cast<Cand*>(red);
+      constexpr int NW = (K::THREADS + 31) / 32;
+      static_assert(NW * sizeof(Cand) <= K::THREADS * 8, "candidates fit the reduction area");
+      if ((tid & 31) == 0) { cand[tid >> 5].v = amax_v; cand[tid >> 5].o = amax_o; }
+      __syncthreads();
+      if (tid < 32) {
+        T bv = T(0);
+        uint32_t bo = kAmaxNone;
+        if (tid < NW) { bv = cand[tid].v; bo = cand[tid].o; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const T ov = __shfl_down_sync(0xffffffffu, bv, o);
+          const uint32_t oo = __shfl_down_sync(0xffffffffu, bo, o);
+          if (amax_better(ov, oo, bv, bo)) { bv = ov; bo = oo; }
+        }
+        if (tid == 0) {
+          static_cast<T*>(p.amax_val)[tile] = bv;
+          p.amax_idx[tile] = bo == kAmaxNone ? (int64_t)-1 : (int64_t)bo;
         }
       }
     }

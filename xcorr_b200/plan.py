@@ -153,6 +153,27 @@ class CorrelationPlan:
                                            out.data_ptr(), self.workspace.data_ptr(), stream), "xcb_correlate")
         return out
 
+    def correlate_argmax(self, mask=None):
+        """Arg-max and maximum of every (pair, window) correlation function without storing it (the last
+        inverse pass reduces its tile; ``xcb_correlate_argmax``).  `mask` = ``(row_width, half_width,
+        n_rows)`` restricts the lags to the 2-D window of a row-embedded image correlation.  Returns
+        ``(index, value)`` shaped ``(n_pairs, n_windows)``; `index` counts from ``index_min``."""
+        if self.stack:
+            raise ValueError("correlate_argmax does not apply to stacking plans")
+        idx = torch.empty(self.n_jobs, dtype=torch.int64, device=self.device)
+        val = torch.empty(self.n_jobs, dtype=self.dtype, device=self.device)
+        m = None
+        if mask is not None:
+            m = _lib.xcb_lag_mask(int(mask[0]), int(mask[1]), int(mask[2]))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.xcb_correlate_argmax(self._plan, self.spec.data_ptr(), self.sumsq.data_ptr(),
+                                                  ctypes.byref(m) if m is not None else None, idx.data_ptr(),
+                                                  val.data_ptr(), self.workspace.data_ptr(), stream),
+                   "xcb_correlate_argmax")
+        # jobs are window-major (job = w * n_pairs + p)
+        shape = (self.n_windows, len(self.pairs))
+        return idx.view(shape).t(), val.view(shape).t()
+
     def argmax(self, ccf):
         """First index of the maximum along the last axis, and the maximum."""
         rows = ccf.reshape(-1, ccf.shape[-1])

@@ -23,7 +23,7 @@ import torch
 
 from ..plan import CorrelationPlan
 
-__all__ = ['correlate1d', 'correlate2d', 'Correlate2dPlan']
+__all__ = ['correlate1d', 'correlate2d', 'Correlate2dPlan', 'timelapse_pairs']
 
 
 def _row_width(T):
@@ -31,34 +31,79 @@ def _row_width(T):
     return max(16, -(-(2 * T - 1) // 16) * 16)
 
 
-class Correlate2dPlan:
-    """All 2-D correlations of ``n_images`` arrays ``F x T`` over a pair list."""
+def timelapse_pairs(n_days, k=1):
+    """Day pairs ``(time1, time2)`` the timelapse script evaluates: everything on and below the k-th
+    super-diagonal (``signal/tri.py:19-55`` ``np.tri(N, N, k)``, applied with k = 1 at
+    ``scripts/timelapse.py:348-352``): N(N+1)/2 + N-1 pairs for k = 1."""
+    return [(i, j) for i in range(n_days) for j in range(min(n_days, i + k + 1))]
 
-    def __init__(self, F, T, n_images, pairs, dtype=torch.float32, normalize=True, device=None):
+
+class Correlate2dPlan:
+    """All 2-D correlations of ``n_images`` arrays ``F x T`` over a pair list.
+
+    :meth:`correlate_argmax` is the timelapse kernel proper (``scripts/timelapse.py:255-268`` keeps
+    ``cc2.argmax()`` -> value, delta-freq, delta-lag per day pair): the maximum over the
+    ``(2F-1) x (2T-1)`` window is taken inside the last inverse pass and no ``cc2`` is stored.
+    :meth:`correlate` still returns the full ``cc2`` (parity, plots).
+
+    With ``day_shard=(rank, world)`` the images are split over the ranks of ``torch.distributed``'s
+    default group: every rank transforms ``ceil(n_images / world)`` of them and ONE all-gather of the
+    half spectra (NCCL) hands every rank all of them; `pairs` is then this rank's share of the pair list
+    (SURVEY 8e, config 5)."""
+
+    def __init__(self, F, T, n_images, pairs, dtype=torch.float32, normalize=True, device=None, day_shard=None):
         self.F, self.T, self.W = int(F), int(T), _row_width(T)
         self.n = self.F * self.W
         self.pairs = [(int(i), int(j)) for i, j in pairs]
-        self.plan = CorrelationPlan(self.n, n_images, self.pairs, dtype=dtype, normalize=normalize,
+        self.n_images = int(n_images)
+        self.rank, self.world = (int(day_shard[0]), int(day_shard[1])) if day_shard else (0, 1)
+        self.per = -(-self.n_images // self.world)                       # images transformed per rank
+        lo = min(self.n_images, self.rank * self.per)
+        self.day_slice = slice(lo, min(self.n_images, lo + self.per))
+        self.plan = CorrelationPlan(self.n, self.per * self.world, self.pairs, dtype=dtype, normalize=normalize,
                                     device=device, n_blocks=1)
+        self.fwd = self.plan if self.world == 1 else \
+            CorrelationPlan(self.n, self.per, [], dtype=dtype, normalize=normalize, device=device, n_blocks=1)
         self.dtype, self.device = self.plan.dtype, self.plan.device
-        a = torch.arange(-(self.F - 1), self.F, device=self.device).view(-1, 1)
-        b = torch.arange(-(self.T - 1), self.T, device=self.device).view(1, -1)
-        # 1-D output index of shift (dF, dT): lag dF*W + dT sits at (n-1) + lag
-        self.index = ((self.n - 1) + a * self.W + b).reshape(-1)
+        self._x = torch.zeros((self.per if self.world > 1 else self.n_images, self.F, self.W), dtype=self.dtype,
+                              device=self.device)                        # row-embedded images; the padding stays zero
+        self._index = None
 
     def embed(self, images):
-        """(n_images, F, T) -> (n_images, F*W) zero-padded rows."""
-        x = torch.zeros((images.shape[0], self.F, self.W), dtype=self.dtype, device=self.device)
-        x[:, :, :self.T] = images.to(self.dtype)
-        return x.reshape(images.shape[0], self.n)
+        """(k, F, T) -> (k, F*W): every image row is followed by W - T zeros, so that the 1-D lag
+        ``dF*W + dT`` of the flattened arrays is the 2-D shift (dF, dT)."""
+        k = images.shape[0]
+        self._x[:k, :, :self.T].copy_(images)
+        return self._x.reshape(self._x.shape[0], self.n)
 
     def forward(self, images):
-        self.plan.forward(self.embed(images))
+        """Transform this rank's images (all of them without sharding) and, when sharded, all-gather
+        the spectra and the norms."""
+        x = self.embed(images)
+        self.fwd.forward(x)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(torch.view_as_real(self.plan.spec), torch.view_as_real(self.fwd.spec))
+            dist.all_gather_into_tensor(self.plan.sumsq, self.fwd.sumsq)
 
     def correlate(self):
         """cc2 of every pair, shape (n_pairs, 2F-1, 2T-1)."""
+        if self._index is None:
+            a = torch.arange(-(self.F - 1), self.F, device=self.device).view(-1, 1)
+            b = torch.arange(-(self.T - 1), self.T, device=self.device).view(1, -1)
+            # 1-D output index of shift (dF, dT): lag dF*W + dT sits at (n-1) + lag
+            self._index = ((self.n - 1) + a * self.W + b).reshape(-1)
         ccf = self.plan.correlate()[:, 0]
-        return ccf.index_select(1, self.index).reshape(len(self.pairs), 2 * self.F - 1, 2 * self.T - 1)
+        return ccf.index_select(1, self._index).reshape(len(self.pairs), 2 * self.F - 1, 2 * self.T - 1)
+
+    def correlate_argmax(self, images=None):
+        """(value, dF, dT) of the maximum of every pair's cc2 (first maximal index in C order, like
+        ``np.unravel_index(cc2.argmax(), cc2.shape)``), fused into the inverse transform."""
+        if images is not None:
+            self.forward(images)
+        idx, val = self.plan.correlate_argmax(mask=(self.W, self.T, self.F))
+        t = idx[:, 0] - (self.n - 1) + (self.T - 1) + self.F * self.W      # lag + (T-1) + F*W > 0
+        return val[:, 0], t // self.W - self.F, t % self.W - (self.T - 1)
 
     def argmax(self, cc2):
         """(value, dF, dT) of the maximum of each cc2 (first maximal index,
