@@ -502,7 +502,7 @@ def run_gpu(args):
 
     # ---------------- end to end through core.process, against the measured PCIe ceiling ----------------
     pcie = pcie_probe(torch, dev, barrier)
-    wpc = max(1, min(args.steps, 4))
+    wpc = max(1, min(args.steps, max(2, 6 // world)))        # windows per process() call: 3.9 GB of page-locked cc each
     e2e_ms, ds = e2e_core_process(torch, xb, dev, x_host, R, n, K, args.steps, args.warmup, wpc, barrier)
     got = ds.variables["cc"].data
     assert int(np.argmax(got[0, 0])) == (n - 1 - i0) + 137 and ds.variables["status"].data.min() == 1

@@ -191,6 +191,17 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
                         int64_t y_stride, int64_t n, int32_t n_signals, const xcb_sos* f, const xcb_pointwise* pre,
                         const double* stats, void* workspace, void* stream);
 
+/* Polyphase FIR rate change (the north-star decimator; scipy.signal.upfirdn / resample_poly semantics, offered as
+ * op 'resample_poly' beside the obspy-faithful ('decimate', {...}) of stream/process.py:34-37):
+ *   y[k] = sum_i x[i] * taps[(k + k0) * down - i * up],   k < n_out
+ * i.e. zero-stuffing by `up`, FIR, keep every `down`-th sample, skip the first k0 outputs -- computed directly,
+ * n_taps / up multiply-adds per output, float64 accumulation.  taps: device double[n_taps] (host design:
+ * scipy.signal.firwin as resample_poly does it); `pre` (optional) is applied to x on the fly. */
+XCB_API int xcb_upfirdn(int32_t dtype_in, const void* x, int64_t x_stride, int64_t n_in, int32_t dtype_out, void* y,
+                        int64_t y_stride, int64_t n_out, int32_t n_signals, const double* taps, int32_t n_taps,
+                        int32_t up, int32_t down, int64_t k0, const xcb_pointwise* pre, const double* stats,
+                        void* stream);
+
 /* ------------------------------------------------------------------------
  * Plain complex transforms on the same pass kernels, and DFTs of ARBITRARY
  * length through Bluestein's algorithm.  They replace the numpy / pyfftw calls

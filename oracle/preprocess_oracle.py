@@ -298,6 +298,11 @@ def process(x, sampling_rate, operations, trace_start=0.0, starttime=None, endti
         elif name == "resample":
             params = dict(params)
             y, fs = resample(y, fs, params.pop("sampling_rate"), **params)
+        elif name == "resample_poly":
+            # the north-star polyphase decimator: scipy's own implementation IS the published algorithm (pinned)
+            up, down = int(params.pop("up")), int(params.pop("down"))
+            y = signal.resample_poly(y, up, down, **params)
+            fs = fs * up / down
         elif name == "interpolate":
             params = dict(params)
             if params.pop("method", None) != "lanczos":

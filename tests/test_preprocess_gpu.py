@@ -128,3 +128,33 @@ def test_oplist_error_behaviour(env):
         sp.process(x, [("decimate", {"factor": 20})], sampling_rate=50.0, raise_error=True)
     assert set(sp.device_operations()) == {"decimate", "detrend", "filter", "interpolate", "normalize", "resample", "running_rms", "taper", "trim"}
     assert "remove_response" in sp.list_operations() and sp.is_operation("merge")
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_polyphase_fir_rate_change_matches_scipy(env, dtype, tol):
+    """('resample_poly', {up, down}): the north-star polyphase-FIR decimator against scipy.signal.resample_poly
+    itself (zero-phase Kaiser-windowed FIR, upfirdn), alone and inside the config-2 style chain."""
+    torch, _, sp, pre, _ = env
+    from scipy import signal
+    fs = 250.0
+    x = raw_traces(3, 100_003, fs, seed=77)
+    for up, down in ((1, 5), (1, 2), (2, 5), (3, 7), (5, 2), (1, 16), (4, 6), (1, 1)):
+        ops = [("resample_poly", {"up": up, "down": down})]
+        got, ref = run(env, x, fs, ops, dtype)
+        assert np.array_equal(ref, np.stack([signal.resample_poly(r.astype(dtype).astype(np.float64), up, down) for r in x]))
+        assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref)), (up, down)
+    # other windows, short traces (shorter than the filter), and the decimating chain of config 2 with the FIR
+    got, ref = run(env, x[:, :37], fs, [("resample_poly", {"up": 1, "down": 5, "window": "hamming"})], dtype)
+    assert np.max(np.abs(got - ref)) <= tol * np.max(np.abs(ref))
+    chain = [("detrend", {"type": "demean"}),
+             ("taper", {"type": "cosine", "max_percentage": 0.05, "max_length": 30.0}),
+             ("filter", {"type": "bandpass", "freqmin": 3.0, "freqmax": 12.0}),
+             ("resample_poly", {"up": 1, "down": 5}),
+             ("detrend", {"type": "demean"}),
+             ("taper", {"type": "cosine", "max_percentage": 0.05, "max_length": 30.0})]
+    got, ref = run(env, x, fs, chain, dtype)
+    assert got.shape[1] == 20_001
+    assert np.max(np.abs(got - ref)) <= (1e-11 if dtype == np.float64 else 1e-5) * np.max(np.abs(ref))
+    with pytest.raises(RuntimeError):
+        sp.process(torch.zeros((1, 100), device="cuda"), [("resample_poly", {"up": 1, "down": 5, "padtype": "line"})],
+                   sampling_rate=fs, raise_error=True)

@@ -113,6 +113,8 @@ SYMBOLS = {
                                                    ctypes.POINTER(ctypes.c_size_t)]),
     "xcb_sosfilt": (ctypes.c_int, [_i32, _vp, _i64, _i32, _vp, _i64, _i64, _i32, ctypes.POINTER(xcb_sos),
                                    ctypes.POINTER(xcb_pointwise), _vp, _vp, _vp]),
+    "xcb_upfirdn": (ctypes.c_int, [_i32, _vp, _i64, _i64, _i32, _vp, _i64, _i64, _i32, _vp, _i32, _i32, _i32, _i64,
+                                   ctypes.POINTER(xcb_pointwise), _vp, _vp]),
     "xcb_profile_enable": (ctypes.c_int, [_vp, _i32]),
     "xcb_profile_read": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(_i64)]),

@@ -27,7 +27,7 @@ import pandas as pd
 from . import init as _init  # noqa: F401
 from ..stream import process as stream_process
 
-__all__ = ['process', 'compile_operations']
+__all__ = ['process', 'compile_operations', 'clear_caches']
 
 
 def _channel(receiver):
@@ -61,6 +61,30 @@ def compile_operations(ops, channels, window_length):
                                                                      endtime=float(window_length))))
         out[chan] = lst
     return out
+
+
+# Plans, preprocessing programs and the page-locked staging buffers outlive one call: the reference's unit of
+# work is one (pair, day) file (core/lazy.py:26-82), so process() is called over and over with the same shapes,
+# and creating a plan (tables, workspace) or page-locking memory costs more than a window of correlations.
+_PLAN_CACHE, _PROGRAM_CACHE, _STAGERS = {}, {}, {}
+_PLAN_CACHE_MAX = 3
+
+
+def clear_caches():
+    """Release the cached plans, programs and staging buffers."""
+    _PLAN_CACHE.clear()
+    _PROGRAM_CACHE.clear()
+    _STAGERS.clear()
+
+
+def _cached_plan(key, make):
+    if key in _PLAN_CACHE:
+        _PLAN_CACHE[key] = _PLAN_CACHE.pop(key)           # most recently used last
+        return _PLAN_CACHE[key]
+    while len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[key] = make()
+    return _PLAN_CACHE[key]
 
 
 class _Stager:
@@ -152,10 +176,11 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         todo = todo[:1]
     batches = [todo[b:b + windows_per_batch] for b in range(0, len(todo), windows_per_batch)]
 
-    plans, programs = {}, {}
+    ops_key = stream_process.operations_to_json(dict(dataset.coords['pair'].attrs['preprocess']))
+    programs = _PROGRAM_CACHE.setdefault((ops_key, window_length), {})
     with torch.cuda.device(dev):
         s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        stager = _Stager(torch, dev)
+        stager = _STAGERS.setdefault(str(dev), _Stager(torch, dev))
         x_dev = [None, None]
         ccf_dev = [None, None]
         ev_run = [None, None]                 # compute of the batch that last used slot s
@@ -238,11 +263,12 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                     for (k, j) in members:
                         ok[k, j] = True
                         offsets[k, j] = start_final
-                if W not in plans:
-                    plans[W] = CorrelationPlan(npts, R, pair_idx, n_windows=W, dtype=dtype, index_min=i0, index_max=i1,
-                                               normalize=cc.attrs['normalize'] == 1,
-                                               unbiased=cc.attrs['bias_correct'] == 1, device=dev)
-                plans[W](x, out=ccf_dev[slot])
+                normalize, unbiased = cc.attrs['normalize'] == 1, cc.attrs['bias_correct'] == 1
+                plan = _cached_plan(
+                    (str(dev), npts, R, tuple(pair_idx), W, str(dtype), i0, i1, bool(normalize), bool(unbiased)),
+                    lambda: CorrelationPlan(npts, R, pair_idx, n_windows=W, dtype=dtype, index_min=i0, index_max=i1,
+                                            normalize=normalize, unbiased=unbiased, device=dev))
+                plan(x, out=ccf_dev[slot])
                 ev_run[slot] = torch.cuda.Event()
                 ev_run[slot].record(s_run)
             # cells of this batch that get a result

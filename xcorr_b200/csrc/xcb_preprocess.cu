@@ -425,6 +425,54 @@ __global__ void __launch_bounds__(32) sos_carry_sweep(int d, int64_t n_groups, c
   }
 }
 
+// ------------------------------------------------------ polyphase FIR (upfirdn)
+// y[k] = sum_i x[i] h[(k + k0) down - i up]: the zero-stuffed input is never formed and only every
+// down-th output is computed -- `n_taps / up` multiply-adds per output (scipy.signal.upfirdn /
+// resample_poly).  A block owns kFirTile consecutive outputs of one signal: the input span they touch
+// (with the optional detrend / taper prologue applied) and the taps sit in shared memory as float64.
+constexpr int kFirTile = 512;
+template <class TI, class TO>
+__global__ void __launch_bounds__(256) upfirdn_kernel(const TI* __restrict__ x, int64_t xs, int64_t n_in,
+                                                      TO* __restrict__ y, int64_t ys, int64_t n_out,
+                                                      const double* __restrict__ taps, int n_taps, int up, int down,
+                                                      int64_t k0, int span, PointwiseDev pw,
+                                                      const double* __restrict__ stats) {
+  extern __shared__ double fir_sm[];                     // taps [n_taps], then the input span
+  double* h = fir_sm;
+  double* xw = fir_sm + n_taps;
+  const int sig = blockIdx.y;
+  const int64_t ka = (int64_t)blockIdx.x * kFirTile;
+  int64_t kb = ka + kFirTile;
+  if (kb > n_out) kb = n_out;
+  // first input any output of the tile can touch: ceil(((ka + k0) down - (n_taps - 1)) / up), floor division safe
+  const int64_t qa = (ka + k0) * (int64_t)down - (n_taps - 1);
+  const int64_t i_lo = qa >= 0 ? (qa + up - 1) / up : -((-qa) / up);
+  double c0, c1;
+  trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n_in, c0, c1);
+  const TI* xi = x + (int64_t)sig * xs;
+  for (int t = threadIdx.x; t < n_taps; t += 256) h[t] = taps[t];
+  for (int t = threadIdx.x; t < span; t += 256) {
+    const int64_t i = i_lo + t;
+    xw[t] = (i >= 0 && i < n_in) ? pointwise_value(pw, (double)xi[i], i, n_in, c0, c1) : 0.0;
+  }
+  __syncthreads();
+  TO* yo = y + (int64_t)sig * ys;
+  for (int64_t k = ka + threadIdx.x; k < kb; k += 256) {
+    const int64_t q = (k + k0) * (int64_t)down;          // position in the zero-stuffed input
+    const int64_t i_hi = q / up;
+    int m = (int)(q - i_hi * up);                        // tap that meets x[i_hi]
+    const double* xp = xw + (i_hi - i_lo);
+    double a0 = 0.0, a1 = 0.0;
+    int t = 0;
+    for (; m + up < n_taps; m += 2 * up, t += 2) {       // xw is zero outside the signal: no bounds in the loop
+      a0 = fma(h[m], xp[-t], a0);
+      a1 = fma(h[m + up], xp[-t - 1], a1);
+    }
+    if (m < n_taps) a0 = fma(h[m], xp[-t], a0);
+    yo[k] = (TO)(a0 + a1);
+  }
+}
+
 // ------------------------------------------------------------------ dispatch
 struct SosArgs {
   const void* x; int64_t xs; void* y; int64_t ys; int64_t n; int n_signals;
@@ -626,6 +674,39 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   }
   if (run_phase_s(f->n_sections, 3, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
   return XCB_OK;
+}
+
+XCB_API int xcb_upfirdn(int32_t dtype_in, const void* x, int64_t x_stride, int64_t n_in, int32_t dtype_out, void* y,
+                        int64_t y_stride, int64_t n_out, int32_t n_signals, const double* taps, int32_t n_taps,
+                        int32_t up, int32_t down, int64_t k0, const xcb_pointwise* pre, const double* stats,
+                        void* stream) {
+  if (!x || !y || !taps || n_in < 1 || n_out < 1 || n_signals < 1 || n_taps < 1 || up < 1 || down < 1 || k0 < 0 ||
+      !dtype_ok(dtype_in) || !dtype_ok(dtype_out))
+    return XCB_ERR_ARG;
+  if (pre && pre->detrend && !stats) return XCB_ERR_ARG;
+  if (pre && pre->taper_left + pre->taper_right > n_in) return XCB_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // inputs touched by one tile of outputs: (kFirTile - 1) * down / up + n_taps / up + 2
+  const int span = (int)(((int64_t)(kFirTile - 1) * down + n_taps - 1) / up + 2);
+  const size_t smem = sizeof(double) * ((size_t)n_taps + (size_t)span);
+  if (smem > 200 * 1024) return XCB_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)((n_out + kFirTile - 1) / kFirTile), (unsigned)n_signals);
+  const PointwiseDev pw = to_dev(pre);
+#define XCB_FIR(TI, TO)                                                                                              \
+  do {                                                                                                               \
+    if (smem > 48 * 1024 &&                                                                                          \
+        cudaFuncSetAttribute(upfirdn_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=      \
+            cudaSuccess)                                                                                             \
+      return XCB_ERR_CUDA;                                                                                           \
+    upfirdn_kernel<TI, TO><<<grid, 256, smem, st>>>(static_cast<const TI*>(x), x_stride, n_in, static_cast<TO*>(y),  \
+                                                    y_stride, n_out, taps, n_taps, up, down, k0, span, pw, stats);   \
+  } while (0)
+  if (dtype_in == XCB_F32 && dtype_out == XCB_F32) XCB_FIR(float, float);
+  else if (dtype_in == XCB_F32) XCB_FIR(float, double);
+  else if (dtype_out == XCB_F32) XCB_FIR(double, float);
+  else XCB_FIR(double, double);
+#undef XCB_FIR
+  return cudaGetLastError() == cudaSuccess ? XCB_OK : XCB_ERR_CUDA;
 }
 
 }  // extern "C"
