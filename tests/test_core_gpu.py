@@ -1,5 +1,7 @@
 """The batched process driver (core/process.py:82-165 replacement) against a
 cell-by-cell oracle loop."""
+import os
+
 import numpy as np
 import pandas as pd
 import pytest
@@ -158,3 +160,78 @@ def test_buffered_windows_trim_injection_and_config_errors():
         with pytest.raises((NotImplementedError, ArithmeticError, TypeError)):
             core.process(ds2, provider, verb=0)
         assert not np.any(ds2.variables["status"].data)
+
+
+def test_overlapping_windows_share_one_transfer_and_day_batched_files(tmp_path):
+    """core/init.py:28 default overlap (0.875): eight windows a day share 87.5 % of their samples.  Windows handed
+    over as views of ONE longer trace are copied to the device once (union), results equal the window-by-window
+    path.  Then the day-batched task loop (core/lazy.py:26-82 for all pairs of a day): per-pair files, resume."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from xcorr_b200 import core, io
+    from xcorr_b200.core import process as proc_mod
+    from oracle import cc_oracle as orc
+
+    recv = ["IM.H10N1..EDH", "IM.H10N2..EDH", "IM.H03S1..EDH"]
+    pairs = [f"{recv[0]}-{recv[1]}", f"{recv[0]}-{recv[2]}", f"{recv[1]}-{recv[2]}"]
+    fs, wl, ov = 50.0, 800.0, 0.875
+    ops = {"EDH": [("detrend", {"type": "demean"}), ("taper", {"type": "cosine", "max_percentage": 0.05})]}
+    t0 = pd.Timestamp("2015-01-15")
+    init_args = dict(preprocess=ops, attrs=dict(institution="i", author="a", source="s"), sampling_rate=fs,
+                     window_length=wl, window_overlap=ov, clip_lag=(-5.0, 20.0), dtype=np.float32)
+    ds = core.init(pairs, t0, t0 + pd.Timedelta(seconds=800), **init_args)
+    times = pd.DatetimeIndex(ds.coords["time"].data)
+    W, n, hop = len(times), int(wl * fs), int(wl * (1 - ov) * fs)
+    assert W == 8 and hop == 5000
+    long = {r: (orc.synthetic_receivers(3, n + W * hop, seed=77, delay=31)[k] + 0.5).astype(np.float32)
+            for k, r in enumerate(recv)}
+
+    def views(receiver, time):
+        w = times.get_loc(time)
+        return long[receiver][w * hop:w * hop + n], fs, 0.0          # a view of the continuous trace
+
+    def copies(receiver, time):
+        d, rate, off = views(receiver, time)
+        return d.copy(), rate, off
+
+    core.process(ds, views, windows_per_batch=8, verb=0)
+    h2d_shared = proc_mod.last_stats["h2d_bytes"]
+    ref = core.init(pairs, t0, t0 + pd.Timedelta(seconds=800), **init_args)
+    core.process(ref, copies, windows_per_batch=8, verb=0)
+    assert proc_mod.last_stats["h2d_bytes"] == 3 * W * n * 4
+    assert h2d_shared == 3 * (n + (W - 1) * hop) * 4 < 0.25 * proc_mod.last_stats["h2d_bytes"]
+    assert np.array_equal(ds.variables["cc"].data, ref.variables["cc"].data) and ds.variables["status"].data.min() == 1
+    i0, i1 = ds.coords["lag"].attrs["index_min"], ds.coords["lag"].attrs["index_max"]
+    from oracle import preprocess_oracle as pre
+    x0, _ = pre.process(long[recv[0]][2 * hop:2 * hop + n], fs, ops["EDH"])
+    x1, _ = pre.process(long[recv[1]][2 * hop:2 * hop + n], fs, ops["EDH"])
+    cell = orc.process_cell(x0.astype(np.float32), x1.astype(np.float32), n, i0, i1, dtype=np.float64)
+    assert np.max(np.abs(ds.variables["cc"].data[0, 2] - cell)) <= 1e-5 * np.max(np.abs(cell))
+
+    # ---- the day-batched task loop ----
+    root = str(tmp_path)
+    day_args = dict(init_args, window_overlap=0.0)
+    gone = {"n": 0}
+
+    def provider(receiver, time):
+        if receiver == recv[2] and gone["n"] == 0:
+            return None                                               # first run: one receiver is missing
+        w = (time - t0) // pd.Timedelta(seconds=wl)
+        return long[receiver][int(w) * hop:int(w) * hop + n], fs, 0.0
+
+    res = core.process_day(pairs, t0, day_args, provider, root, freq="1600s", verb=0)
+    assert res == {pairs[0]: True, pairs[1]: False, pairs[2]: False}
+    f0 = io.ncfile(pairs[0], t0, root)
+    assert os.path.exists(f0) and not os.path.exists(io.ncfile(pairs[1], t0, root))
+    first = io.read(f0)
+    gone["n"] = 1
+    res = core.process_day(pairs, t0, day_args, provider, root, freq="1600s", verb=0)
+    assert res == {p: True for p in pairs}                           # pair 0 was complete: skipped, the others written
+    again = io.read(f0)
+    assert np.array_equal(first.variables["cc"].data, again.variables["cc"].data)
+    one = io.read(io.ncfile(pairs[2], t0, root))
+    assert one.variables["cc"].data.shape[0] == 1 and one.variables["status"].data.min() == 1
+    assert list(one.coords["pair"].data) == [pairs[2]]
+    assert core.day_tasks(pairs, pd.date_range(t0, periods=2, freq="D"),
+                          done=lambda p, t: p == pairs[0]) == {t0: pairs[1:], t0 + pd.Timedelta("1D"): pairs[1:]}

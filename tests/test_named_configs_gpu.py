@@ -118,11 +118,13 @@ def test_sixteen_receivers_midsize_every_cell(env, dtype):
     """Same structure as config 3 (16 receivers, 120 pairs, cropped lags -> blocks, 16 x R2 row axis,
     grouped kernel) at a size where EVERY cell is compared with the reference restatement."""
     torch, xb, orc = env
-    n, R, K = 200_000, 16, 75_000
+    n, R, K = 120_000, 16, 16_000
     pairs = xb.all_pairs(R)
     rec = orc.synthetic_receivers(R, n, seed=3001, delay=137).astype(np.float32)
     x = torch.from_numpy(rec).cuda().to(_tdt(torch, dtype))
-    plan = xb.CorrelationPlan(n, R, pairs, dtype=_tdt(torch, dtype), index_min=n - 1, index_max=n - 1 + K)
+    # the benchmark's geometry in small: 2 blocks, middle pass of 150, 256-point row axis (2M = 76800 >= 60000 + K)
+    plan = xb.CorrelationPlan(n, R, pairs, dtype=_tdt(torch, dtype), index_min=n - 1, index_max=n - 1 + K,
+                              dims=(150, 256), n_blocks=2, block_len=60_000)
     assert plan.n_blocks >= 2 and plan.n_groups > 0 and 3 * plan.n_groups <= len(pairs), (plan.dims, plan.n_groups)
     got = plan(x)[:, 0].cpu().numpy()
     r64 = rec.astype(np.float64)

@@ -29,6 +29,10 @@ def _worker(rank, world, port, n_windows, out_q):
         local = full[:, mine].clone()
         got = parallel.gather_ccf(local, n_windows, dst=0)
         ok_gather = (got is None) if rank != 0 else bool(torch.equal(got, full))
+        # several slabs of pairs (staging bounded by chunk_bytes) into a caller-provided output
+        out = torch.zeros_like(full) if rank == 0 else None
+        got2 = parallel.gather_ccf(local, n_windows, dst=0, out=out, chunk_bytes=4 * 17 * 4 + 1)
+        ok_gather = ok_gather and ((got2 is None) if rank != 0 else (got2 is out and bool(torch.equal(out, full))))
         stack = local.sum(dim=1)
         parallel.reduce_stack(stack)
         ok_reduce = bool(torch.allclose(stack, full.sum(dim=1)))
@@ -62,3 +66,21 @@ def test_gather_and_reduce_world2():
     for rank, ok_g, ok_r, mine in res:
         assert ok_g and ok_r, (rank, ok_g, ok_r)
         assert mine == list(range(rank, n_windows, world))
+
+
+def test_timelapse_pairs_tile_over_ranks():
+    """Config 5 sharding: the masked triangle of scripts/timelapse.py:348-360 split over ranks, the
+    day transforms split in contiguous slices."""
+    from xcorr_b200.signal.correlate import timelapse_pairs
+    D = 365
+    pairs = timelapse_pairs(D)
+    assert len(pairs) == D * (D + 1) // 2 + D - 1 and (0, 1) in pairs and (0, 2) not in pairs and (364, 0) in pairs
+    mask = np.tri(D, D, k=1, dtype=bool)                     # signal/tri.py:19-55
+    assert sorted(pairs) == sorted(zip(*np.nonzero(mask)))
+    for world in (1, 2, 8):
+        shares = [pairs[r::world] for r in range(world)]
+        assert sorted(p for s in shares for p in s) == sorted(pairs)
+        assert max(map(len, shares)) - min(map(len, shares)) <= 1
+        per = -(-D // world)
+        days = [list(range(min(D, r * per), min(D, (r + 1) * per))) for r in range(world)]
+        assert sorted(d for s in days for d in s) == list(range(D))

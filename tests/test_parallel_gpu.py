@@ -33,6 +33,19 @@ def _worker(rank, world, port, q):
         full = parallel.gather_ccf(local, W, dst=0)
         stack = parallel.reduce_stack(local.sum(dim=1))
         ok = True
+        # config 5 sharding: day transforms split over the ranks, ONE all-gather of the half spectra, the day
+        # pairs tiled over the ranks; must equal the unsharded plan bit for bit
+        from xcorr_b200.signal import Correlate2dPlan, timelapse_pairs
+        F, T, D = 64, 16, 7
+        g = torch.Generator(device="cuda")
+        g.manual_seed(5)
+        days = torch.randn((D, F, T), generator=g, device="cuda", dtype=torch.float32) ** 2
+        allp = timelapse_pairs(D)
+        sharded = Correlate2dPlan(F, T, D, allp[rank::world], dtype=torch.float32, day_shard=(rank, world))
+        v, dF, dT = sharded.correlate_argmax(days[sharded.day_slice])
+        single = Correlate2dPlan(F, T, D, allp[rank::world], dtype=torch.float32)
+        v1, dF1, dT1 = single.correlate_argmax(days)
+        ok &= bool(torch.equal(v, v1) and torch.equal(dF, dF1) and torch.equal(dT, dT1))
         if rank == 0:
             got = full.cpu().numpy()
             for qq, (i, j) in enumerate(pairs):

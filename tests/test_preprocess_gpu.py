@@ -126,7 +126,7 @@ def test_oplist_error_behaviour(env):
         sp.process(x, [("remove_response", {})], sampling_rate=50.0, raise_error=True)
     with pytest.raises(RuntimeError):
         sp.process(x, [("decimate", {"factor": 20})], sampling_rate=50.0, raise_error=True)
-    assert set(sp.device_operations()) == {"decimate", "detrend", "filter", "interpolate", "normalize", "resample", "running_rms", "taper", "trim"}
+    assert set(sp.device_operations()) == {"decimate", "detrend", "filter", "interpolate", "normalize", "resample", "resample_poly", "running_rms", "taper", "trim"}
     assert "remove_response" in sp.list_operations() and sp.is_operation("merge")
 
 

@@ -67,6 +67,7 @@ def compile_operations(ops, channels, window_length):
 # work is one (pair, day) file (core/lazy.py:26-82), so process() is called over and over with the same shapes,
 # and creating a plan (tables, workspace) or page-locking memory costs more than a window of correlations.
 _PLAN_CACHE, _PROGRAM_CACHE, _STAGERS = {}, {}, {}
+last_stats = {}                # of the most recent process() call: {'h2d_bytes': ...}
 _PLAN_CACHE_MAX = 3
 
 
@@ -85,6 +86,26 @@ def _cached_plan(key, make):
         _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
     _PLAN_CACHE[key] = make()
     return _PLAN_CACHE[key]
+
+
+def _shared_base(arrs):
+    """If all arrays are contiguous 1-D views of one longer contiguous 1-D array and overlap enough that
+    their union is smaller than their sum, return ``(base, element offsets, lo, hi)``; else None."""
+    if len(arrs) < 2:
+        return None
+    base = arrs[0].base
+    if base is None or not isinstance(base, np.ndarray) or base.ndim != 1 or not base.flags.c_contiguous:
+        return None
+    p0, item = base.__array_interface__['data'][0], base.itemsize
+    offs = []
+    for a in arrs:
+        if a.base is not base or a.ndim != 1 or not a.flags.c_contiguous or a.dtype != base.dtype:
+            return None
+        offs.append((a.__array_interface__['data'][0] - p0) // item)
+    lo, hi = min(offs), max(o + len(a) for o, a in zip(offs, arrs))
+    if hi - lo >= sum(len(a) for a in arrs):
+        return None
+    return base, offs, lo, hi
 
 
 class _Stager:
@@ -185,6 +206,7 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         ccf_dev = [None, None]
         ev_run = [None, None]                 # compute of the batch that last used slot s
         ev_out = [None, None]                 # its device -> host copy
+        h2d_bytes = [0]
 
         def program_for(chan, n_raw, rate, off):
             key = (chan, n_raw, rate, off)
@@ -234,20 +256,40 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                     continue
                 start_final = prog.trace_start_out + skip / prog.fs_out
                 tdt = torch.float32 if ndt == np.float32 else torch.float64
-                srcs = [torch.from_numpy(raw[m][0]) for m in members]
-                if all(t.is_pinned() and t.is_contiguous() for t in srcs):
-                    # the caller's I/O layer already reads into page-locked memory: DMA straight from it
+                arrs = [raw[m][0] for m in members]
+                shared = _shared_base(arrs)
+                if shared is not None:
+                    # overlapping windows (core/init.py:28, window_overlap = 0.875: eight windows a day share
+                    # 87.5 % of their samples) handed over as views of ONE longer trace: the union goes to the
+                    # device once and the windows are cut there
+                    base, offs, lo, hi = shared
+                    src = torch.from_numpy(base[lo:hi])
+                    hb, devbase = stager.get(slot, ('base', gi), (hi - lo,), tdt, host=not src.is_pinned())
                     _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
                     with torch.cuda.stream(s_in):
-                        for m, t in enumerate(srcs):
-                            devbuf[m].copy_(t, non_blocking=True)
+                        if hb is not None:
+                            hb.numpy()[...] = base[lo:hi]
+                            src = hb
+                        devbase.copy_(src, non_blocking=True)
+                        for m, o in enumerate(offs):
+                            devbuf[m].copy_(devbase[o - lo:o - lo + n_raw], non_blocking=True)
+                    h2d_bytes[0] += (hi - lo) * src.element_size()
                 else:
-                    host, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt)
-                    hnp = host.numpy()
-                    for m, (k, j) in enumerate(members):
-                        hnp[m] = raw[(k, j)][0]
-                    with torch.cuda.stream(s_in):
-                        devbuf.copy_(host, non_blocking=True)
+                    srcs = [torch.from_numpy(a) for a in arrs]
+                    if all(t.is_pinned() and t.is_contiguous() for t in srcs):
+                        # the caller's I/O layer already reads into page-locked memory: DMA straight from it
+                        _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
+                        with torch.cuda.stream(s_in):
+                            for m, t in enumerate(srcs):
+                                devbuf[m].copy_(t, non_blocking=True)
+                    else:
+                        host, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt)
+                        hnp = host.numpy()
+                        for m, a in enumerate(arrs):
+                            hnp[m] = a
+                        with torch.cuda.stream(s_in):
+                            devbuf.copy_(host, non_blocking=True)
+                    h2d_bytes[0] += len(members) * n_raw * devbuf.element_size()
                 staged.append((prog, devbuf, members, skip, start_final))
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)
@@ -331,6 +373,7 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         cc.attrs['long_name'] = 'Unbiased ' + cc.attrs['long_name']
         cc.attrs['standard_name'] = 'unbiased_' + cc.attrs['standard_name']
         dataset.attrs['history'] += f", Unbiased CC @ {pd.Timestamp.now()}"
+    last_stats['h2d_bytes'] = int(h2d_bytes[0])                     # bookkeeping: bytes copied host -> device
     # update metadata hash (core/process.py:183)
     dataset.attrs['sha256_hash_metadata'] = hash_dataset(dataset, metadata_only=True)
     return dataset
