@@ -170,7 +170,8 @@ def test_overlapping_windows_share_one_transfer_and_day_batched_files(tmp_path):
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from xcorr_b200 import core, io
-    from xcorr_b200.core import process as proc_mod
+    import importlib
+    proc_mod = importlib.import_module("xcorr_b200.core.process")
     from oracle import cc_oracle as orc
 
     recv = ["IM.H10N1..EDH", "IM.H10N2..EDH", "IM.H03S1..EDH"]

@@ -257,39 +257,50 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 start_final = prog.trace_start_out + skip / prog.fs_out
                 tdt = torch.float32 if ndt == np.float32 else torch.float64
                 arrs = [raw[m][0] for m in members]
-                shared = _shared_base(arrs)
-                if shared is not None:
-                    # overlapping windows (core/init.py:28, window_overlap = 0.875: eight windows a day share
-                    # 87.5 % of their samples) handed over as views of ONE longer trace: the union goes to the
-                    # device once and the windows are cut there
+                _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
+                # overlapping windows (core/init.py:28, window_overlap = 0.875: eight windows a day share 87.5 % of
+                # their samples) handed over as views of ONE longer trace per receiver: the union of a receiver's
+                # windows goes to the device once and the windows are cut there
+                by_base = {}
+                for m, a in enumerate(arrs):
+                    by_base.setdefault(id(a.base) if a.base is not None else ('own', m), []).append(m)
+                loose = []
+                for bi, (key, ms) in enumerate(by_base.items()):
+                    shared = _shared_base([arrs[m] for m in ms])
+                    if shared is None:
+                        loose += ms
+                        continue
                     base, offs, lo, hi = shared
                     src = torch.from_numpy(base[lo:hi])
-                    hb, devbase = stager.get(slot, ('base', gi), (hi - lo,), tdt, host=not src.is_pinned())
-                    _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
+                    hb, devbase = stager.get(slot, ('base', gi, bi), (hi - lo,), tdt, host=not src.is_pinned())
                     with torch.cuda.stream(s_in):
                         if hb is not None:
                             hb.numpy()[...] = base[lo:hi]
                             src = hb
                         devbase.copy_(src, non_blocking=True)
-                        for m, o in enumerate(offs):
+                        for m, o in zip(ms, offs):
                             devbuf[m].copy_(devbase[o - lo:o - lo + n_raw], non_blocking=True)
-                    h2d_bytes[0] += (hi - lo) * src.element_size()
-                else:
-                    srcs = [torch.from_numpy(a) for a in arrs]
+                    h2d_bytes[0] += (hi - lo) * devbase.element_size()
+                if loose:
+                    srcs = [torch.from_numpy(arrs[m]) for m in loose]
                     if all(t.is_pinned() and t.is_contiguous() for t in srcs):
                         # the caller's I/O layer already reads into page-locked memory: DMA straight from it
-                        _, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt, host=False)
                         with torch.cuda.stream(s_in):
-                            for m, t in enumerate(srcs):
+                            for m, t in zip(loose, srcs):
                                 devbuf[m].copy_(t, non_blocking=True)
                     else:
-                        host, devbuf = stager.get(slot, gi, (len(members), n_raw), tdt)
+                        host, devtmp = stager.get(slot, ('loose', gi), (len(loose), n_raw), tdt,
+                                                  device=len(loose) != len(members))
                         hnp = host.numpy()
-                        for m, a in enumerate(arrs):
-                            hnp[m] = a
+                        for k2, m in enumerate(loose):
+                            hnp[k2] = arrs[m]
                         with torch.cuda.stream(s_in):
-                            devbuf.copy_(host, non_blocking=True)
-                    h2d_bytes[0] += len(members) * n_raw * devbuf.element_size()
+                            if len(loose) == len(members):
+                                devbuf.copy_(host, non_blocking=True)
+                            else:
+                                devtmp.copy_(host, non_blocking=True)
+                                devbuf[torch.tensor(loose, device=dev)] = devtmp
+                    h2d_bytes[0] += len(loose) * n_raw * devbuf.element_size()
                 staged.append((prog, devbuf, members, skip, start_final))
             ev_in = torch.cuda.Event()
             ev_in.record(s_in)

@@ -240,9 +240,11 @@ template <class T, int R1, int R2> int prepare() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_INV_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
   if (e != cudaSuccess) return (int)e;
-  if constexpr (R1 == 16)
+  if constexpr (R1 == 16) {
     e = cudaFuncSetAttribute(xcb_pair_product_grouped<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              PairGrouped<T, R1, R2>::SMEM);
+    if (e != cudaSuccess) return (int)e;
+  }
   return (int)e;
 }
 

@@ -305,12 +305,12 @@ XCB_HD void twiddle_chain(const PassParams<T>& p, uint32_t e0, uint32_t de, cx<T
 }
 
 // v[r] <- v[r] * w^r, r = 1..R-1 (stage-2 twiddles W_N^(r*j), w = W_N^j)
-template <int R, class T> XCB_HD void twiddle_powers(cx<T> w, cx<T>* v) {
+template <int R, bool PK = false, class T> XCB_HD void twiddle_powers(cx<T> w, cx<T>* v) {
   cx<T> wr = w;
 #pragma unroll
   for (int r = 1; r < R; ++r) {
-    v[r] = cmul(v[r], wr);
-    if (r + 1 < R) wr = cmul(wr, w);
+    v[r] = xmul<PK>(v[r], wr);
+    if (r + 1 < R) wr = xmul<PK>(wr, w);
   }
 }
 
@@ -821,6 +821,9 @@ template <class T, int R1, int R2> struct RowWarp {
   template <int MODE> static XCB_HD bool is_pro(const PassParams<T>& p) {
     return MODE == 0 ? p.load_mode == RL_PROLOGUE : MODE == 2;
   }
+  // the pair-product kernels (MODE 2) are bound by instruction issue: packed f32x2 complex arithmetic there
+  // (xcb_types.h); the forward pass measured slower with it (1.34 -> 1.40 ms) and keeps the scalar form
+  template <int MODE> struct Pk { static constexpr bool value = MODE == 2; };
 
   struct Slot {
     int64_t batch, row;
@@ -874,7 +877,7 @@ template <class T, int R1, int R2> struct RowWarp {
   // v[r] += sw * a[r R2] * conj(b[r R2]), r < R1: this lane's share of one term
   // (block / stacked window) of the cross-spectrum; a, b point at the lane's first
   // element of the two rows (global memory, or rows staged in shared memory)
-  template <bool SCALED>
+  template <bool SCALED, bool PK>
   static XCB_HD void accumulate_t(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw) {
     constexpr int H = R1 / 2;                       // two batches of loads bound the registers
 #pragma unroll
@@ -883,17 +886,15 @@ template <class T, int R1, int R2> struct RowWarp {
 #pragma unroll
       for (int r = 0; r < H; ++r) { a[r] = a_row[(h * H + r) * R2]; b[r] = b_row[(h * H + r) * R2]; }
 #pragma unroll
-      for (int r = 0; r < H; ++r) {
-        const T ax = SCALED ? a[r].x * sw : a[r].x, ay = SCALED ? a[r].y * sw : a[r].y;
-        v[h * H + r].x += ax * b[r].x + ay * b[r].y;
-        v[h * H + r].y += ay * b[r].x - ax * b[r].y;
-      }
+      for (int r = 0; r < H; ++r)
+        v[h * H + r] = xmulc_acc<PK>(SCALED ? xscale<PK>(a[r], sw) : a[r], b[r], v[h * H + r]);   // += a conj(b)
     }
   }
   // `scaled`: per-term norms (stacked windows); else the single scale is applied after the sum
+  template <bool PK = false>
   static XCB_HD void accumulate(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw, bool scaled = true) {
-    if (scaled) accumulate_t<true>(v, a_row, b_row, sw);
-    else accumulate_t<false>(v, a_row, b_row, sw);
+    if (scaled) accumulate_t<true, PK>(v, a_row, b_row, sw);
+    else accumulate_t<false, PK>(v, a_row, b_row, sw);
   }
 
   // slot 0 of a spectrum holds (X[0], X[M]), both real: C[0] and C[M] are plain products
@@ -926,7 +927,7 @@ template <class T, int R1, int R2> struct RowWarp {
           int64_t oi, oj;
           T sw;
           term(p, jb, w, per_term, oi, oj, sw);
-          accumulate(v, z + oi, z + oj, sw, per_term);
+          accumulate<Pk<MODE>::value>(v, z + oi, z + oj, sw, per_term);
         }
         if (s.row0 && s.j == 0) v[0] = packed_dc(p, jb, per_term);
 #pragma unroll
@@ -950,11 +951,11 @@ template <class T, int R1, int R2> struct RowWarp {
   }
 
   // stage 2: read the stage layout, inner twiddles, radix-R2 -> v[r] = element j + R1 r
-  static XCB_HD void stage2(const PassParams<T>& p, const Slot& s, cx<T>* v) {
+  template <bool PK = false> static XCB_HD void stage2(const PassParams<T>& p, const Slot& s, cx<T>* v) {
 #pragma unroll
     for (int r = 0; r < R2; ++r) v[r] = s.buf[r * P1 + s.j];
-    twiddle_powers<R2>(ld_ro(p.tw_inner + s.j), v);
-    fft_reg<R2>(v);
+    twiddle_powers<R2, PK>(ld_ro(p.tw_inner + s.j), v);
+    fft_reg<R2, PK>(v);
   }
 
   template <int MODE = 0>
@@ -972,20 +973,20 @@ template <class T, int R1, int R2> struct RowWarp {
       for (int r = 0; r < R1; ++r) {
         const int e = s.j + r * R2;
         const cx<T> cm = s.mbuf[mirror(s, e)];
-        const cx<T> W = cmul(wrow, ld_ro(p.tw2_inner + e));
+        constexpr bool PK = Pk<MODE>::value;
+        const cx<T> W = xmul<PK>(wrow, ld_ro(p.tw2_inner + e));
         // E = C[k] + conj(C[M-k]), D = C[k] - conj(C[M-k]), O = conj(W) D, V = (E + iO)/2; keep fs conj(V)
-        cx<T> E, D;
-        E.x = v[r].x + cm.x; E.y = v[r].y - cm.y;
-        D.x = v[r].x - cm.x; D.y = v[r].y + cm.y;
-        const cx<T> O = cmulc(D, W);
-        cx<T> o;
-        o.x = fs * (E.x - O.y); o.y = -fs * (E.y + O.x);
+        const cx<T> cmc = cconj(cm);
+        const cx<T> E = xadd<PK>(v[r], cmc), D = xsub<PK>(v[r], cmc);
+        const cx<T> O = xmulc<PK>(D, W);
+        cx<T> o = xscale<PK>(xadd<PK>(E, cpi(O)), fs);   // fs (E + iO) ...
+        o.y = -o.y;                                       // ... conjugated
         if (r == 0 && s.row0 && s.j == 0) {          // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
           o.x = fs * (v[0].x + v[0].y); o.y = -fs * (v[0].x - v[0].y);
         }
         v[r] = o;
       }
-      fft_reg<R1>(v);
+      fft_reg<R1, Pk<MODE>::value>(v);
     } else {
       stage2(p, s, v);
     }
@@ -1010,7 +1011,7 @@ template <class T, int R1, int R2> struct RowWarp {
     cx<T>* v = ctx.v;
     if (s.active) {
       if (is_pro<MODE>(p)) {
-        stage2(p, s, v);
+        stage2<Pk<MODE>::value>(p, s, v);
         if (p.store_mode == RS_EPI) {
           T* outp = p.ccf + p.jobs[s.batch].out_off;
 #pragma unroll

@@ -166,70 +166,94 @@ template <int S> __device__ __forceinline__ double cascade(const SosRegs<S>& f, 
   return v;
 }
 
-constexpr int kIlp = 1;   // chunks per thread
+constexpr int kIlp = 1;   // chunks per thread (the dispatch below sizes its grids with it)
 constexpr int kBatch = 8; // samples fetched ahead per thread: the loads leave the serial recurrence's critical path
 
-// phase 1: zero-state final state of every chunk (thread q owns chunks kIlp*q ... kIlp*q + kIlp-1)
+// One chunk of one signal through the cascade, from state z.  Everything that does not change inside a chunk
+// is decided once per chunk so that a sample costs its 5 S multiply-adds plus a handful of instructions (the
+// first version re-derived 64-bit indices, bounds, taper membership and `t / decimate` per sample: 160
+// instructions per sample, two thirds of them integer -- profiles/ncu_r02_preprocess.md):
+//   * 32-bit sample indices (a trace holds < 2^31 samples), a running double for the trend's abscissa;
+//   * chunks that touch no taper ramp (all but ~15 per trace) skip the taper test;
+//   * full batches of kBatch samples run unguarded, the ragged end of the last chunk separately;
+//   * kept (decimated) samples are tracked with a counter instead of a division.
+// MODE 1: phase 1 -- zero-state pass; writes the kept zero-state outputs to yzs when given.
+// MODE 3: phase 3 -- true start state; stores the (kept) outputs to y.
+template <int S, class TI, class TO, int MODE>
+__device__ __forceinline__ void scan_chunk(const TI* __restrict__ xi, int n, int t0, int len, const SosRegs<S>& fr,
+                                           double (&z)[2 * S], const PointwiseDev& pw, double c0, double c1,
+                                           int reverse, int decim, double* __restrict__ yz, TO* __restrict__ yo) {
+  const int dir = reverse ? -1 : 1;
+  int i = reverse ? n - 1 - t0 : t0;                       // signal index of the chunk's first sample
+  const TI* px = xi + i;
+  // does the chunk touch a taper ramp?
+  const int i_lo = reverse ? i - (len - 1) : i, i_hi = reverse ? i : i + (len - 1);
+  const bool ramps = i_lo < pw.taper_left || i_hi >= n - pw.taper_right;
+  const bool trend = pw.detrend != 0;
+  double di = (double)i;
+  const double ddir = (double)dir;
+  int next_keep = ((t0 + decim - 1) / decim) * decim - t0;  // local index of the first kept sample (once per chunk)
+  int64_t ko = ((int64_t)t0 + decim - 1) / decim;           // its output index
+  auto sample = [&](double v, int jl) {
+    if (trend) v -= fma(c1, di, c0);
+    if (ramps) {
+      const int ii = i + dir * jl;
+      if (ii < pw.taper_left) v *= __ldg(pw.ramp_left + ii);
+      else if (ii >= n - pw.taper_right) v *= __ldg(pw.ramp_right + (ii - (n - pw.taper_right)));
+    }
+    di += ddir;
+    const double y = cascade<S>(fr, z, v);
+    if (MODE == 1) {
+      if (yz && jl == next_keep) { yz[ko++] = y; next_keep += decim; }
+    } else {
+      if (decim == 1) yo[i + dir * jl] = (TO)y;
+      else if (jl == next_keep) { yo[ko++] = (TO)y; next_keep += decim; }
+    }
+  };
+  TI buf[kBatch], nxt[kBatch];
+  const int full = len / kBatch * kBatch;
+  if (full > 0) {
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) buf[b] = __ldg(px + dir * b);
+  }
+  for (int j0 = 0; j0 < full; j0 += kBatch) {
+    if (j0 + kBatch < full) {
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) nxt[b] = __ldg(px + dir * (j0 + kBatch + b));
+    }
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) sample((double)buf[b], j0 + b);
+#pragma unroll
+    for (int b = 0; b < kBatch; ++b) buf[b] = nxt[b];
+  }
+  for (int jl = full; jl < len; ++jl) sample((double)__ldg(px + dir * jl), jl);
+}
+
+// phase 1: zero-state final state of every chunk (one thread per chunk)
 template <int S, class TI>
 __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
                                                   int chunk, int64_t n_chunks, const __grid_constant__ SosCoef<S> f,
                                                   PointwiseDev pw, const double* __restrict__ stats, int reverse,
                                                   double* __restrict__ zstate, double* __restrict__ yzs, int decim,
                                                   int64_t n_out) {
-  const int64_t per_sig = (n_chunks + kIlp - 1) / kIlp;
   const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (gid >= (int64_t)n_signals * per_sig) return;
-  const int sig = (int)(gid / per_sig);
-  const int64_t cb = (gid - (int64_t)sig * per_sig) * kIlp;
+  if (gid >= (int64_t)n_signals * n_chunks) return;
+  const int sig = (int)(gid / n_chunks);
+  const int c = (int)(gid - (int64_t)sig * n_chunks);
   double c0, c1;
   trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
-  const TI* xi = x + (int64_t)sig * xs;
   SosRegs<S> fr;
   load_coefficients<S>(f, fr);
-  double z[kIlp][2 * S];
+  double z[2 * S];
 #pragma unroll
-  for (int u = 0; u < kIlp; ++u)
+  for (int k = 0; k < 2 * S; ++k) z[k] = 0.0;
+  const int t0 = c * chunk;
+  const int len = (int)n - t0 < chunk ? (int)n - t0 : chunk;
+  scan_chunk<S, TI, double, 1>(x + (int64_t)sig * xs, (int)n, t0, len, fr, z, pw, c0, c1, reverse, decim,
+                               yzs ? yzs + (int64_t)sig * n_out : nullptr, (double*)nullptr);
+  double* out = zstate + ((int64_t)sig * n_chunks + c) * (2 * S);
 #pragma unroll
-    for (int k = 0; k < 2 * S; ++k) z[u][k] = 0.0;
-  TI buf[kIlp][kBatch], nxt[kIlp][kBatch];
-  auto fetch = [&](TI (&dst)[kIlp][kBatch], int j0) {
-#pragma unroll
-    for (int u = 0; u < kIlp; ++u)
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int64_t t = (cb + u) * chunk + j0 + b;
-        dst[u][b] = (j0 + b < chunk && t < n) ? __ldg(xi + (reverse ? n - 1 - t : t)) : TI(0);
-      }
-  };
-  fetch(buf, 0);
-  for (int j0 = 0; j0 < chunk; j0 += kBatch) {
-    fetch(nxt, j0 + kBatch);
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b)
-#pragma unroll
-      for (int u = 0; u < kIlp; ++u) {
-        const int64_t t = (cb + u) * chunk + j0 + b;
-        if (j0 + b < chunk && t < n) {
-          const int64_t i = reverse ? n - 1 - t : t;
-          const double v = cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
-          // decimating cascades keep the zero-state output of the kept samples (chunk % decim == 0, so the
-          // kept local indices are the same in every chunk); phase 3 adds the zero-input response
-          if (yzs && (j0 + b) % decim == 0) yzs[(int64_t)sig * n_out + t / decim] = v;
-        }
-      }
-#pragma unroll
-    for (int u = 0; u < kIlp; ++u)
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) buf[u][b] = nxt[u][b];
-  }
-#pragma unroll
-  for (int u = 0; u < kIlp; ++u) {
-    if (cb + u < n_chunks) {
-      double* out = zstate + ((int64_t)sig * n_chunks + cb + u) * (2 * S);
-#pragma unroll
-      for (int k = 0; k < 2 * S; ++k) out[k] = z[u][k];
-    }
-  }
+  for (int k = 0; k < 2 * S; ++k) out[k] = z[k];
 }
 
 // phase 3: rerun every chunk from its true start state and store
@@ -239,101 +263,75 @@ __global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int6
                                                   const __grid_constant__ SosCoef<S> f, PointwiseDev pw,
                                                   const double* __restrict__ stats, int reverse, int decim,
                                                   const double* __restrict__ sstart) {
-  const int64_t per_sig = (n_chunks + kIlp - 1) / kIlp;
   const int64_t gid = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (gid >= (int64_t)n_signals * per_sig) return;
-  const int sig = (int)(gid / per_sig);
-  const int64_t cb = (gid - (int64_t)sig * per_sig) * kIlp;
+  if (gid >= (int64_t)n_signals * n_chunks) return;
+  const int sig = (int)(gid / n_chunks);
+  const int c = (int)(gid - (int64_t)sig * n_chunks);
   double c0, c1;
   trend_coefficients(pw, stats ? stats + sig * 4 : nullptr, n, c0, c1);
-  const TI* xi = x + (int64_t)sig * xs;
-  TO* yo = y + (int64_t)sig * ys;
   SosRegs<S> fr;
   load_coefficients<S>(f, fr);
-  double z[kIlp][2 * S];
-  int64_t next_keep[kIlp];
+  double z[2 * S];
+  const double* in = sstart + ((int64_t)sig * n_chunks + c) * (2 * S);
 #pragma unroll
-  for (int u = 0; u < kIlp; ++u) {
-    const int64_t c = cb + u < n_chunks ? cb + u : n_chunks - 1;
-    const double* in = sstart + ((int64_t)sig * n_chunks + c) * (2 * S);
-#pragma unroll
-    for (int k = 0; k < 2 * S; ++k) z[u][k] = in[k];
-    next_keep[u] = ((cb + u) * (int64_t)chunk + decim - 1) / decim * decim;   // first t >= t0 with t % decim == 0
-  }
-  TI buf[kIlp][kBatch], nxt[kIlp][kBatch];
-  auto fetch = [&](TI (&dst)[kIlp][kBatch], int j0) {
-#pragma unroll
-    for (int u = 0; u < kIlp; ++u)
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) {
-        const int64_t t = (cb + u) * chunk + j0 + b;
-        dst[u][b] = (j0 + b < chunk && t < n) ? __ldg(xi + (reverse ? n - 1 - t : t)) : TI(0);
-      }
-  };
-  fetch(buf, 0);
-  for (int j0 = 0; j0 < chunk; j0 += kBatch) {
-    fetch(nxt, j0 + kBatch);
-#pragma unroll
-    for (int b = 0; b < kBatch; ++b)
-#pragma unroll
-      for (int u = 0; u < kIlp; ++u) {
-        const int64_t t = (cb + u) * chunk + j0 + b;
-        if (j0 + b < chunk && t < n) {
-          const int64_t i = reverse ? n - 1 - t : t;
-          const double v = cascade<S>(fr, z[u], pointwise_value(pw, (double)buf[u][b], i, n, c0, c1));
-          if (decim == 1) {
-            yo[i] = (TO)v;
-          } else if (t == next_keep[u]) {
-            yo[t / decim] = (TO)v;
-            next_keep[u] += decim;
-          }
-        }
-      }
-#pragma unroll
-    for (int u = 0; u < kIlp; ++u)
-#pragma unroll
-      for (int b = 0; b < kBatch; ++b) buf[u][b] = nxt[u][b];
-  }
+  for (int k = 0; k < 2 * S; ++k) z[k] = in[k];
+  const int t0 = c * chunk;
+  const int len = (int)n - t0 < chunk ? (int)n - t0 : chunk;
+  scan_chunk<S, TI, TO, 3>(x + (int64_t)sig * xs, (int)n, t0, len, fr, z, pw, c0, c1, reverse, decim,
+                           (double*)nullptr, y + (int64_t)sig * ys);
 }
 
 // phase 3 of a DECIMATING cascade: by linearity the true output is the zero-state output phase 1
 // kept (yzs) plus the zero-input response of the chunk's start state, y[r] = yzs[r] + sum_k G[r][k] s0[k],
 // with G the response of the kept local samples to unit start states (host: scipy, like the carry
-// matrices).  d multiply-adds per kept sample instead of rerunning 5 S per input sample.  Thread q owns
-// chunk q; the block keeps G in shared memory and all lanes read the same row (broadcast).
+// matrices).  d multiply-adds per kept sample instead of rerunning 5 S per input sample.
 // A block takes kZinChunks consecutive chunks of one signal: their kept outputs are contiguous, so
-// the threads walk them coalesced; G (row pitch d + 1: conflict free) and the chunks' start states sit
-// in shared memory.
-constexpr int kZinChunks = 32;
+// the threads (one per kept local sample) walk them coalesced.
+constexpr int kZinChunks = 64;
 template <class TO>
 __global__ void __launch_bounds__(128) sos_phase3_zin(const double* __restrict__ yzs, TO* __restrict__ y, int64_t ys,
                                                       int64_t n_out, int rows, int64_t n_chunks, int d,
                                                       const double* __restrict__ G,
                                                       const double* __restrict__ sstart) {
-  extern __shared__ double zin_sm[];                     // G [rows][d + 1], then s0 [kZinChunks][d]
-  double* g_sm = zin_sm;
-  double* s_sm = zin_sm + rows * (d + 1);
+  // A thread owns ONE kept local sample r: its row of G stays in registers (zero padded to 24) while the block
+  // walks kZinChunks chunks, whose start states sit in shared memory and are read as warp-wide broadcasts.
+  // (First version: G and the states both in shared memory -- two shared loads per multiply-add, 222 us for
+  // 308 MB, short_scoreboard the top stall; profiles/ncu_r02_preprocess.md.)
+  extern __shared__ double zin_sm[];                     // s0 [kZinChunks][24]
   const int64_t blocks_per_sig = (n_chunks + kZinChunks - 1) / kZinChunks;
   const int sig = (int)(blockIdx.x / blocks_per_sig);
   const int64_t c0 = (blockIdx.x - (int64_t)sig * blocks_per_sig) * kZinChunks;
   const int nc = (int)(n_chunks - c0 < kZinChunks ? n_chunks - c0 : kZinChunks);
-  for (int i = threadIdx.x; i < rows * d; i += 128) g_sm[(i / d) * (d + 1) + i % d] = G[i];
   const double* in = sstart + ((int64_t)sig * n_chunks + c0) * d;
-  for (int i = threadIdx.x; i < nc * d; i += 128) s_sm[i] = in[i];
+  for (int i = threadIdx.x; i < nc * 24; i += 128) {
+    const int c = i / 24, k = i - c * 24;
+    zin_sm[i] = k < d ? in[c * d + k] : 0.0;
+  }
   __syncthreads();
   const double* src = yzs + (int64_t)sig * n_out;
   TO* dst = y + (int64_t)sig * ys;
-  const int64_t o0 = c0 * rows;
-  const int count = nc * rows;
-  for (int o = threadIdx.x; o < count && o0 + o < n_out; o += 128) {
-    const int c = o / rows, r = o - c * rows;
-    const double* g = g_sm + r * (d + 1);
-    const double* s0 = s_sm + c * d;
-    double a0 = src[o0 + o], a1 = 0.0;
-    int k = 0;
-    for (; k + 1 < d; k += 2) { a0 = fma(g[k], s0[k], a0); a1 = fma(g[k + 1], s0[k + 1], a1); }
-    if (k < d) a0 = fma(g[k], s0[k], a0);
-    dst[o0 + o] = (TO)(a0 + a1);
+  for (int r = threadIdx.x; r < rows; r += 128) {
+    double g[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) g[k] = k < d ? __ldg(G + (int64_t)r * d + k) : 0.0;
+    int64_t o = c0 * rows + r;
+    double cur = o < n_out ? src[o] : 0.0;
+    for (int c = 0; c < nc; ++c, o += rows) {
+      const int64_t on = o + rows;
+      const double nxt = (c + 1 < nc && on < n_out) ? src[on] : 0.0;      // next zero-state output in flight
+      const double2* s0 = reinterpret_cast<const double2*>(zin_sm + c * 24);
+      double a0 = cur, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 24; k += 4) {
+        const double2 p0 = s0[k / 2], p1 = s0[k / 2 + 1];
+        a0 = fma(g[k], p0.x, a0);
+        a1 = fma(g[k + 1], p0.y, a1);
+        a2 = fma(g[k + 2], p1.x, a2);
+        a3 = fma(g[k + 3], p1.y, a3);
+      }
+      if (o < n_out) dst[o] = (TO)((a0 + a1) + (a2 + a3));
+      cur = nxt;
+    }
   }
 }
 
@@ -629,6 +627,7 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   if (f->n_sections < 1 || f->n_sections > kMaxSections || f->chunk < 1 || f->decimate < 1) return XCB_ERR_ARG;
   if (!f->carry || !f->carry_group) return XCB_ERR_ARG;
   if (f->reverse && f->decimate != 1) return XCB_ERR_UNSUPPORTED;
+  if (n >= 2147483647LL) return XCB_ERR_UNSUPPORTED;             // the scan indexes samples with 32 bits
   if (pre && pre->detrend && !stats) return XCB_ERR_ARG;
   if (pre && pre->taper_left + pre->taper_right > n) return XCB_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -648,8 +647,7 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   a.reverse = f->reverse; a.decim = f->decimate; a.zstate = dz; a.sstart = ds; a.coef = f->coef;
   if (f->zin_response && (f->decimate < 2 || f->chunk % f->decimate != 0 || f->reverse)) return XCB_ERR_ARG;
   // the fast path keeps the response table in (default-sized) shared memory; else rerun the cascade
-  const bool zin = f->zin_response != nullptr &&
-                   sizeof(double) * ((size_t)(f->chunk / f->decimate) * (L.d + 1) + (size_t)kZinChunks * L.d) <= 48 * 1024;
+  const bool zin = f->zin_response != nullptr;
   a.yzs = zin ? reinterpret_cast<double*>(ws + L.off_y) : nullptr;
   a.n_out = L.n_out;
   a.zin = f->zin_response;
@@ -662,7 +660,7 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   if (zin) {
     const int rows = f->chunk / f->decimate;
     const int64_t blocks_per_sig = (L.n_chunks + kZinChunks - 1) / kZinChunks;
-    const size_t smem = sizeof(double) * ((size_t)rows * (L.d + 1) + (size_t)kZinChunks * L.d);
+    const size_t smem = sizeof(double) * (size_t)kZinChunks * 24;
     const unsigned grid = (unsigned)((int64_t)n_signals * blocks_per_sig);
     if (dtype_out == XCB_F32)
       sos_phase3_zin<float><<<grid, 128, smem, st>>>(a.yzs, static_cast<float*>(y), y_stride, L.n_out, rows, L.n_chunks,

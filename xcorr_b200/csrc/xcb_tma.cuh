@@ -453,7 +453,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
         T sw = T(1);
         if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
-        W::accumulate(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw, per_term);
+        W::template accumulate<true>(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw, per_term);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[buf]);       // this warp is done with the buffer (and its mail)
