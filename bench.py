@@ -20,7 +20,7 @@ Printed JSON line:
                 the timed region, against the PCIe ceiling measured in the same run
   roofline      dominant kernel vs the measured HBM peak (traffic: ncu capture under profiles/)
   step_roofline whole step vs SURVEY 8d's minimal-traffic model
-  configs       short legs of the other named configurations (cfg3/f64, cfg2, cfg4, cfg5)
+  configs       short legs of the other named configurations (cfg1, cfg3/f64, cfg2, cfg4, cfg5)
   cpu_baseline  the reference's own xcorr/util/cc.py (oracle/_ref) on the host cores, FULL-SIZE windows
 
 `--impl reference` times the reference's util/cc.py alone (full-size 24 h @ 250 Hz windows, one
@@ -309,6 +309,7 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
     peak, _ = peaks()
     out = {"workload": name}
     extra = {}
+    sub_timers = {}
     if name in ("cfg3_f64", "cfg3_full"):
         dt = torch.float64 if name == "cfg3_f64" else torch.float32
         b = 8 if dt == torch.float64 else 4
@@ -327,6 +328,18 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         alg = b_alg(R, len(pairs), n, K, b)
         extra = dict(passes=list(plan.dims), blocks=plan.n_blocks)
         desc = f"16 receivers / 120 pairs, 24h@250Hz, K={K}"
+    elif name in ("cfg1", "cfg1_f32"):
+        dt = torch.float64 if name == "cfg1" else torch.float32
+        b = 8 if dt == torch.float64 else 4
+        n, R, K = 4_320_000, 2, 1_620_000
+        pairs = [(0, 1)]
+        plan = xb.CorrelationPlan(n, R, pairs, dtype=dt, index_min=n - 1, index_max=n - 1 + K, device=dev)
+        x = make_inputs(torch, R, n, dev, dt, 1 + rank)
+        step, _ = plan.graphed(x)                   # ten ~15 us kernels: one graph launch instead of ten launches
+        units, unit = 1, "pair-days/s"
+        alg = b_alg(R, 1, n, K, b)
+        extra = dict(passes=list(plan.dims), blocks=plan.n_blocks, launch="CUDA graph replay of forward + correlate")
+        desc = "1 pair, 24h@50Hz, lags (0, 9h) (the reference's CPU-runnable case)"
     elif name in ("cfg2", "cfg2_f64"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
         b = 8 if dt == torch.float64 else 4
@@ -339,6 +352,7 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
 
         def step():
             plan(prog.run(raw))
+        sub_timers["ms_preprocess"] = lambda: prog.run(raw)
         units, unit = len(pairs), "pair-days/s"
         alg = b_alg(R, len(pairs), n, 1_620_000, b, n_raw)
         extra = dict(passes=list(plan.dims), blocks=plan.n_blocks)
@@ -414,6 +428,15 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
     barrier()
     ms = e0.elapsed_time(e1) / steps
     clocks = sampler.result()
+    for key, fn in sub_timers.items():               # parts of the step, timed on their own afterwards
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b2.record()
+        torch.cuda.synchronize()
+        extra[key] = a.elapsed_time(b2) / steps
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -512,7 +535,7 @@ def run_gpu(args):
     # ---------------- the other named configurations (short legs) ----------------
     legs = []
     if not args.no_legs and args.workload == "cfg3" and args.dtype == "f32":
-        for name in ("cfg3_f64", "cfg2", "cfg4", "cfg5"):
+        for name in ("cfg1", "cfg3_f64", "cfg2", "cfg4", "cfg5"):
             try:
                 legs.append(config_leg(name, torch, dev, 3, 2, rank, world, dist))
             except Exception as error:                      # a leg must not take the headline down

@@ -830,6 +830,9 @@ template <class T, int R1, int R2> struct RowWarp {
     cx<T>* buf;        // this half's row buffer
     const cx<T>* mbuf; // buffer holding the mirrored row
     cx<T> wrow;        // W_L^klow(row): half-step twiddle of the row's leading digits
+    cx<T> w_inner;     // W_N^j: inner twiddle of the second radix stage
+    const cx<T>* tw2;  // W_2N^e table (global, or the grouped kernel's shared-memory copy)
+    T fs;              // pair product: scale of the job when known up front, < 0: derive from the norms
     int j;
     bool active;       // this half-warp has a row
     bool row0;         // row 0 mirrors itself with e -> (N - e) mod N
@@ -856,6 +859,9 @@ template <class T, int R1, int R2> struct RowWarp {
     s.mbuf = base + (self ? col : (col ^ 1)) * COLBUF;
     s.wrow.x = T(1); s.wrow.y = T(0);
     if (s.active) s.wrow = row_twiddle(p, s.row);
+    s.w_inner = ld_ro(p.tw_inner + s.j);
+    s.tw2 = p.tw2_inner;
+    s.fs = T(-1);
     return s;
   }
   static XCB_HD double* red_ptr(unsigned char* smem_raw) {
@@ -954,7 +960,7 @@ template <class T, int R1, int R2> struct RowWarp {
   template <bool PK = false> static XCB_HD void stage2(const PassParams<T>& p, const Slot& s, cx<T>* v) {
 #pragma unroll
     for (int r = 0; r < R2; ++r) v[r] = s.buf[r * P1 + s.j];
-    twiddle_powers<R2, PK>(ld_ro(p.tw_inner + s.j), v);
+    twiddle_powers<R2, PK>(s.w_inner, v);
     fft_reg<R2, PK>(v);
   }
 
@@ -964,17 +970,20 @@ template <class T, int R1, int R2> struct RowWarp {
     if (!s.active) return;
     if (is_pro<MODE>(p)) {
       if (s.j >= R2) return;
-      const Job jb = p.jobs[s.batch];
-      const bool per_term = p.normalize && p.stack_sig_stride != 0;
-      T fs = T(0.5);
-      if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
+      T fs = s.fs;
+      if (fs < T(0)) {
+        const Job jb = p.jobs[s.batch];
+        const bool per_term = p.normalize && p.stack_sig_stride != 0;
+        fs = T(0.5);
+        if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
+      }
       const cx<T> wrow = s.wrow;
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         const int e = s.j + r * R2;
         const cx<T> cm = s.mbuf[mirror(s, e)];
         constexpr bool PK = Pk<MODE>::value;
-        const cx<T> W = xmul<PK>(wrow, ld_ro(p.tw2_inner + e));
+        const cx<T> W = xmul<PK>(wrow, s.tw2[e]);
         // E = C[k] + conj(C[M-k]), D = C[k] - conj(C[M-k]), O = conj(W) D, V = (E + iO)/2; keep fs conj(V)
         const cx<T> cmc = cconj(cm);
         const cx<T> E = xadd<PK>(v[r], cmc), D = xsub<PK>(v[r], cmc);
@@ -1041,7 +1050,7 @@ template <class T, int R1, int R2> struct RowWarp {
         for (int r = 0; r < R2; ++r) {
           const int k = s.j + r * R1;
           const cx<T> zm = s.mbuf[mirror(s, k)];
-          const cx<T> W = cmul(wrow, ld_ro(p.tw2_inner + k));
+          const cx<T> W = cmul(wrow, s.tw2[k]);
           cx<T> S, D;
           S.x = v[r].x + zm.x; S.y = v[r].y - zm.y;
           D.x = v[r].x - zm.x; D.y = v[r].y + zm.y;

@@ -306,8 +306,22 @@ template <class T, int R1, int R2> struct PairGrouped {
   static constexpr int EXCH_OFF = NBUF * STAGE_BYTES;
   static constexpr int BAR_OFF = EXCH_OFF + C * W::COLBUF * 2 * (int)sizeof(T);
   static constexpr int MAIL_OFF = BAR_OFF + 64;
-  static constexpr int SMEM = MAIL_OFF + NBUF * 64;
-  static constexpr bool kOk = (ROW_BYTES % 16) == 0 && SMEM <= 113 * 1024 && 2 * MAX_ROWS <= 32;   // two CTAs per SM
+  // per-CTA tables (filled once): the half-step twiddles W_2N^e of the row axis and, when the launch has few
+  // enough groups, one record per (group, consumer warp) -- so that an item starts from shared memory
+  // instead of a chain of dependent global loads (group -> job -> norms)
+  static constexpr int TW2_OFF = MAIL_OFF + NBUF * 64;
+  static constexpr int REC_OFF = TW2_OFF + N * 2 * (int)sizeof(T);
+  static constexpr int SMEM_MAX = (227 * 1024 - 2 * 1024) / 2;                                    // two CTAs per SM
+  static constexpr int MAX_REC_GROUPS = (SMEM_MAX - REC_OFF) / (WARPS * 16) > 0 ? (SMEM_MAX - REC_OFF) / (WARPS * 16) : 0;
+  static constexpr int SMEM = REC_OFF + MAX_REC_GROUPS * WARPS * 16;
+  static constexpr bool kOk = (ROW_BYTES % 16) == 0 && REC_OFF <= SMEM_MAX && 2 * MAX_ROWS <= 32;
+};
+
+// what a consumer warp needs to know about its job of a group (shared-memory copy of PairGroup / Job / norms)
+struct alignas(16) PairRec {
+  int32_t batch;        // job index within the launch, -1: this warp has no job in the group
+  uint8_t row_i, row_j, pad0, pad1;
+  double fs;            // 0.5 / (||x_i|| ||x_j||) (0.5 when not normalised or when the norms are per term)
 };
 
 // what the producer tells the consumers about the item whose first term sits in a buffer
@@ -337,6 +351,27 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   if (tid == 0) {
     for (int b = 0; b < NBUF; ++b) { mbar_init(&full[b], 1); mbar_init(&empty[b], K::WARPS); }
     fence_barrier_init();
+  }
+  cx<T>* tw2 = reinterpret_cast<cx<T>*>(smem_raw + K::TW2_OFF);
+  PairRec* recs = reinterpret_cast<PairRec*>(smem_raw + K::REC_OFF);
+  const bool per_term_all = p.normalize && p.stack_sig_stride != 0;
+  const bool use_recs = p.n_groups <= K::MAX_REC_GROUPS;
+  for (int i = tid; i < N; i += K::THREADS) tw2[i] = ld_ro(p.tw2_inner + i);
+  if (use_recs) {
+    for (int i = tid; i < p.n_groups * K::WARPS; i += K::THREADS) {
+      const PairGroup& g = p.groups[i / K::WARPS];
+      const int w = i % K::WARPS;
+      PairRec r;
+      r.batch = -1; r.row_i = r.row_j = r.pad0 = r.pad1 = 0; r.fs = 0.5;
+      if (w < g.n_jobs) {
+        r.batch = g.job[w];
+        r.row_i = g.ji[w];
+        r.row_j = (uint8_t)(g.n_i + g.jj[w]);
+        const Job jb = p.jobs[r.batch];
+        if (p.normalize && !per_term_all) r.fs = 0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j];
+      }
+      recs[i] = r;
+    }
   }
   __syncthreads();
 
@@ -416,30 +451,48 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   ctx.tid = tid;
   uint32_t step = 0;
   const bool per_term = p.normalize && p.stack_sig_stride != 0;
+  const cx<T> w_inner = ld_ro(p.tw_inner + (tid & 15));             // W_N^j of this lane, item independent
   for (;;) {
     int buf = (int)(step % NBUF);
-    mbar_wait_backoff(&full[buf], (step / NBUF) & 1u);
+    mbar_wait(&full[buf], (step / NBUF) & 1u);         // (no back-off: a sleeping warp wakes up to 0.5 us late)
     const int64_t item = mail[buf].item;
     if (item < 0) break;
     const int64_t ra = mail[buf].ra, rb = mail[buf].rb;
     const int64_t q = item / p.n_groups;
-    const PairGroup& g = p.groups[item - q * p.n_groups];
+    const int gi = (int)(item - q * p.n_groups);
     const bool self = ra == rb;
     typename W::Slot s;
-    const bool has_job = warp < g.n_jobs;
-    s.batch = has_job ? g.job[warp] : 0;
+    bool has_job;
+    int row_i, row_j;
+    T fs_rec = T(0.5);
+    if (use_recs) {
+      const PairRec rec = recs[gi * K::WARPS + warp];
+      has_job = rec.batch >= 0;
+      s.batch = has_job ? rec.batch : 0;
+      row_i = rec.row_i; row_j = rec.row_j;
+      fs_rec = (T)rec.fs;
+    } else {
+      const PairGroup& g = p.groups[gi];
+      has_job = warp < g.n_jobs;
+      s.batch = has_job ? g.job[warp] : 0;
+      row_i = has_job ? g.ji[warp] : 0; row_j = has_job ? g.n_i + g.jj[warp] : 0;
+    }
     s.row = side ? rb : ra;
     s.row0 = ra == 0;
     s.j = tid & 15;
     s.active = has_job && !(side && self);
     s.wrow = mail[buf].wrow[side];
+    s.w_inner = w_inner;
+    s.tw2 = tw2;
+    s.fs = (use_recs && !per_term) ? fs_rec : T(-1);
     const int col = tid >> 4;
     s.buf = exch + col * W::COLBUF;
     s.mbuf = exch + (self ? col : (col ^ 1)) * W::COLBUF;
     ctx.bid = item;
     const bool lane_on = s.active && s.j < R2;
-    const Job jb = p.jobs[s.batch];
-    const int row_i = has_job ? g.ji[warp] : 0, row_j = has_job ? g.n_i + g.jj[warp] : 0;
+    Job jb;
+    jb.spec_i = jb.spec_j = 0; jb.out_off = 0; jb.sig_i = jb.sig_j = 0;
+    if (!use_recs || per_term || s.row0) jb = p.jobs[s.batch];      // (row 0 reads the spectra's slot 0 directly)
 
     cx<T>* v = ctx.v;
 #pragma unroll
@@ -447,7 +500,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     for (int w = 0; w < n_terms; ++w, ++step) {
       if (w > 0) {
         buf = (int)(step % NBUF);
-        mbar_wait_backoff(&full[buf], (step / NBUF) & 1u);
+        mbar_wait(&full[buf], (step / NBUF) & 1u);
       }
       if (lane_on) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;

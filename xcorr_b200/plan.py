@@ -205,3 +205,25 @@ class CorrelationPlan:
     def __call__(self, x, out=None):
         self.forward(x)
         return self.correlate(out)
+
+    def graphed(self, x, out=None):
+        """Capture ``forward(x)`` + ``correlate(out)`` into a CUDA graph on static buffers and return
+        ``(replay, out)``: ``replay()`` re-runs the whole step with one launch.  Small windows (config 1: ten
+        kernels of ~15 us) are bound by launch gaps, not by the kernels; the captured step removes them.  `x` and
+        `out` must keep their addresses (refill `x` in place between replays)."""
+        shape = (len(self.pairs), self.n_lags) if self.stack else (len(self.pairs), self.n_windows, self.n_lags)
+        if out is None:
+            out = (torch.zeros if self.stack else torch.empty)(shape, dtype=self.dtype, device=self.device)
+        with torch.cuda.device(self.device):
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                 # warm-up outside the capture (lazy module loading)
+                self.forward(x)
+                self.correlate(out=out)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.forward(x)
+                self.correlate(out=out)
+        self._graph = graph
+        return graph.replay, out
