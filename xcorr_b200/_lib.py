@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxcorr_b200.so")
+# XCB_LIB: another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("XCB_LIB") or os.path.join(_HERE, "libxcorr_b200.so")
 
 XCB_F32, XCB_F64 = 0, 1
 XCB_OK = 0

@@ -331,6 +331,11 @@ template <class T> struct alignas(64) PairMail {
   cx<T> wrow[2];
 };
 
+// (Two CTAs per SM: ptxas budgets 96 registers for the float kernel -- the register file is allocated for an even
+// number of warps, so the 9 warps count as 10; __maxnreg__(112) leaves ONE CTA per SM: 3.9 -> 5.7 ms.  Forcing the
+// staged-row loads of the accumulate phase 2 / 4 / 8 elements ahead of their multiply-adds with volatile shared loads
+// (ncu shows ptxas reusing one register pair per element: LDS, FFMA2, FFMA2, LDS ...) spills at 96 registers and
+// measured 4.38 / 4.09 / 4.31 ms against 3.91 ms for the compiler's own schedule.)
 template <class T, int R1, int R2>
 __global__ void __launch_bounds__(PairGrouped<T, R1, R2>::THREADS, 2)
 xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
