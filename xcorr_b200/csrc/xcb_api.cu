@@ -568,7 +568,8 @@ static int correlate_argmax_t(const xcb_plan* pl, const void* spec, const double
   xcb_rnorm<<<(unsigned)((pl->n_signals + 255) / 256), 256, 0, st>>>(sumsq, pl->n_signals, rnorm);
   XCB_CUDA(cudaGetLastError());
   const int C = tile_cols<T>();
-  const int64_t tiles = (g.M / g.S[0]) * ((g.S[1] + C - 1) / C);          // tiles per job of the last inverse pass
+  // candidates per job of the last inverse pass: tiles x warps of its CTA (xcb_tma.cuh, COL_INV_AMAX)
+  const int64_t tiles = (g.M / g.S[0]) * ((g.S[1] + C - 1) / C) * ((pl->launch[0]->threads + 31) / 32);
   const int64_t fl = std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs);
   T* pval = nullptr;
   int64_t* pidx = nullptr;

@@ -254,38 +254,45 @@ template <class T> XCB_HD bool amax_better(T vb, uint32_t ob, T va, uint32_t oa)
   if (nb) return ob < oa;
   return vb > va || (vb == va && ob < oa);
 }
-// final packed element m = (r[2m], r[2m+1]): offer its kept, unmasked lags to the running candidate (bv, bo)
-template <class T> XCB_HD void amax_consider(const PassParams<T>& p, uint32_t m, T re, T im, T& bv, uint32_t& bo) {
+// circular lag l of the transform with raw value x: its cropped output index and scaled value, if the lag is kept
+// (inside [i0, i1), not masked)
+template <class T> XCB_HD bool amax_lag(const PassParams<T>& p, uint32_t l, T x, uint32_t& o, T& val,
+                                        bool prescaled = false) {
   const uint32_t n = (uint32_t)p.n, L = (uint32_t)p.L;
   const uint32_t i0 = (uint32_t)p.i0, K = (uint32_t)(p.i1 - p.i0);
+  uint32_t i;
+  if (p.epi_direct) {
+    o = l;
+    i = l + i0;
+  } else {
+    if (l < n) i = l + (n - 1u);
+    else if (l > L - n) i = l - (L - n + 1u);
+    else return false;
+    o = i - i0;
+  }
+  if (o >= K) return false;
+  if (p.mask_w) {
+    // lag = i - (n-1) = dF * W + dT;  t = lag + (T-1) + F*W > 0  ->  dF + F = t / W,  dT + T-1 = t % W
+    const uint32_t W = (uint32_t)p.mask_w, Tm = (uint32_t)p.mask_t, F = (uint32_t)p.mask_f;
+    const uint32_t t = i + (Tm - 1u) + F * W - (n - 1u);
+    const uint32_t q = p.mask_shift >= 0 ? (t >> p.mask_shift) : t / W;
+    const uint32_t dt = t - q * W;
+    if (dt >= 2u * Tm - 1u || q < 1u || q > 2u * F - 1u) return false;
+  }
+  val = prescaled ? x : x * p.escale;
+  if (p.unbiased) {
+    const uint32_t k = i >= n - 1u ? i - (n - 1u) : (n - 1u) - i;
+    val *= T((double)n / (double)(n - k));
+  }
+  return true;
+}
+// final packed element m = (r[2m], r[2m+1]): offer its kept, unmasked lags to the running candidate (bv, bo)
+template <class T> XCB_HD void amax_consider(const PassParams<T>& p, uint32_t m, T re, T im, T& bv, uint32_t& bo) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint32_t l = 2u * m + (uint32_t)h;
-    uint32_t i, o;
-    if (p.epi_direct) {
-      o = l;
-      i = l + i0;
-    } else {
-      if (l < n) i = l + (n - 1u);
-      else if (l > L - n) i = l - (L - n + 1u);
-      else continue;
-      o = i - i0;
-    }
-    if (o >= K) continue;
-    if (p.mask_w) {
-      // lag = i - (n-1) = dF * W + dT;  t = lag + (T-1) + F*W > 0  ->  dF + F = t / W,  dT + T-1 = t % W
-      const uint32_t W = (uint32_t)p.mask_w, Tm = (uint32_t)p.mask_t, F = (uint32_t)p.mask_f;
-      const uint32_t t = i + (Tm - 1u) + F * W - (n - 1u);
-      const uint32_t q = p.mask_shift >= 0 ? (t >> p.mask_shift) : t / W;
-      const uint32_t dt = t - q * W;
-      if (dt >= 2u * Tm - 1u || q < 1u || q > 2u * F - 1u) continue;
-    }
-    T val = (h ? im : re) * p.escale;
-    if (p.unbiased) {
-      const uint32_t k = i >= n - 1u ? i - (n - 1u) : (n - 1u) - i;
-      val *= T((double)n / (double)(n - k));
-    }
-    if (amax_better(val, o, bv, bo)) { bv = val; bo = o; }
+    uint32_t o;
+    T val;
+    if (amax_lag(p, 2u * m + (uint32_t)h, h ? im : re, o, val) && amax_better(val, o, bv, bo)) { bv = val; bo = o; }
   }
 }
 

@@ -203,13 +203,35 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       twiddle_powers<R2>(w_inner, v);
       fft_reg<R2>(v);
       if (ROLE == COL_INV_AMAX) {
-        // fused arg-max: the lags of this tile are offered to a per-thread candidate, nothing is stored
+        // fused arg-max: nothing is stored.  Branch-free first pass over the thread's 2 R2 lags: largest value
+        // and its slot (a compare and two selects per lag); ties and NaNs only raise a flag.  The index / 2-D mask /
+        // weight arithmetic then runs ONCE, for the winning slot; the exact np.argmax walk over all lags
+        // (amax_consider) is the fallback for flagged threads, a masked winner, or weighted lags.  (First version:
+        // exact walk for every lag plus a block reduction per tile -- 0.9 TB/s on the 8 KB tiles of config 5.)
         const uint32_t m0 = (uint32_t)(base + c), inner = (uint32_t)p.inner;
+        T best = T(0);
+        int slot = -1;
+        bool exact = p.unbiased != 0;
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
           const int k = j + r * R1;
-          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
-            amax_consider(p, m0 + (uint32_t)k * inner, v[r].x, -v[r].y, amax_v, amax_o);
+          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1])) {
+            const T re = v[r].x * p.escale, im = -v[r].y * p.escale;      // the values np.argmax would see
+            if (slot < 0 || re > best) { best = re; slot = 2 * r; } else if (!(re < best)) exact = true;
+            if (im > best) { best = im; slot = 2 * r + 1; } else if (!(im < best)) exact = true;
+          }
+        }
+        if (slot >= 0 && !exact) {
+          const uint32_t l = 2u * (m0 + (uint32_t)(j + (slot >> 1) * R1) * inner) + (uint32_t)(slot & 1);
+          if (!amax_lag(p, l, best, amax_o, amax_v, true)) { exact = true; amax_o = kAmaxNone; }
+        }
+        if (exact) {
+#pragma unroll
+          for (int r = 0; r < R2; ++r) {
+            const int k = j + r * R1;
+            if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1]))
+              amax_consider(p, m0 + (uint32_t)k * inner, v[r].x, -v[r].y, amax_v, amax_o);
+          }
         }
       } else if (kStore == CS_TW) {
         cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + batch * p.out_stride + base + c;
@@ -241,33 +263,21 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       }
     }
     if (ROLE == COL_INV_AMAX) {
-      // tile candidate: warp shuffles, then one slot per warp in `red` (free in this role), then warp 0
+      // one candidate per warp and tile goes to global memory; xcb_argmax_final_rows reduces the tiles x warps of a
+      // job (no block barrier here: the tiles of a CTA belong to different jobs anyway)
+      constexpr int NW = (K::THREADS + 31) / 32;
+      const int lane = tid & 31;
+      const int nlane = K::THREADS - (tid & ~31) < 32 ? K::THREADS - (tid & ~31) : 32;   // the last warp may be partial
+      const unsigned live = nlane == 32 ? 0xffffffffu : ((1u << nlane) - 1u);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const T ov = __shfl_down_sync(0xffffffffu, amax_v, o);
-        const uint32_t oo = __shfl_down_sync(0xffffffffu, amax_o, o);
-        if (amax_better(ov, oo, amax_v, amax_o)) { amax_v = ov; amax_o = oo; }
+        const T ov = __shfl_down_sync(live, amax_v, o);
+        const uint32_t oo = __shfl_down_sync(live, amax_o, o);
+        if (lane + o < nlane && amax_better(ov, oo, amax_v, amax_o)) { amax_v = ov; amax_o = oo; }
       }
-      struct Cand { T v; uint32_t o; uint32_t pad; };
-      Cand* cand = reinterpret_cast<Cand*>(red);
-      constexpr int NW = (K::THREADS + 31) / 32;
-      static_assert(NW * sizeof(Cand) <= K::THREADS * 8, "candidates fit the reduction area");
-      if ((tid & 31) == 0) { cand[tid >> 5].v = amax_v; cand[tid >> 5].o = amax_o; }
-      __syncthreads();
-      if (tid < 32) {
-        T bv = T(0);
-        uint32_t bo = kAmaxNone;
-        if (tid < NW) { bv = cand[tid].v; bo = cand[tid].o; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const T ov = __shfl_down_sync(0xffffffffu, bv, o);
-          const uint32_t oo = __shfl_down_sync(0xffffffffu, bo, o);
-          if (amax_better(ov, oo, bv, bo)) { bv = ov; bo = oo; }
-        }
-        if (tid == 0) {
-          static_cast<T*>(p.amax_val)[tile] = bv;
-          p.amax_idx[tile] = bo == kAmaxNone ? (int64_t)-1 : (int64_t)bo;
-        }
+      if (lane == 0) {
+        static_cast<T*>(p.amax_val)[tile * NW + (tid >> 5)] = amax_v;
+        p.amax_idx[tile * NW + (tid >> 5)] = amax_o == kAmaxNone ? (int64_t)-1 : (int64_t)amax_o;
       }
     }
   }

@@ -181,9 +181,10 @@ class CorrelationPlan:
             rows = rows.contiguous()
         idx = torch.empty(rows.shape[0], dtype=torch.int64, device=ccf.device)
         val = torch.empty(rows.shape[0], dtype=ccf.dtype, device=ccf.device)
-        stream = torch.cuda.current_stream(ccf.device).cuda_stream
-        _lib.check(self._lib.xcb_argmax(_xcb_dtype(ccf.dtype), rows.data_ptr(), rows.shape[0], rows.shape[1],
-                                        idx.data_ptr(), val.data_ptr(), stream), "xcb_argmax")
+        with torch.cuda.device(ccf.device):          # xcb_argmax has no plan: it launches on the current device
+            stream = torch.cuda.current_stream(ccf.device).cuda_stream
+            _lib.check(self._lib.xcb_argmax(_xcb_dtype(ccf.dtype), rows.data_ptr(), rows.shape[0], rows.shape[1],
+                                            idx.data_ptr(), val.data_ptr(), stream), "xcb_argmax")
         return idx.reshape(ccf.shape[:-1]), val.reshape(ccf.shape[:-1])
 
     # -- measurement aid ------------------------------------------------------

@@ -587,8 +587,13 @@ class PreprocessProgram:
     def run(self, x, out_dtype=None):
         """x: CUDA tensor (n_signals, npts) float32/float64, last dim contiguous.
         Returns a new tensor (n_signals, npts_out).  All launches go to the
-        current stream; the cached workspaces make one program usable from one
+        current stream of x's device; the cached workspaces make one program usable from one
         stream at a time."""
+        import torch
+        with torch.cuda.device(x.device):              # the preprocessing entry points launch on the current device
+            return self._run(x, out_dtype)
+
+    def _run(self, x, out_dtype=None):
         import torch
         lib = _lib.load()
         if x.dim() != 2 or x.shape[1] != self.npts_in or x.stride(1) != 1 or not x.is_cuda:
