@@ -21,6 +21,9 @@ correlation functions of batch ``b`` are copied out (straight into ``dataset.cc`
 when :func:`xcorr_b200.core.init` placed it in page-locked memory) while batch
 ``b+1`` runs.
 """
+import os
+import time
+
 import numpy as np
 import pandas as pd
 
@@ -207,6 +210,12 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         ev_run = [None, None]                 # compute of the batch that last used slot s
         ev_out = [None, None]                 # its device -> host copy
         h2d_bytes = [0]
+        trace = [] if os.environ.get('XCB_TIMELINE') else None      # per-batch device / host time stamps (diagnostic)
+
+        def mark(stream):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            return ev
 
         def program_for(chan, n_raw, rate, off):
             key = (chan, n_raw, rate, off)
@@ -222,6 +231,7 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         def launch(slot, batch):
             """Gather + async H2D + preprocess + correlate + async D2H of one batch."""
             W = len(batch)
+            tl = {'host_launch0': time.perf_counter()} if trace is not None else None
             raw, offsets = {}, np.full((R, W), np.nan)
             for k, r in enumerate(receivers):
                 for j, w in enumerate(batch):
@@ -244,6 +254,9 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
             if ev_run[slot] is not None:
                 s_in.wait_event(ev_run[slot])                     # x_dev[slot] and the staging twins are free again
                 ev_run[slot].synchronize()                        # ... and so are the page-locked buffers on the host
+            if tl is not None:
+                tl['host_gathered'] = time.perf_counter()
+                tl['h2d0'] = mark(s_in)
             staged = []
             for gi, ((chan, n_raw, rate, off, ndt), members) in enumerate(groups.items()):
                 prog = program_for(chan, n_raw, rate, off)
@@ -302,12 +315,15 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                                 devbuf[torch.tensor(loose, device=dev)] = devtmp
                     h2d_bytes[0] += len(loose) * n_raw * devbuf.element_size()
                 staged.append((prog, devbuf, members, skip, start_final))
-            ev_in = torch.cuda.Event()
+            ev_in = torch.cuda.Event(enable_timing=trace is not None)
             ev_in.record(s_in)
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in)
                 if ev_out[slot] is not None:
                     s_run.wait_event(ev_out[slot])                # ccf_dev[slot] drained
+                if tl is not None:
+                    tl['h2d1'] = ev_in
+                    tl['run0'] = mark(s_run)
                 for prog, devbuf, members, skip, start_final in staged:
                     y = prog.run(devbuf, out_dtype=dtype)
                     ks = torch.tensor([k for k, _ in members], device=dev)
@@ -322,7 +338,7 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                     lambda: CorrelationPlan(npts, R, pair_idx, n_windows=W, dtype=dtype, index_min=i0, index_max=i1,
                                             normalize=normalize, unbiased=unbiased, device=dev))
                 plan(x, out=ccf_dev[slot])
-                ev_run[slot] = torch.cuda.Event()
+                ev_run[slot] = torch.cuda.Event(enable_timing=trace is not None)
                 ev_run[slot].record(s_run)
             # cells of this batch that get a result
             cells = []
@@ -335,6 +351,9 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 batch == list(range(batch[0], batch[0] + W))
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_run[slot])
+                if tl is not None:
+                    tl['run1'] = ev_run[slot]
+                    tl['d2h0'] = mark(s_out)
                 if direct:
                     # rows of the page-locked dataset array are contiguous per pair: one DMA per pair
                     if W == cc_t.shape[1]:
@@ -346,8 +365,12 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 else:
                     host_out, _ = stager.get(slot, 'out', (P, W, K), dtype, device=False)
                     host_out.copy_(ccf_dev[slot], non_blocking=True)
-                ev_out[slot] = torch.cuda.Event()
+                ev_out[slot] = torch.cuda.Event(enable_timing=trace is not None)
                 ev_out[slot].record(s_out)
+            if tl is not None:
+                tl['d2h1'] = ev_out[slot]
+                tl['host_launch1'] = time.perf_counter()
+                trace.append(tl)
             return batch, cells, offsets, host_out, ev_out[slot]
 
         def finish(pending):
@@ -376,6 +399,11 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
         if pending is not None:
             finish(pending)
         torch.cuda.synchronize(dev)
+        if trace:
+            t0, h0 = trace[0]['h2d0'], trace[0]['host_launch0']
+            last_stats['timeline'] = [
+                {k: (round(t0.elapsed_time(v), 3) if not isinstance(v, float) else round((v - h0) * 1e3, 3))
+                 for k, v in tl.items()} for tl in trace]
 
     dataset.attrs['history'] += f", Process ended @ {pd.Timestamp.now()}"
     if cc.attrs['bias_correct'] == 1 and cc.attrs['unbiased'] == 0:

@@ -833,7 +833,7 @@ template <class T, int R1, int R2> struct RowWarp {
   template <int MODE> struct Pk { static constexpr bool value = MODE == 2; };
 
   struct Slot {
-    int64_t batch, row;
+    int32_t batch, row;   // (32 bits: a launch has fewer than 2^31 jobs and rows; 64-bit products at the uses)
     cx<T>* buf;        // this half's row buffer
     const cx<T>* mbuf; // buffer holding the mirrored row
     cx<T> wrow;        // W_L^klow(row): half-step twiddle of the row's leading digits
@@ -852,14 +852,14 @@ template <class T, int R1, int R2> struct RowWarp {
     uint32_t tile, batch;
     if (p.tile_major) { tile = bid / (uint32_t)p.n_batch; batch = bid - tile * (uint32_t)p.n_batch; }
     else { batch = bid / (uint32_t)p.tiles_per_batch; tile = bid - batch * (uint32_t)p.tiles_per_batch; }
-    s.batch = batch;
+    s.batch = (int32_t)batch;
     const int col = ctx.tid >> 4, side = col & 1;
     s.j = ctx.tid & 15;
     int64_t ra, rb;
     const bool valid = RowPass<T, R1, R2>::pair_rows(p, (int64_t)tile * (C / 2) + (col >> 1), ra, rb);
     const bool self = ra == rb;
     s.active = valid && !(side && self);
-    s.row = side ? rb : ra;
+    s.row = (int32_t)(side ? rb : ra);
     s.row0 = ra == 0;
     cx<T>* base = reinterpret_cast<cx<T>*>(smem_raw);
     s.buf = base + col * COLBUF;
@@ -903,6 +903,52 @@ template <class T, int R1, int R2> struct RowWarp {
         v[h * H + r] = xmulc_acc<PK>(SCALED ? xscale<PK>(a[r], sw) : a[r], b[r], v[h * H + r]);   // += a conj(b)
     }
   }
+  // first unscaled term: v[r] = a[r R2] conj(b[r R2]).  The a's are loaded straight INTO the accumulators (all
+  // R1 loads in flight without staging registers), the b's follow in two batches.  (ncu, grouped kernel: with
+  // zeroed accumulators and a multiply-add per term ptxas, at its register limit, reused one register pair for
+  // every element -- LDS, LDS, FFMA2, FFMA2 sixteen times in series, 20 % of the kernel's stall samples.)
+  template <bool PK>
+  static XCB_HD void accumulate_first(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row) {
+#pragma unroll
+    for (int r = 0; r < R1; ++r) v[r] = a_row[r * R2];
+    constexpr int H = R1 / 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      cx<T> b[H];
+#pragma unroll
+      for (int r = 0; r < H; ++r) b[r] = b_row[(h * H + r) * R2];
+#pragma unroll
+      for (int r = 0; r < H; ++r) v[h * H + r] = xmulc<PK>(v[h * H + r], b[r]);
+    }
+  }
+  // further unscaled terms in batches of Q elements (Q a and Q b values staged)
+  template <bool PK, int Q>
+  static XCB_HD void accumulate_next(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row) {
+#pragma unroll
+    for (int h = 0; h < R1 / Q; ++h) {
+      cx<T> a[Q], b[Q];
+#pragma unroll
+      for (int r = 0; r < Q; ++r) { a[r] = a_row[(h * Q + r) * R2]; b[r] = b_row[(h * Q + r) * R2]; }
+#pragma unroll
+      for (int r = 0; r < Q; ++r) v[h * Q + r] = xmulc_acc<PK>(a[r], b[r], v[h * Q + r]);
+    }
+  }
+  // two unscaled terms at once (block mode with two blocks): v[r] = a0 conj(b0) + a1 conj(b1), Q elements per batch
+  template <bool PK, int Q>
+  static XCB_HD void accumulate_two(cx<T>* v, const cx<T>* a0, const cx<T>* b0, const cx<T>* a1, const cx<T>* b1) {
+#pragma unroll
+    for (int r = 0; r < R1; ++r) v[r] = a0[r * R2];
+#pragma unroll
+    for (int h = 0; h < R1 / Q; ++h) {
+      cx<T> x[Q], y[Q], z[Q];
+#pragma unroll
+      for (int r = 0; r < Q; ++r) {
+        x[r] = b0[(h * Q + r) * R2]; y[r] = a1[(h * Q + r) * R2]; z[r] = b1[(h * Q + r) * R2];
+      }
+#pragma unroll
+      for (int r = 0; r < Q; ++r) v[h * Q + r] = xmulc_acc<PK>(y[r], z[r], xmulc<PK>(v[h * Q + r], x[r]));
+    }
+  }
   // `scaled`: per-term norms (stacked windows); else the single scale is applied after the sum
   template <bool PK = false>
   static XCB_HD void accumulate(cx<T>* v, const cx<T>* a_row, const cx<T>* b_row, T sw, bool scaled = true) {
@@ -933,7 +979,7 @@ template <class T, int R1, int R2> struct RowWarp {
       if (is_pro<MODE>(p)) {
         const Job jb = p.jobs[s.batch];
         const bool per_term = p.normalize && p.stack_sig_stride != 0;
-        const cx<T>* z = p.spec + s.row * N + s.j;
+        const cx<T>* z = p.spec + (int64_t)s.row * N + s.j;
 #pragma unroll
         for (int r = 0; r < R1; ++r) v[r].x = v[r].y = T(0);
         for (int w = 0; w < p.n_stack; ++w) {
@@ -947,11 +993,11 @@ template <class T, int R1, int R2> struct RowWarp {
         for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];       // publish C (linear index)
       } else {
         if (p.load_mode == RL_REAL) {
-          const T* x = reinterpret_cast<const T*>(p.in) + s.batch * p.in_stride;
+          const T* x = reinterpret_cast<const T*>(p.in) + (int64_t)s.batch * p.in_stride;
 #pragma unroll
-          for (int r = 0; r < R1; ++r) v[r] = load_real_packed(p, x, s.row * N + s.j + r * R2, ctx.ss);
+          for (int r = 0; r < R1; ++r) v[r] = load_real_packed(p, x, (int64_t)s.row * N + s.j + r * R2, ctx.ss);
         } else {
-          const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + s.batch * p.in_stride + s.row * N + s.j;
+          const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in) + (int64_t)s.batch * p.in_stride + (int64_t)s.row * N + s.j;
 #pragma unroll
           for (int r = 0; r < R1; ++r) v[r] = src[r * R2];
         }
@@ -971,32 +1017,60 @@ template <class T, int R1, int R2> struct RowWarp {
     fft_reg<R2, PK>(v);
   }
 
+  // W_2N^(r R2) = exp(-i pi r / R1): the half-step twiddle of element e = j + r R2 is W_2N^j times this constant,
+  // so the pair product needs one table value per lane instead of one per element (the grouped kernel is bound
+  // by shared-memory wavefronts: ncu L1/TEX throughput 77 %)
+  static XCB_HD cx<T> half_step(int r) {
+    constexpr double c[16] = {1, 0.98078528040323043, 0.92387953251128674, 0.83146961230254524, 0.70710678118654757,
+                              0.55557023301960229, 0.38268343236508984, 0.19509032201612833, 0.0,
+                              -0.19509032201612819, -0.38268343236508973, -0.55557023301960196, -0.70710678118654746,
+                              -0.83146961230254535, -0.92387953251128674, -0.98078528040323043};
+    constexpr double sn[16] = {0, 0.19509032201612825, 0.38268343236508978, 0.55557023301960218, 0.70710678118654746,
+                               0.83146961230254524, 0.92387953251128674, 0.98078528040323043, 1, 0.98078528040323043,
+                               0.92387953251128674, 0.83146961230254546, 0.70710678118654757, 0.55557023301960218,
+                               0.38268343236508989, 0.19509032201612861};
+    cx<T> w; w.x = (T)c[r]; w.y = (T)-sn[r];
+    return w;
+  }
+  template <bool PK> static XCB_HD cx<T> row_w(const cx<T>& wb, int r) {
+    if (r == 0) return wb;
+    if (r == R1 / 2) return cmi(wb);                 // exp(-i pi/2) = -i
+    return xmul<PK>(wb, half_step(r));
+  }
+  // E = C[k] + conj(C[M-k]), D = C[k] - conj(C[M-k]), O = conj(W) D, V = (E + iO)/2; returns fs conj(V)
+  template <bool PK> static XCB_HD cx<T> tangle_one(const cx<T>& c, const cx<T>& cm, const cx<T>& W, T fs) {
+    const cx<T> cmc = cconj(cm);
+    const cx<T> E = xadd<PK>(c, cmc), D = xsub<PK>(c, cmc);
+    const cx<T> O = xmulc<PK>(D, W);
+    cx<T> o = xscale<PK>(xadd<PK>(E, cpi(O)), fs);   // fs (E + iO) ...
+    o.y = -o.y;                                       // ... conjugated
+    return o;
+  }
+  static XCB_HD T job_scale(const PassParams<T>& p, const Slot& s) {
+    T fs = s.fs;
+    if (fs < T(0)) {
+      const Job jb = p.jobs[s.batch];
+      const bool per_term = p.normalize && p.stack_sig_stride != 0;
+      fs = T(0.5);
+      if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
+    }
+    return fs;
+  }
+
   template <int MODE = 0>
   static XCB_HD void phase_b(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
     cx<T>* v = ctx.v;
     if (!s.active) return;
     if (is_pro<MODE>(p)) {
       if (s.j >= R2) return;
-      T fs = s.fs;
-      if (fs < T(0)) {
-        const Job jb = p.jobs[s.batch];
-        const bool per_term = p.normalize && p.stack_sig_stride != 0;
-        fs = T(0.5);
-        if (p.normalize && !per_term) fs = T(0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j]);
-      }
-      const cx<T> wrow = s.wrow;
+      const T fs = job_scale(p, s);
+      constexpr bool PK = Pk<MODE>::value;
+      const cx<T> wb = xmul<PK>(s.wrow, s.tw2[s.j]);
 #pragma unroll
       for (int r = 0; r < R1; ++r) {
         const int e = s.j + r * R2;
         const cx<T> cm = s.mbuf[mirror(s, e)];
-        constexpr bool PK = Pk<MODE>::value;
-        const cx<T> W = xmul<PK>(wrow, s.tw2[e]);
-        // E = C[k] + conj(C[M-k]), D = C[k] - conj(C[M-k]), O = conj(W) D, V = (E + iO)/2; keep fs conj(V)
-        const cx<T> cmc = cconj(cm);
-        const cx<T> E = xadd<PK>(v[r], cmc), D = xsub<PK>(v[r], cmc);
-        const cx<T> O = xmulc<PK>(D, W);
-        cx<T> o = xscale<PK>(xadd<PK>(E, cpi(O)), fs);   // fs (E + iO) ...
-        o.y = -o.y;                                       // ... conjugated
+        cx<T> o = tangle_one<PK>(v[r], cm, row_w<PK>(wb, r), fs);
         if (r == 0 && s.row0 && s.j == 0) {          // V[0] = (C[0] + C[M])/2 + i (C[0] - C[M])/2
           o.x = fs * (v[0].x + v[0].y); o.y = -fs * (v[0].x - v[0].y);
         }
@@ -1007,6 +1081,33 @@ template <class T, int R1, int R2> struct RowWarp {
       stage2(p, s, v);
     }
   }
+
+#if XCB_PK_DEVICE
+  // Pair product, rows other than the self-mirrored ones: the mirrored element of (row ra, e = j + r R2) is
+  // (row rb, N - 1 - e) = lane R2 - 1 - j of the OTHER half-warp, register R1 - 1 - r -- a warp shuffle
+  // instead of a round trip through the row buffers (16 stores + 16 loads per lane).  Called by ALL lanes of a
+  // warp that has a job (lanes j >= R2 only serve the shuffles).
+  static __device__ __forceinline__ void phase_b_shfl(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
+    cx<T>* v = ctx.v;
+    constexpr bool PK = true;
+    const bool on = s.j < R2;
+    const int src = ((ctx.tid & 16) ^ 16) + (R2 - 1 - s.j < 0 ? 0 : R2 - 1 - s.j);
+    const T fs = job_scale(p, s);
+    cx<T> wb;
+    wb.x = T(1); wb.y = T(0);
+    if (on) wb = xmul<PK>(s.wrow, s.tw2[s.j]);
+#pragma unroll
+    for (int r = 0; r < R1 / 2; ++r) {
+      const int q = R1 - 1 - r;
+      cx<T> ma, mb;                                  // mirrors of elements r and q: the partner's registers q and r
+      ma.x = __shfl_sync(0xffffffffu, v[q].x, src); ma.y = __shfl_sync(0xffffffffu, v[q].y, src);
+      mb.x = __shfl_sync(0xffffffffu, v[r].x, src); mb.y = __shfl_sync(0xffffffffu, v[r].y, src);
+      v[r] = tangle_one<PK>(v[r], ma, row_w<PK>(wb, r), fs);
+      v[q] = tangle_one<PK>(v[q], mb, row_w<PK>(wb, q), fs);
+    }
+    if (on) fft_reg<R1, PK>(v);
+  }
+#endif
 
   template <int MODE = 0>
   static XCB_HD void phase_c(const PassParams<T>& p, Ctx& ctx, const Slot& s) {
@@ -1032,9 +1133,9 @@ template <class T, int R1, int R2> struct RowWarp {
           T* outp = p.ccf + p.jobs[s.batch].out_off;
 #pragma unroll
           for (int r = 0; r < R2; ++r)
-            epilogue_store(p, outp, (uint32_t)(s.row * N + s.j + r * R1), v[r].x, -v[r].y);
+            epilogue_store(p, outp, (uint32_t)s.row * (uint32_t)N + (uint32_t)(s.j + r * R1), v[r].x, -v[r].y);
         } else {
-          cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+          cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + (int64_t)s.batch * p.out_stride + (int64_t)s.row * N + s.j;
 #pragma unroll
           for (int r = 0; r < R2; ++r) dst[r * R1] = cconj(v[r]);
         }
@@ -1043,16 +1144,16 @@ template <class T, int R1, int R2> struct RowWarp {
         T* outp = p.ccf + p.jobs[s.batch].out_off;
 #pragma unroll
         for (int r = 0; r < R2; ++r)
-          epilogue_store(p, outp, (uint32_t)(s.row * N + s.j + r * R1), v[r].x, -v[r].y);
+          epilogue_store(p, outp, (uint32_t)s.row * (uint32_t)N + (uint32_t)(s.j + r * R1), v[r].x, -v[r].y);
       } else if (p.store_mode != RS_HALF) {
         // plain complex transform (xcb_fft_*): no real <-> packed conversion
-        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + (int64_t)s.batch * p.out_stride + (int64_t)s.row * N + s.j;
 #pragma unroll
         for (int r = 0; r < R2; ++r) dst[r * R1] = p.store_mode == RS_CONJ ? cconj(v[r]) : v[r];
       } else {
         // X[k] = (S - i W D)/2 with S = Z[k] + conj(Z[M-k]), D = Z[k] - conj(Z[M-k]), W = W_L^k
         const cx<T> wrow = s.wrow;
-        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + s.batch * p.out_stride + s.row * N + s.j;
+        cx<T>* dst = reinterpret_cast<cx<T>*>(p.out) + (int64_t)s.batch * p.out_stride + (int64_t)s.row * N + s.j;
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
           const int k = s.j + r * R1;

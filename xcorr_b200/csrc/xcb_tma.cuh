@@ -305,6 +305,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef XCB_ACC_BATCH
+#define XCB_ACC_BATCH 4     // elements staged per batch when a further term is added (registers: 4 per element)
+#endif
 template <class T, int R1, int R2> struct PairGrouped {
   using W = RowWarp<T, R1, R2>;
   static constexpr int N = W::N, C = W::C, WARPS = W::THREADS / 32;      // consumer warps = jobs per group
@@ -470,11 +473,10 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   for (;;) {
     int buf = (int)(step % NBUF);
     mbar_wait(&full[buf], (step / NBUF) & 1u);         // (no back-off: a sleeping warp wakes up to 0.5 us late)
-    const int64_t item = mail[buf].item;
+    const int32_t item = (int32_t)mail[buf].item;       // (the launch guarantees fewer than 2^31 items)
     if (item < 0) break;
-    const int64_t ra = mail[buf].ra, rb = mail[buf].rb;
-    const int64_t q = item / p.n_groups;
-    const int gi = (int)(item - q * p.n_groups);
+    const int32_t ra = (int32_t)mail[buf].ra, rb = (int32_t)mail[buf].rb;
+    const int gi = (int)((uint32_t)item % (uint32_t)p.n_groups);
     const bool self = ra == rb;
     typename W::Slot s;
     bool has_job;
@@ -510,29 +512,59 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     if (!use_recs || per_term || s.row0) jb = p.jobs[s.batch];      // (row 0 reads the spectra's slot 0 directly)
 
     cx<T>* v = ctx.v;
+    if (per_term || !lane_on) {
 #pragma unroll
-    for (int r = 0; r < R1; ++r) v[r].x = v[r].y = T(0);
-    for (int w = 0; w < n_terms; ++w, ++step) {
+      for (int r = 0; r < R1; ++r) v[r].x = v[r].y = T(0);
+    }
+    int w0 = 0;
+    if (!per_term && n_terms == 2 && NBUF >= 3) {
+      // both terms in one go (straight-line code: the loads of a whole batch are in flight together)
+      const int buf1 = (int)((step + 1) % NBUF);
+      mbar_wait(&full[buf1], ((step + 1) / NBUF) & 1u);
+      if (lane_on) {
+        const cx<T>* st0 = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
+        const cx<T>* st1 = reinterpret_cast<const cx<T>*>(smem_raw + buf1 * K::STAGE_BYTES) + s.j;
+        const int oa = (row_i * 2 + side) * N, ob = (row_j * 2 + side) * N;
+        W::template accumulate_two<true, XCB_ACC_BATCH>(v, st0 + oa, st0 + ob, st1 + oa, st1 + ob);
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&empty[buf]); mbar_arrive(&empty[buf1]); }
+      step += 2;
+      w0 = 2;
+    }
+    for (int w = w0; w < n_terms; ++w, ++step) {
       if (w > 0) {
         buf = (int)(step % NBUF);
         mbar_wait(&full[buf], (step / NBUF) & 1u);
       }
       if (lane_on) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
-        T sw = T(1);
-        if (per_term) sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
-        W::template accumulate<true>(v, st + (row_i * 2 + side) * N, st + (row_j * 2 + side) * N, sw, per_term);
+        const cx<T>* sa = st + (row_i * 2 + side) * N;
+        const cx<T>* sb = st + (row_j * 2 + side) * N;
+        if (per_term) {
+          const T sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
+          W::template accumulate<true>(v, sa, sb, sw, true);
+        } else if (w == 0) {
+          W::template accumulate_first<true>(v, sa, sb);
+        } else {
+          W::template accumulate_next<true, XCB_ACC_BATCH>(v, sa, sb);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[buf]);       // this warp is done with the buffer (and its mail)
     }
-    if (lane_on) {
-      if (s.row0 && s.j == 0) v[0] = W::packed_dc(p, jb, per_term);
+    if (sizeof(T) == 4 && has_job && !self && !s.row0) {
+      // mirrored elements by warp shuffle (warp-uniform branch; lanes j >= R2 hold zeros and only take part)
+      W::phase_b_shfl(p, ctx, s);
+    } else {
+      if (lane_on) {
+        if (s.row0 && s.j == 0) v[0] = W::packed_dc(p, jb, per_term);
 #pragma unroll
-      for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];           // publish C (linear index)
+        for (int r = 0; r < R1; ++r) s.buf[s.j + r * R2] = v[r];           // publish C (linear index)
+      }
+      __syncwarp();
+      W::template phase_b<2>(p, ctx, s);
     }
-    __syncwarp();
-    W::template phase_b<2>(p, ctx, s);
     __syncwarp();
     W::template phase_c<2>(p, ctx, s);
     __syncwarp();
