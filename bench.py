@@ -530,7 +530,10 @@ def run_gpu(args):
 
     # ---------------- end to end through core.process, against the measured PCIe ceiling ----------------
     pcie = pcie_probe(torch, dev, barrier)
-    wpc = max(1, min(args.steps, max(2, 6 // world)))        # windows per process() call: 3.9 GB of page-locked cc each
+    # windows per process() call (a dataset of that many 24 h windows): 3.9 GB of page-locked `cc` each, so
+    # 10 windows on one rank, fewer when several ranks share the host; every call pays one pipeline ramp
+    # (first H2D + first compute, ~42 ms, before its first D2H can start)
+    wpc = max(1, min(args.steps, max(2, 10 // world)))
     e2e_ms, ds = e2e_core_process(torch, xb, dev, x_host, R, n, K, args.steps, args.warmup, wpc, barrier)
     got = ds.variables["cc"].data
     assert int(np.argmax(got[0, 0])) == (n - 1 - i0) + 137 and ds.variables["status"].data.min() == 1

@@ -7,7 +7,8 @@ from xcorr_b200.signal import Correlate2dPlan, timelapse_pairs
 dev = torch.device("cuda:0")
 F, T, D = 1024, 128, int(os.environ.get("XCB_DAYS", 365))
 pairs = timelapse_pairs(D)
-plan = Correlate2dPlan(F, T, D, pairs, dtype=torch.float32, device=dev)
+plan = Correlate2dPlan(F, T, D, pairs, dtype=torch.float32, device=dev,
+                       max_work_bytes=int(float(os.environ.get('XCB_WORK_MB', 0)) * 2**20))
 g = torch.Generator(device=dev); g.manual_seed(5)
 days = torch.randn((D, F, T), generator=g, device=dev) ** 2
 for _ in range(2):

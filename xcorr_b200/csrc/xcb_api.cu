@@ -363,6 +363,7 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   if (n_blocks <= 1) {
     if (nd == 0) {
       if (!plan_choose_dims(d->n, dims, &nd)) { delete pl; return XCB_ERR_SIZE; }
+      if (d->n_pairs > 0) plan_prefer_row16(d->n, dims, &nd, 1.10);
     } else {
       for (int a = 0; a < nd; ++a) dims[a] = d->dims[a];
     }

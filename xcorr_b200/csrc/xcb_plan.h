@@ -118,6 +118,55 @@ inline bool plan_choose_dims(int64_t n_min, int dims[kMaxDims], int* nd) {
   return true;
 }
 
+// Correlation plans whose chosen row axis is not 16 x R2: the cheapest factorisation WITH such an axis, if it
+// costs at most `slack` times the points.  The 16 x R2 row axes run the warp-synchronous row pass and the
+// staged / grouped pair product (config 4, 256 stacked windows: 100 x 96 x 96 -> 64 x 64 x 240 has 6.7 % more
+// points and takes 10.8 instead of 12.2 ms; larger row axes measured better: 240 > 192 > 160 > 128).
+inline bool plan_prefer_row16(int64_t n_min, int dims[kMaxDims], int* nd, double slack) {
+  double m0 = 1;
+  for (int a = 0; a < *nd; ++a) m0 *= dims[a];
+  const MenuEntry* last = menu_find(dims[*nd - 1]);
+  if (*nd < 2 || (last && last->R1 == 16)) return false;
+  double best = 1e300;
+  int bd[kMaxDims] = {0, 0, 0, 0}, bn = 0, idx[kMaxDims];
+  for (int p = 2; p <= *nd; ++p) {                      // never more passes than the plan it replaces
+    for (int i = 0; i < p; ++i) idx[i] = 0;
+    while (true) {
+      double m = 1;
+      int row = 0;
+      for (int i = 0; i < p; ++i) {
+        const MenuEntry& e = kMenu[idx[i]];
+        m *= e.N;
+        if (e.R1 == 16 && e.N <= 256 && e.N > row) row = e.N;
+      }
+      if (row && m >= (double)n_min && m <= slack * m0) {
+        const double cost = m * (p + 0.5) * (1.0 - 1e-4 * row);
+        if (cost < best) { best = cost; bn = p; for (int i = 0; i < p; ++i) bd[i] = kMenu[idx[i]].N; }
+      }
+      int k = p - 1;
+      while (k >= 0 && idx[k] == kMenuSize - 1) --k;
+      if (k < 0) break;
+      ++idx[k];
+      for (int i = k + 1; i < p; ++i) idx[i] = idx[k];
+    }
+  }
+  if (bn == 0) return false;
+  // row axis last (the largest 16 x R2 length), the others in increasing order (the first pass reads the real
+  // input: a short first axis measured faster there)
+  int row = -1;
+  for (int i = 0; i < bn; ++i) {
+    const MenuEntry* e = menu_find(bd[i]);
+    if (e->R1 == 16 && bd[i] <= 256 && (row < 0 || bd[i] > bd[row])) row = i;
+  }
+  const int rv = bd[row];
+  for (int i = row; i + 1 < bn; ++i) bd[i] = bd[i + 1];
+  std::sort(bd, bd + bn - 1);
+  bd[bn - 1] = rv;
+  for (int i = 0; i < bn; ++i) dims[i] = bd[i];
+  *nd = bn;
+  return true;
+}
+
 inline bool plan_geom_init(PlanGeom& g, int64_t n, const int* dims, int nd, int n_blocks = 1,
                            int64_t block_len = 0, int64_t lag0 = 0, int64_t n_lags = 0) {
   if (n < 1 || nd < 1 || nd > kMaxDims) return false;

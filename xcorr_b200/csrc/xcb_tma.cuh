@@ -77,6 +77,39 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// Warp-wide np.argmax order on (value, index) candidates (amax_better) without branches: the value becomes an
+// unsigned key that orders like the floats (NaN on top, -0 = +0, "no candidate" = 0), REDUX.MAX finds the best key
+// and REDUX.MIN the lowest index among its holders.  (The shuffle tree with amax_better took a third of the
+// arg-max pass of config 5: five rounds of ~25 instructions and six branches each.)
+__device__ __forceinline__ void amax_warp_reduce(unsigned live, float& v, uint32_t& o) {
+  const float c = v + 0.0f;                                        // -0 -> +0
+  const uint32_t u = __float_as_uint(c);
+  uint32_t key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  if (c != c) key = 0xffffffffu;
+  if (o == kAmaxNone) key = 0u;
+  const uint32_t m = __reduce_max_sync(live, key);
+  o = __reduce_min_sync(live, key == m ? o : kAmaxNone);
+  const uint32_t back = (m & 0x80000000u) ? (m & 0x7fffffffu) : ~m;
+  v = m == 0xffffffffu ? __uint_as_float(0x7fc00000u) : __uint_as_float(back);
+}
+__device__ __forceinline__ void amax_warp_reduce(unsigned live, double& v, uint32_t& o) {
+  const double c = v + 0.0;
+  const unsigned long long u = (unsigned long long)__double_as_longlong(c);
+  unsigned long long key = (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+  if (c != c) key = ~0ull;
+  if (o == kAmaxNone) key = 0ull;
+  const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+  const uint32_t mh = __reduce_max_sync(live, hi);
+  const uint32_t ml = __reduce_max_sync(live, hi == mh ? lo : 0u);
+  o = __reduce_min_sync(live, (hi == mh && lo == ml) ? o : kAmaxNone);
+  const unsigned long long m = ((unsigned long long)mh << 32) | ml;
+  const unsigned long long back = (m >> 63) ? (m & 0x7fffffffffffffffull) : ~m;
+  v = m == ~0ull ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double((long long)back);
+}
+
+#ifndef XCB_COL_MINB_SMALL
+#define XCB_COL_MINB_SMALL 8
+#endif
 #ifndef XCB_COL_MINB
 #define XCB_COL_MINB 3      // resident CTAs per SM the column pass is compiled for, where shared memory allows
 #endif
@@ -88,7 +121,10 @@ template <class T, int R1, int R2> struct ColTma {
   static constexpr int NBOX = N / BOX_ROWS;
   static constexpr int SMEM_SM = 227 * 1024;                                  // per SM, 1 KB reserved per CTA
   static constexpr int fits(int slots, int ctas) { return (slots * SLOT_BYTES + 64 + THREADS * 8 + 1024) * ctas <= SMEM_SM; }
-  static constexpr int MINB = (XCB_COL_MINB >= 3 && fits(2, 3)) ? 3 : 2;      // a 2-slot ring is the minimum
+  // small sub-FFTs have small CTAs (N = 64: 128 threads): compile them for enough CTAs per SM to keep ~24-32
+  // warps resident (ncu, config 5: 84 / 103 registers left 5 / 4 CTAs = 16-20 warps per SM)
+  static constexpr int WANT = sizeof(T) == 4 ? (THREADS <= 128 ? XCB_COL_MINB_SMALL : THREADS <= 192 ? 4 : 3) : 3;
+  static constexpr int MINB = (XCB_COL_MINB >= 3 && fits(3, WANT)) ? WANT : (XCB_COL_MINB >= 3 && fits(2, 3)) ? 3 : 2;
   static constexpr int NSLOT = fits(3, MINB) ? 3 : 2;
   static constexpr int RED_OFF = NSLOT * SLOT_BYTES + 64;
   static constexpr int SMEM = RED_OFF + THREADS * 8;
@@ -269,12 +305,7 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
       const int lane = tid & 31;
       const int nlane = K::THREADS - (tid & ~31) < 32 ? K::THREADS - (tid & ~31) : 32;   // the last warp may be partial
       const unsigned live = nlane == 32 ? 0xffffffffu : ((1u << nlane) - 1u);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const T ov = __shfl_down_sync(live, amax_v, o);
-        const uint32_t oo = __shfl_down_sync(live, amax_o, o);
-        if (lane + o < nlane && amax_better(ov, oo, amax_v, amax_o)) { amax_v = ov; amax_o = oo; }
-      }
+      amax_warp_reduce(live, amax_v, amax_o);
       if (lane == 0) {
         static_cast<T*>(p.amax_val)[tile * NW + (tid >> 5)] = amax_v;
         p.amax_idx[tile * NW + (tid >> 5)] = amax_o == kAmaxNone ? (int64_t)-1 : (int64_t)amax_o;

@@ -51,7 +51,8 @@ class Correlate2dPlan:
     half spectra (NCCL) hands every rank all of them; `pairs` is then this rank's share of the pair list
     (SURVEY 8e, config 5)."""
 
-    def __init__(self, F, T, n_images, pairs, dtype=torch.float32, normalize=True, device=None, day_shard=None):
+    def __init__(self, F, T, n_images, pairs, dtype=torch.float32, normalize=True, device=None, day_shard=None,
+                 max_work_bytes=0):
         self.F, self.T, self.W = int(F), int(T), _row_width(T)
         self.n = self.F * self.W
         self.pairs = [(int(i), int(j)) for i, j in pairs]
@@ -61,7 +62,7 @@ class Correlate2dPlan:
         lo = min(self.n_images, self.rank * self.per)
         self.day_slice = slice(lo, min(self.n_images, lo + self.per))
         self.plan = CorrelationPlan(self.n, self.per * self.world, self.pairs, dtype=dtype, normalize=normalize,
-                                    device=device, n_blocks=1)
+                                    device=device, n_blocks=1, max_work_bytes=max_work_bytes)
         self.fwd = self.plan if self.world == 1 else \
             CorrelationPlan(self.n, self.per, [], dtype=dtype, normalize=normalize, device=device, n_blocks=1)
         self.dtype, self.device = self.plan.dtype, self.plan.device
