@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Timeline of a core.process() call of the e2e leg of bench.py (XCB_TIMELINE stamps per batch)."""
-import os, sys, time, json
+"""Where does the FIRST batch of a core.process() call spend its host time?  (cProfile of launch())"""
+import os, sys, time, json, cProfile, pstats
 os.environ["XCB_TIMELINE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -14,10 +14,11 @@ x = bench.make_inputs(torch, R, n, dev, torch.float32, 3000)
 x_host = [x.cpu().pin_memory()]
 del x
 def barrier(): torch.cuda.synchronize()
-print("pcie", bench.pcie_probe(torch, dev, barrier))
-steps = int(os.environ.get("XCB_STEPS", 6))
-t0 = time.perf_counter()
-ms, ds = bench.e2e_core_process(torch, xb, dev, x_host, R, n, K, steps, 3, min(steps, 6), barrier)
-print("e2e ms/step", ms / steps, "total wall", time.perf_counter() - t0)
-for tl in pm.last_stats["timeline"]:
-    print(json.dumps(tl))
+steps = int(os.environ.get("XCB_STEPS", 3))
+pr = cProfile.Profile()
+ms, ds = bench.e2e_core_process(torch, xb, dev, x_host, R, n, K, steps, 3, steps, barrier)
+pr.enable()
+ms, ds = bench.e2e_core_process(torch, xb, dev, x_host, R, n, K, steps, 3, steps, barrier)
+pr.disable()
+print("e2e ms/step", ms / steps)
+pstats.Stats(pr).sort_stats("tottime").print_stats(14)

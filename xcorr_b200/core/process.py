@@ -118,14 +118,14 @@ class _Stager:
         self.torch, self.dev = torch, dev
         self.host, self.device, self.free_ev = {}, {}, {}
 
-    def get(self, slot, key, shape, dtype, host=True, device=True):
+    def get(self, slot, key, shape, dtype, host=True, device=True, zero=False):
         torch = self.torch
         k = (slot, key)
         n = int(np.prod(shape))
         h = d = None
         if device:
             if k not in self.device or self.device[k].numel() < n or self.device[k].dtype != dtype:
-                self.device[k] = torch.empty(n, dtype=dtype, device=self.dev)
+                self.device[k] = (torch.zeros if zero else torch.empty)(n, dtype=dtype, device=self.dev)
             d = self.device[k][:n].view(*shape)
         if host:
             if k not in self.host or self.host[k].numel() < n or self.host[k].dtype != dtype:
@@ -243,9 +243,10 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                     if data.dtype not in (np.float32, np.float64):
                         data = data.astype(np.float64)            # obspy promotes integer data to float64
                     raw[(k, j)] = (data, float(rate), float(off))
-            if x_dev[slot] is None or x_dev[slot].shape[1] != W:
-                x_dev[slot] = torch.zeros((R, W, npts), dtype=dtype, device=dev)
-                ccf_dev[slot] = torch.empty((P, W, K), dtype=dtype, device=dev)
+            # (persistent across calls like the staging buffers: a fresh cudaMalloc in the first batch of every
+            # call stalled the host for ~0.1 s; traces that stay missing keep the zeros of the allocation)
+            _, x_dev[slot] = stager.get(slot, ('x', R, W, npts), (R, W, npts), dtype, host=False, zero=True)
+            _, ccf_dev[slot] = stager.get(slot, ('ccf', P, W, K), (P, W, K), dtype, host=False)
             x = x_dev[slot]
             ok = np.zeros((R, W), dtype=bool)
             groups = {}
@@ -317,6 +318,8 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 staged.append((prog, devbuf, members, skip, start_final))
             ev_in = torch.cuda.Event(enable_timing=trace is not None)
             ev_in.record(s_in)
+            if tl is not None:
+                tl['host_h2d_queued'] = time.perf_counter()
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in)
                 if ev_out[slot] is not None:
@@ -324,14 +327,21 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 if tl is not None:
                     tl['h2d1'] = ev_in
                     tl['run0'] = mark(s_run)
+                whole = [(k, j) for k in range(R) for j in range(W)]
                 for prog, devbuf, members, skip, start_final in staged:
-                    y = prog.run(devbuf, out_dtype=dtype)
-                    ks = torch.tensor([k for k, _ in members], device=dev)
-                    js = torch.tensor([j for _, j in members], device=dev)
-                    x[ks, js] = y[:, skip:skip + npts]            # core/process.py:156-157 slices [:npts]
+                    y = prog.run(devbuf, out_dtype=dtype, copy=False)       # devbuf is ours: no defensive copy
                     for (k, j) in members:
                         ok[k, j] = True
                         offsets[k, j] = start_final
+                    if len(staged) == 1 and members == whole and y.dtype == dtype and y.stride(1) == 1:
+                        # every trace of the batch came out of one program, in order: the plan reads the
+                        # processed traces where they are (rows of y, core/process.py:156-157 slices [:npts])
+                        x = y[:, skip:skip + npts]
+                    else:
+                        for m, (k, j) in enumerate(members):       # (device -> device, asynchronous: an index
+                            x[k, j].copy_(y[m, skip:skip + npts], non_blocking=True)   # tensor would cost a synchronous upload)
+                if tl is not None:
+                    tl['host_preprocessed'] = time.perf_counter()
                 normalize, unbiased = cc.attrs['normalize'] == 1, cc.attrs['bias_correct'] == 1
                 plan = _cached_plan(
                     (str(dev), npts, R, tuple(pair_idx), W, str(dtype), i0, i1, bool(normalize), bool(unbiased)),
@@ -340,6 +350,8 @@ def process(dataset, waveforms, retry_missing: bool = False, test_run: bool = Fa
                 plan(x, out=ccf_dev[slot])
                 ev_run[slot] = torch.cuda.Event(enable_timing=trace is not None)
                 ev_run[slot].record(s_run)
+            if tl is not None:
+                tl['host_run_queued'] = time.perf_counter()
             # cells of this batch that get a result
             cells = []
             for q, (a, b) in enumerate(pair_idx):

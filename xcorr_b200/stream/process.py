@@ -584,16 +584,17 @@ class PreprocessProgram:
         self._dev_cache[key] = bufs
         return bufs
 
-    def run(self, x, out_dtype=None):
+    def run(self, x, out_dtype=None, copy=True):
         """x: CUDA tensor (n_signals, npts) float32/float64, last dim contiguous.
-        Returns a new tensor (n_signals, npts_out).  All launches go to the
+        Returns a new tensor (n_signals, npts_out); with ``copy=False`` a program that does not
+        change the samples may return `x` itself (or a view of it).  All launches go to the
         current stream of x's device; the cached workspaces make one program usable from one
         stream at a time."""
         import torch
         with torch.cuda.device(x.device):              # the preprocessing entry points launch on the current device
-            return self._run(x, out_dtype)
+            return self._run(x, out_dtype, copy)
 
-    def _run(self, x, out_dtype=None):
+    def _run(self, x, out_dtype=None, copy=True):
         import torch
         lib = _lib.load()
         if x.dim() != 2 or x.shape[1] != self.npts_in or x.stride(1) != 1 or not x.is_cuda:
@@ -688,11 +689,11 @@ class PreprocessProgram:
                 if s.decimate != 1:     # decimate(no_filter=True): data[::factor]
                     y = y[:, ::s.decimate]
             cur = y
-        if cur is x:
+        if cur is x and copy:
             cur = x.clone()
         if cur.dtype != out_dtype:
             cur = cur.to(out_dtype)
-        if not cur.is_contiguous():
+        if not cur.is_contiguous() and (copy or cur.stride(-1) != 1):
             cur = cur.contiguous()
         return cur
 
