@@ -29,7 +29,7 @@ template <class T, int R1, int R2> static void emu_row(const PassParams<T>& p) {
   using G = Cfg<T, R1, R2>;
   std::vector<unsigned char> smem(G::ROW_SMEM + 64);
   int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
-  if constexpr (R1 == 16) {          // warp-synchronous variant: phases are separated by __syncwarp on the device
+  if constexpr (RowWarpOk<R1, R2>::value) {          // warp-synchronous variant: phases are separated by __syncwarp on the device
     using P = RowWarp<T, R1, R2>;
     std::vector<typename P::Ctx> ctx(G::THREADS);
     std::vector<typename P::Slot> slot(G::THREADS);

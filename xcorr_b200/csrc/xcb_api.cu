@@ -245,7 +245,7 @@ struct xcb_plan {
   int64_t n_signals = 0, n_jobs = 0, jobs_in_flight = 0;
   int64_t tiles0 = 0;               // CTAs per signal of the first forward pass
   int64_t win_stride = 1;           // signals between consecutive windows of a receiver
-  size_t work_bytes = 0, partial_bytes = 0, rnorm_bytes = 0;
+  size_t work_bytes = 0, partial_bytes = 0, rnorm_bytes = 0, recs_bytes = 0;
   void* d_hi = nullptr;
   void* d_lo = nullptr;
   void* d_inner[kMaxDims] = {nullptr, nullptr, nullptr, nullptr};
@@ -423,8 +423,10 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
   pl->work_bytes = align_up((size_t)fl * per_job, 256);
 
   // job groups of the staged pair product (row axes 16 x R2 only; see launch_row)
-  if (pl->n_jobs > 0 && menu_find(dims[nd - 1])->R1 == 16) {
-    const int warps = C / 2, max_rows = pl->dtype == XCB_F32 ? stage_rows<float>() : stage_rows<double>();
+  const MenuEntry* rowe = menu_find(dims[nd - 1]);
+  if (pl->n_jobs > 0 && (rowe->R1 == 16 || (rowe->R1 == 8 && rowe->R2 == 8))) {
+    // one job per consumer warp: R1 lanes per row, C rows per CTA (xcb_tma.cuh, PairGrouped::WARPS)
+    const int warps = rowe->R1 * C / 32, max_rows = pl->dtype == XCB_F32 ? stage_rows<float>() : stage_rows<double>();
     std::vector<PairGroup> all, chunk;
     pl->group_off.push_back(0);
     for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += fl) {
@@ -433,6 +435,10 @@ extern "C" int xcb_plan_create(xcb_plan** out, const xcb_desc* d) {
       all.insert(all.end(), chunk.begin(), chunk.end());
       pl->group_off.push_back((int64_t)all.size());
     }
+    // per-call records of the largest chunk (xcb_fill_pair_recs), appended to the caller's workspace
+    size_t most = 0;
+    for (size_t c = 0; c + 1 < pl->group_off.size(); ++c) most = std::max<size_t>(most, (size_t)(pl->group_off[c + 1] - pl->group_off[c]));
+    pl->recs_bytes = align_up(most * kGroupJobs * sizeof(PairRec), 256);
     cudaError_t e = cudaMalloc(&pl->d_groups, all.size() * sizeof(PairGroup));
     if (e == cudaSuccess) e = cudaMemcpy(pl->d_groups, all.data(), all.size() * sizeof(PairGroup), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { xcb_plan_destroy(pl); return cuda_fail(e, "group table"); }
@@ -453,7 +459,7 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
   info->n_signals = pl->n_signals;
   info->n_jobs = pl->n_jobs;
   info->jobs_in_flight = pl->jobs_in_flight;
-  info->workspace_bytes = pl->partial_bytes + pl->rnorm_bytes + pl->work_bytes;
+  info->workspace_bytes = pl->partial_bytes + pl->rnorm_bytes + pl->work_bytes + pl->recs_bytes;
   info->nd = pl->g.nd;
   for (int a = 0; a < kMaxDims; ++a) info->dims[a] = pl->g.dims[a];
   info->dtype = pl->dtype;
@@ -462,7 +468,8 @@ extern "C" int xcb_plan_get_info(const xcb_plan* pl, xcb_plan_info* info) {
   if (pl->d_groups && pl->group_off.size() > 1) {
     const int64_t ng = pl->group_off[1] - pl->group_off[0];
     const int64_t nj = std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs);
-    if (nj >= 3 * ng) info->n_groups = (int32_t)ng;
+    const MenuEntry* rowe = menu_find(pl->g.dims[pl->g.nd - 1]);
+    if (nj >= (rowe && rowe->R1 == 16 ? 3 : 2) * ng) info->n_groups = (int32_t)ng;       // (launch_row's criterion)
   }
   return XCB_OK;
 }
@@ -476,6 +483,7 @@ template <class T> struct DeviceRunner {
   cudaStream_t st;
   int64_t chunk = -1; // inverse passes: launch chunk (selects the job groups)
   unsigned long long* counter = nullptr;   // work-item counter of the staged pair product (in the caller's workspace)
+  PairRec* recs = nullptr;                  // per-call group records (caller's workspace, after the inverse scratch)
   int err = 0;        // cudaError_t of a failed launch, or -1 for an oversized grid
   bool operator()(const PassParams<T>& p0, bool row, int kind) {
     const int a = kind % pl->g.nd;
@@ -484,6 +492,7 @@ template <class T> struct DeviceRunner {
       p.groups = pl->d_groups + pl->group_off[(size_t)chunk];
       p.n_groups = (int32_t)(pl->group_off[(size_t)chunk + 1] - pl->group_off[(size_t)chunk]);
       p.work_counter = counter;
+      p.recs_global = recs;
     }
     const int64_t nblocks = (int64_t)p.n_batch * p.tiles_per_batch;
     if (nblocks >= 2147483647LL) { err = -1; return false; }
@@ -546,6 +555,7 @@ static int correlate_t(const xcb_plan* pl, const void* spec, const double* sumsq
   DeviceRunner<T> run{pl, st};
   run.counter = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ws) + pl->partial_bytes +
                                                       pl->rnorm_bytes - 256);
+  if (pl->recs_bytes) run.recs = reinterpret_cast<PairRec*>(static_cast<unsigned char*>(ws) + pl->partial_bytes + pl->rnorm_bytes + pl->work_bytes);
   for (int64_t j0 = 0; j0 < pl->n_jobs; j0 += pl->jobs_in_flight) {
     int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);
     run.chunk = j0 / pl->jobs_in_flight;
@@ -587,6 +597,7 @@ static int correlate_argmax_t(const xcb_plan* pl, const void* spec, const double
   DeviceRunner<T> run{pl, st};
   run.counter = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(ws) + pl->partial_bytes +
                                                       pl->rnorm_bytes - 256);
+  if (pl->recs_bytes) run.recs = reinterpret_cast<PairRec*>(static_cast<unsigned char*>(ws) + pl->partial_bytes + pl->rnorm_bytes + pl->work_bytes);
   int rc = XCB_OK;
   for (int64_t j0 = 0; j0 < pl->n_jobs && rc == XCB_OK; j0 += pl->jobs_in_flight) {
     const int nj = (int)std::min<int64_t>(pl->jobs_in_flight, pl->n_jobs - j0);

@@ -55,7 +55,7 @@ template <class T, int R1, int R2, bool PRO>
 __global__ void __launch_bounds__(Cfg<T, R1, R2>::THREADS)
 xcb_row_pass(const __grid_constant__ PassParams<T> p) {
   extern __shared__ __align__(16) unsigned char smem[];
-  if constexpr (R1 == 16) {
+  if constexpr (RowWarpOk<R1, R2>::value) {
     // one warp per mirrored row pair, warp-synchronous (RowWarp in xcb_passes.h)
     using P = RowWarp<T, R1, R2>;
     constexpr int MODE = PRO ? 2 : 1;
@@ -199,21 +199,25 @@ template <class T, int R1, int R2> int launch_col(const void* params, int64_t nb
 template <class T, int R1, int R2> int launch_row(const void* params, int64_t nblocks, cudaStream_t s) {
   using G = Cfg<T, R1, R2>;
   const PassParams<T>& p = *static_cast<const PassParams<T>*>(params);
-  if constexpr (R1 == 16) {
+  if constexpr (RowWarpOk<R1, R2>::value) {
     using K = PairGrouped<T, R1, R2>;
     static int staged = -1;
     if (staged < 0) { const char* e = getenv("XCB_STAGED"); staged = (e && e[0] == '0') ? 0 : 1; }
     // worth it when the jobs share spectra (>= 3 jobs per group on average); a lone pair keeps
     // the plain warp kernel, which spreads its row pairs over all warps of a CTA
     if (K::kOk && staged && p.load_mode == RL_PROLOGUE && p.n_groups > 0 && p.work_counter &&
-        p.n_batch >= 3 * p.n_groups && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0 &&
+        p.n_batch >= (R1 == 16 ? 3 : 2) * p.n_groups && reinterpret_cast<uintptr_t>(p.spec) % 16 == 0 &&
         p.n_pairs_rows * (int64_t)p.n_groups < 2147483647LL) {
       static int resident_dev[kMaxDev];   // persistent grid (per device)
       const int resident = resident_ctas((const void*)xcb_pair_product_grouped<T, R1, R2>, K::THREADS, K::SMEM, resident_dev);
-      const int64_t items = p.n_pairs_rows * (int64_t)p.n_groups;
+      const int64_t items = ((p.n_pairs_rows + K::PP - 1) / K::PP) * (int64_t)p.n_groups;
       const int64_t grid = items < resident ? items : resident;
       cudaError_t ce = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
       if (ce != cudaSuccess) return (int)ce;
+      if (p.n_groups > K::MAX_REC_GROUPS && p.recs_global) {
+        const int nrec = p.n_groups * K::WARPS;
+        xcb_fill_pair_recs<T><<<(unsigned)((nrec + 255) / 256), 256, 0, s>>>(p, K::WARPS);
+      }
       xcb_pair_product_grouped<T, R1, R2><<<(unsigned)grid, K::THREADS, K::SMEM, s>>>(p);
       return (int)cudaGetLastError();
     }
@@ -240,7 +244,7 @@ template <class T, int R1, int R2> int prepare() {
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(xcb_col_pass_tma<T, R1, R2, COL_INV_AMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmem);
   if (e != cudaSuccess) return (int)e;
-  if constexpr (R1 == 16) {
+  if constexpr (RowWarpOk<R1, R2>::value) {
     e = cudaFuncSetAttribute(xcb_pair_product_grouped<T, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              PairGrouped<T, R1, R2>::SMEM);
     if (e != cudaSuccess) return (int)e;

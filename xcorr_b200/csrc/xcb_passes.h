@@ -56,6 +56,13 @@ struct PairGroup {
   int32_t n_rows, pad2;
 };
 
+// what a consumer warp of the staged pair product needs to know about its job of a group (copy of PairGroup / Job / norms)
+struct alignas(16) PairRec {
+  int32_t batch;        // job index within the launch, -1: this warp has no job in the group
+  uint8_t row_i, row_j, pad0, pad1;
+  double fs;            // 0.5 / (||x_i|| ||x_j||) (0.5 when not normalised or when the norms are per term)
+};
+
 template <class T> struct PassParams {
   // ---- geometry ----
   int32_t N;                 // sub-FFT length of this pass
@@ -93,6 +100,8 @@ template <class T> struct PassParams {
   int32_t n_groups;          // pair product: job groups of this launch (0 = ungrouped kernel)
   const PairGroup* groups;
   unsigned long long* work_counter;   // staged pair product: next work item (zeroed before the launch)
+  struct PairRec* recs_global;        // per (group, consumer warp) records in the caller's workspace, for launches with
+                                      // more groups than the kernel's shared-memory table holds (filled before the launch)
   // ---- pair product (inverse first pass) ----
   int32_t nd;                // number of passes p
   int32_t dims[kMaxDims];    // N_1..N_p
@@ -813,11 +822,17 @@ template <class T, int R1, int R2> struct RowPass {
 //   pair product      : A X_i conj(X_j) summed over blocks / stacked windows,
 //                       publish C | B read mirror, tangle, radix-R1 | C write
 //                       stage layout | D read, twiddle, radix-R2, store
+// which (R1, R2) run warp-synchronously: LN = R1 lanes per row -- a half-warp for the 16 x R2 lengths, a
+// quarter-warp (two mirrored row pairs per warp) for 8 x 8
+template <int R1, int R2> struct RowWarpOk { static constexpr bool value = (R1 == 16 && R2 <= 16) || (R1 == 8 && R2 == 8); };
+
 template <class T, int R1, int R2> struct RowWarp {
-  static_assert(R1 == 16 && R2 <= 16, "one half-warp per row");
+  static_assert(RowWarpOk<R1, R2>::value, "R1 lanes per row, R2 <= R1");
   using G = Cfg<T, R1, R2>;
   using Ctx = ThreadCtx<T, 16>;
-  static constexpr int N = R1 * R2, C = G::C, THREADS = 16 * C;
+  static constexpr int LN = R1;                      // lanes per row
+  static constexpr int PP = 32 / (2 * LN);           // mirrored row pairs per warp
+  static constexpr int N = R1 * R2, C = G::C, THREADS = LN * C;
   static constexpr int P1 = R1 + 1;                  // padded pitch of the stage exchange
   static constexpr int COLBUF = R2 * P1;             // complex elements per row buffer (>= N)
   static constexpr int SMEM = C * COLBUF * 2 * (int)sizeof(T) + THREADS * 8;
@@ -853,8 +868,8 @@ template <class T, int R1, int R2> struct RowWarp {
     if (p.tile_major) { tile = bid / (uint32_t)p.n_batch; batch = bid - tile * (uint32_t)p.n_batch; }
     else { batch = bid / (uint32_t)p.tiles_per_batch; tile = bid - batch * (uint32_t)p.tiles_per_batch; }
     s.batch = (int32_t)batch;
-    const int col = ctx.tid >> 4, side = col & 1;
-    s.j = ctx.tid & 15;
+    const int col = ctx.tid / LN, side = col & 1;
+    s.j = ctx.tid % LN;
     int64_t ra, rb;
     const bool valid = RowPass<T, R1, R2>::pair_rows(p, (int64_t)tile * (C / 2) + (col >> 1), ra, rb);
     const bool self = ra == rb;
@@ -1017,7 +1032,7 @@ template <class T, int R1, int R2> struct RowWarp {
     fft_reg<R2, PK>(v);
   }
 
-  // W_2N^(r R2) = exp(-i pi r / R1): the half-step twiddle of element e = j + r R2 is W_2N^j times this constant,
+  // W_2N^(r R2) = exp(-i pi r / R1) (table of multiples of pi/16): the half-step twiddle of element e = j + r R2 is W_2N^j times this constant,
   // so the pair product needs one table value per lane instead of one per element (the grouped kernel is bound
   // by shared-memory wavefronts: ncu L1/TEX throughput 77 %)
   static XCB_HD cx<T> half_step(int r) {
@@ -1029,7 +1044,7 @@ template <class T, int R1, int R2> struct RowWarp {
                                0.83146961230254524, 0.92387953251128674, 0.98078528040323043, 1, 0.98078528040323043,
                                0.92387953251128674, 0.83146961230254546, 0.70710678118654757, 0.55557023301960218,
                                0.38268343236508989, 0.19509032201612861};
-    cx<T> w; w.x = (T)c[r]; w.y = (T)-sn[r];
+    cx<T> w; w.x = (T)c[r * (16 / R1)]; w.y = (T)-sn[r * (16 / R1)];
     return w;
   }
   template <bool PK> static XCB_HD cx<T> row_w(const cx<T>& wb, int r) {
@@ -1091,7 +1106,8 @@ template <class T, int R1, int R2> struct RowWarp {
     cx<T>* v = ctx.v;
     constexpr bool PK = true;
     const bool on = s.j < R2;
-    const int src = ((ctx.tid & 16) ^ 16) + (R2 - 1 - s.j < 0 ? 0 : R2 - 1 - s.j);
+    const int lane = ctx.tid & 31;                    // partner: same row pair, other side, lane R2 - 1 - j
+    const int src = (lane & ~(2 * LN - 1)) + ((lane & LN) ^ LN) + (R2 - 1 - s.j < 0 ? 0 : R2 - 1 - s.j);
     const T fs = job_scale(p, s);
     cx<T> wb;
     wb.x = T(1); wb.y = T(0);

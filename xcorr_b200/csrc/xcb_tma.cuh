@@ -248,13 +248,27 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
         T best = T(0);
         int slot = -1;
         bool exact = p.unbiased != 0;
+        // every row of the tile can hold a kept lag (all lags wanted: the timelapse kernel) and the scale is
+        // positive: compare the raw values (same order) and scale the winner only
+        const bool all_rows = p.keep_lo[0] <= 0 && p.keep_lo[1] <= p.keep_hi[0] && p.keep_hi[1] >= N && p.escale > T(0);
+        if (all_rows) {
+          best = v[0].x; slot = 0;
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-          const int k = j + r * R1;
-          if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1])) {
-            const T re = v[r].x * p.escale, im = -v[r].y * p.escale;      // the values np.argmax would see
-            if (slot < 0 || re > best) { best = re; slot = 2 * r; } else if (!(re < best)) exact = true;
+          for (int r = 0; r < R2; ++r) {
+            const T re = v[r].x, im = -v[r].y;
+            if (r > 0) { if (re > best) { best = re; slot = 2 * r; } else if (!(re < best)) exact = true; }
             if (im > best) { best = im; slot = 2 * r + 1; } else if (!(im < best)) exact = true;
+          }
+          best *= p.escale;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R2; ++r) {
+            const int k = j + r * R1;
+            if ((k >= p.keep_lo[0] && k < p.keep_hi[0]) || (k >= p.keep_lo[1] && k < p.keep_hi[1])) {
+              const T re = v[r].x * p.escale, im = -v[r].y * p.escale;      // the values np.argmax would see
+              if (slot < 0 || re > best) { best = re; slot = 2 * r; } else if (!(re < best)) exact = true;
+              if (im > best) { best = im; slot = 2 * r + 1; } else if (!(im < best)) exact = true;
+            }
           }
         }
         if (slot >= 0 && !exact) {
@@ -336,44 +350,63 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef XCB_NBUF8
+#define XCB_NBUF8 3
+#endif
 #ifndef XCB_ACC_BATCH
 #define XCB_ACC_BATCH 4     // elements staged per batch when a further term is added (registers: 4 per element)
 #endif
 template <class T, int R1, int R2> struct PairGrouped {
   using W = RowWarp<T, R1, R2>;
   static constexpr int N = W::N, C = W::C, WARPS = W::THREADS / 32;      // consumer warps = jobs per group
+  static constexpr int PP = W::PP;                                       // mirrored row pairs per warp and item
   static constexpr int THREADS = W::THREADS + 32;                        // + one producer warp
   static constexpr int MAX_ROWS = stage_rows<T>();                       // distinct spectra per group
-  static constexpr int NBUF = sizeof(T) == 4 ? 3 : 2;                    // staging ring
+  static constexpr int NBUF = W::LN == 8 ? XCB_NBUF8 : (sizeof(T) == 4 ? 3 : 2);   // staging ring
   static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
-  static constexpr int STAGE_BYTES = MAX_ROWS * 2 * ROW_BYTES;           // [row][side]
+  static constexpr int STAGE_BYTES = MAX_ROWS * PP * 2 * ROW_BYTES;      // [row][pair][side]
+  static constexpr int MINB = W::THREADS <= 128 ? 4 : 2;                 // resident CTAs the kernel is compiled for
   static constexpr int EXCH_OFF = NBUF * STAGE_BYTES;
   static constexpr int BAR_OFF = EXCH_OFF + C * W::COLBUF * 2 * (int)sizeof(T);
   static constexpr int MAIL_OFF = BAR_OFF + 64;
   // per-CTA tables (filled once): the half-step twiddles W_2N^e of the row axis and, when the launch has few
   // enough groups, one record per (group, consumer warp) -- so that an item starts from shared memory
   // instead of a chain of dependent global loads (group -> job -> norms)
-  static constexpr int TW2_OFF = MAIL_OFF + NBUF * 64;
+  static constexpr int TW2_OFF = MAIL_OFF + NBUF * 256;
   static constexpr int REC_OFF = TW2_OFF + N * 2 * (int)sizeof(T);
-  static constexpr int SMEM_MAX = (227 * 1024 - 2 * 1024) / 2;                                    // two CTAs per SM
+  static constexpr int SMEM_MAX = (227 * 1024 - MINB * 1024) / MINB;                              // MINB CTAs per SM
   static constexpr int MAX_REC_GROUPS = (SMEM_MAX - REC_OFF) / (WARPS * 16) > 0 ? (SMEM_MAX - REC_OFF) / (WARPS * 16) : 0;
   static constexpr int SMEM = REC_OFF + MAX_REC_GROUPS * WARPS * 16;
-  static constexpr bool kOk = (ROW_BYTES % 16) == 0 && REC_OFF <= SMEM_MAX && 2 * MAX_ROWS <= 32;
+  static constexpr bool kOk = (ROW_BYTES % 16) == 0 && REC_OFF <= SMEM_MAX && 2 * PP * MAX_ROWS <= 32 && PP <= 2;
 };
 
-// what a consumer warp needs to know about its job of a group (shared-memory copy of PairGroup / Job / norms)
-struct alignas(16) PairRec {
-  int32_t batch;        // job index within the launch, -1: this warp has no job in the group
-  uint8_t row_i, row_j, pad0, pad1;
-  double fs;            // 0.5 / (||x_i|| ||x_j||) (0.5 when not normalised or when the norms are per term)
-};
+// the record of consumer warp `w` of group `g` (PairRec, xcb_passes.h)
+template <class T> __device__ __forceinline__ PairRec make_pair_rec(const PassParams<T>& p, const PairGroup& g, int w) {
+  PairRec r;
+  r.batch = -1; r.row_i = r.row_j = r.pad0 = r.pad1 = 0; r.fs = 0.5;
+  if (w < g.n_jobs) {
+    r.batch = g.job[w];
+    r.row_i = g.ji[w];
+    r.row_j = (uint8_t)(g.n_i + g.jj[w]);
+    const Job jb = p.jobs[r.batch];
+    if (p.normalize && p.stack_sig_stride == 0) r.fs = 0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j];
+  }
+  return r;
+}
+// fills p.recs_global (WARPS records per group) before a launch whose groups do not fit the kernel's shared table
+template <class T> __global__ void xcb_fill_pair_recs(const __grid_constant__ PassParams<T> p, int warps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.n_groups * warps) p.recs_global[i] = make_pair_rec(p, p.groups[i / warps], i % warps);
+}
 
 // what the producer tells the consumers about the item whose first term sits in a buffer
-template <class T> struct alignas(64) PairMail {
-  int64_t item;        // -1: no more work
-  int64_t ra, rb;
-  cx<T> wrow[2];
+template <class T> struct alignas(256) PairMail {
+  int32_t item;        // -1: no more work
+  int32_t ra[2], rb[2];        // per row pair of the item (-1: past the last pair)
+  cx<T> wrow[2][2];            // [pair][side]
+  alignas(16) PairRec rec[kGroupJobs];   // the item's records, bulk-copied from p.recs_global (launches with many groups)
 };
+static_assert(sizeof(PairMail<double>) <= 256, "mail slots are 256 bytes apart");
 
 // (Two CTAs per SM: ptxas budgets 96 registers for the float kernel -- the register file is allocated for an even
 // number of warps, so the 9 warps count as 10; __maxnreg__(112) leaves ONE CTA per SM: 3.9 -> 5.7 ms.  Forcing the
@@ -381,12 +414,12 @@ template <class T> struct alignas(64) PairMail {
 // (ncu shows ptxas reusing one register pair per element: LDS, FFMA2, FFMA2, LDS ...) spills at 96 registers and
 // measured 4.38 / 4.09 / 4.31 ms against 3.91 ms for the compiler's own schedule.)
 template <class T, int R1, int R2>
-__global__ void __launch_bounds__(PairGrouped<T, R1, R2>::THREADS, 2)
+__global__ void __launch_bounds__(PairGrouped<T, R1, R2>::THREADS, PairGrouped<T, R1, R2>::MINB)
 xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   using K = PairGrouped<T, R1, R2>;
   using W = RowWarp<T, R1, R2>;
   using RP = RowPass<T, R1, R2>;
-  constexpr int N = K::N, NBUF = K::NBUF;
+  constexpr int N = K::N, NBUF = K::NBUF, PP = K::PP, LN = W::LN;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + K::BAR_OFF);   // [NBUF] filled by the bulk copies
   uint64_t* empty = full + NBUF;                                         // [NBUF] released by the consumer warps
@@ -394,7 +427,8 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   PairMail<T>* mail = reinterpret_cast<PairMail<T>*>(smem_raw + K::MAIL_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t n_items = p.n_pairs_rows * (int64_t)p.n_groups;          // item = row pair * n_groups + group
+  // item = (block of PP row pairs) * n_groups + group
+  const int64_t n_items = ((p.n_pairs_rows + PP - 1) / PP) * (int64_t)p.n_groups;
   const int n_terms = p.n_stack;
 
   if (tid == 0) {
@@ -403,23 +437,11 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   }
   cx<T>* tw2 = reinterpret_cast<cx<T>*>(smem_raw + K::TW2_OFF);
   PairRec* recs = reinterpret_cast<PairRec*>(smem_raw + K::REC_OFF);
-  const bool per_term_all = p.normalize && p.stack_sig_stride != 0;
   const bool use_recs = p.n_groups <= K::MAX_REC_GROUPS;
   for (int i = tid; i < N; i += K::THREADS) tw2[i] = ld_ro(p.tw2_inner + i);
   if (use_recs) {
     for (int i = tid; i < p.n_groups * K::WARPS; i += K::THREADS) {
-      const PairGroup& g = p.groups[i / K::WARPS];
-      const int w = i % K::WARPS;
-      PairRec r;
-      r.batch = -1; r.row_i = r.row_j = r.pad0 = r.pad1 = 0; r.fs = 0.5;
-      if (w < g.n_jobs) {
-        r.batch = g.job[w];
-        r.row_i = g.ji[w];
-        r.row_j = (uint8_t)(g.n_i + g.jj[w]);
-        const Job jb = p.jobs[r.batch];
-        if (p.normalize && !per_term_all) r.fs = 0.5 * p.rnorm[jb.sig_i] * p.rnorm[jb.sig_j];
-      }
-      recs[i] = r;
+      recs[i] = make_pair_rec(p, p.groups[i / K::WARPS], i % K::WARPS);
     }
   }
   __syncthreads();
@@ -432,11 +454,11 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     // so it is software pipelined: while the copies of item k are issued, the record
     // of item k+1 is in flight and the counter of item k+2 is being claimed. ----
     struct Raw {                                        // loads issued, values not yet used
-      int64_t item, ra, rb, spec;
+      int64_t item, ra, rb, spec;                       // ra, rb: the rows of THIS lane's pair
       int32_t n_i, n_rows;
       cx<T> hi, lo;
     };
-    const int r = lane >> 1, sd = lane & 1;
+    const int r = lane / (2 * PP), pp = (lane >> 1) % PP, sd = lane & 1;   // staged row, row pair, side of this lane
     auto claim = [&]() -> unsigned long long { return lane == 0 ? atomicAdd(p.work_counter, 1ULL) : 0ULL; };
     auto start = [&](unsigned long long tok) {
       Raw w;
@@ -446,12 +468,12 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       if (w.item < n_items) {
         const int64_t q = w.item / p.n_groups;
         const PairGroup& g = p.groups[w.item - q * p.n_groups];
-        RP::pair_rows(p, q, w.ra, w.rb);
+        if (!RP::pair_rows(p, q * PP + pp, w.ra, w.rb)) w.ra = w.rb = -1;      // past the last row pair
         w.n_i = g.n_i;
         w.n_rows = g.n_rows;
         w.spec = g.rows[r < 2 * kGroupJobs ? r : 0];
-        if (lane < 2) {
-          const uint32_t kl = RP::klow_of_row(p, lane ? w.rb : w.ra);
+        if (lane < 2 * PP && w.ra >= 0) {
+          const uint32_t kl = RP::klow_of_row(p, sd ? w.rb : w.ra);
           w.hi = ld_ro(p.tw2_hi + (kl >> p.tw_shift));
           w.lo = ld_ro(p.tw2_lo + (kl & p.tw_mask));
         }
@@ -470,23 +492,30 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       }
       const Raw nxt = start(tok);                       // its loads are in flight during this item's copies
       tok = claim();
-      const int sides = cur.ra == cur.rb ? 1 : 2;
-      const bool mine = r < cur.n_rows && sd < sides;
+      // a self-mirrored row pair stages one side only, a pair past the end nothing
+      const bool mine = r < cur.n_rows && r < K::MAX_ROWS && cur.ra >= 0 && (sd == 0 || cur.ra != cur.rb);
+      const uint32_t n_copies = __popc(__ballot_sync(0xffffffffu, mine));
       const int64_t src = cur.spec + (sd ? cur.rb : cur.ra) * N;
       const cx<T> wr = cmul(cur.hi, cur.lo);
       for (int w = 0; w < n_terms; ++w, ++step) {
         const int buf = (int)(step % NBUF);
         mbar_wait_backoff(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
-        if (w == 0 && lane < 2) {
-          mail[buf].wrow[lane] = wr;
-          if (lane == 0) { mail[buf].item = cur.item; mail[buf].ra = cur.ra; mail[buf].rb = cur.rb; }
+        if (w == 0 && lane < 2 * PP) {
+          mail[buf].wrow[pp][sd] = wr;
+          if (sd == 0) { mail[buf].ra[pp] = (int32_t)cur.ra; mail[buf].rb[pp] = (int32_t)cur.rb; }
+          if (lane == 0) mail[buf].item = (int32_t)cur.item;
         }
         __syncwarp();
-        if (lane == 0) mbar_expect_tx(&full[buf], (uint32_t)(cur.n_rows * sides * K::ROW_BYTES));
+        const bool mail_recs = w == 0 && !use_recs && p.recs_global != nullptr;
+        if (lane == 0) {
+          mbar_expect_tx(&full[buf], n_copies * (uint32_t)K::ROW_BYTES + (mail_recs ? K::WARPS * 16u : 0u));
+          if (mail_recs)
+            bulk_load(&mail[buf].rec[0], p.recs_global + (cur.item % p.n_groups) * K::WARPS, K::WARPS * 16u, &full[buf]);
+        }
         if (mine) {
           const int64_t toff = p.use_blk_off ? (r < cur.n_i ? p.blk_off_i[w] : p.blk_off_j[w]) : w * p.stack_spec_stride;
-          bulk_load(smem_raw + buf * K::STAGE_BYTES + (r * 2 + sd) * K::ROW_BYTES, p.spec + src + toff, K::ROW_BYTES,
-                    &full[buf]);
+          bulk_load(smem_raw + buf * K::STAGE_BYTES + ((r * PP + pp) * 2 + sd) * K::ROW_BYTES, p.spec + src + toff,
+                    K::ROW_BYTES, &full[buf]);
         }
       }
       cur = nxt;
@@ -495,26 +524,33 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
   }
 
   // ---- consumer warps: one job of the group each ----
-  const int side = (tid >> 4) & 1;
+  const int side = (tid / LN) & 1, pp = ((tid & 31) / (2 * LN));       // side and row pair of this lane within its warp
   typename W::Ctx ctx;
   ctx.tid = tid;
   uint32_t step = 0;
   const bool per_term = p.normalize && p.stack_sig_stride != 0;
-  const cx<T> w_inner = ld_ro(p.tw_inner + (tid & 15));             // W_N^j of this lane, item independent
+  const cx<T> w_inner = ld_ro(p.tw_inner + (tid % LN));             // W_N^j of this lane, item independent
   for (;;) {
     int buf = (int)(step % NBUF);
     mbar_wait(&full[buf], (step / NBUF) & 1u);         // (no back-off: a sleeping warp wakes up to 0.5 us late)
-    const int32_t item = (int32_t)mail[buf].item;       // (the launch guarantees fewer than 2^31 items)
+    const int32_t item = mail[buf].item;                // (the launch guarantees fewer than 2^31 items)
     if (item < 0) break;
-    const int32_t ra = (int32_t)mail[buf].ra, rb = (int32_t)mail[buf].rb;
+    const int32_t ra = mail[buf].ra[pp], rb = mail[buf].rb[pp];
     const int gi = (int)((uint32_t)item % (uint32_t)p.n_groups);
     const bool self = ra == rb;
+    // the shuffle path needs every row pair of the warp to be an ordinary one (neither row 0 nor self-mirrored)
+    bool ordinary = ra > 0 && ra != rb;
+    if (PP == 2) {
+      const int32_t oa = mail[buf].ra[pp ^ 1], ob = mail[buf].rb[pp ^ 1];
+      ordinary = ordinary && oa > 0 && oa != ob;
+    }
     typename W::Slot s;
     bool has_job;
     int row_i, row_j;
     T fs_rec = T(0.5);
-    if (use_recs) {
-      const PairRec rec = recs[gi * K::WARPS + warp];
+    const bool mailed = !use_recs && p.recs_global != nullptr;
+    if (use_recs || mailed) {
+      const PairRec rec = use_recs ? recs[gi * K::WARPS + warp] : mail[buf].rec[warp];
       has_job = rec.batch >= 0;
       s.batch = has_job ? rec.batch : 0;
       row_i = rec.row_i; row_j = rec.row_j;
@@ -527,20 +563,20 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     }
     s.row = side ? rb : ra;
     s.row0 = ra == 0;
-    s.j = tid & 15;
-    s.active = has_job && !(side && self);
-    s.wrow = mail[buf].wrow[side];
+    s.j = tid % LN;
+    s.active = has_job && ra >= 0 && !(side && self);
+    s.wrow = mail[buf].wrow[pp][side];
     s.w_inner = w_inner;
     s.tw2 = tw2;
-    s.fs = (use_recs && !per_term) ? fs_rec : T(-1);
-    const int col = tid >> 4;
+    s.fs = ((use_recs || mailed) && !per_term) ? fs_rec : T(-1);
+    const int col = tid / LN;
     s.buf = exch + col * W::COLBUF;
     s.mbuf = exch + (self ? col : (col ^ 1)) * W::COLBUF;
     ctx.bid = item;
     const bool lane_on = s.active && s.j < R2;
     Job jb;
     jb.spec_i = jb.spec_j = 0; jb.out_off = 0; jb.sig_i = jb.sig_j = 0;
-    if (!use_recs || per_term || s.row0) jb = p.jobs[s.batch];      // (row 0 reads the spectra's slot 0 directly)
+    if (!(use_recs || mailed) || per_term || s.row0) jb = p.jobs[s.batch];      // (row 0 reads the spectra's slot 0 directly)
 
     cx<T>* v = ctx.v;
     if (per_term || !lane_on) {
@@ -555,7 +591,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       if (lane_on) {
         const cx<T>* st0 = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
         const cx<T>* st1 = reinterpret_cast<const cx<T>*>(smem_raw + buf1 * K::STAGE_BYTES) + s.j;
-        const int oa = (row_i * 2 + side) * N, ob = (row_j * 2 + side) * N;
+        const int oa = ((row_i * PP + pp) * 2 + side) * N, ob = ((row_j * PP + pp) * 2 + side) * N;
         W::template accumulate_two<true, XCB_ACC_BATCH>(v, st0 + oa, st0 + ob, st1 + oa, st1 + ob);
       }
       __syncwarp();
@@ -570,8 +606,8 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       }
       if (lane_on) {
         const cx<T>* st = reinterpret_cast<const cx<T>*>(smem_raw + buf * K::STAGE_BYTES) + s.j;
-        const cx<T>* sa = st + (row_i * 2 + side) * N;
-        const cx<T>* sb = st + (row_j * 2 + side) * N;
+        const cx<T>* sa = st + ((row_i * PP + pp) * 2 + side) * N;
+        const cx<T>* sb = st + ((row_j * PP + pp) * 2 + side) * N;
         if (per_term) {
           const T sw = T(p.rnorm[jb.sig_i + w * p.stack_sig_stride] * p.rnorm[jb.sig_j + w * p.stack_sig_stride]);
           W::template accumulate<true>(v, sa, sb, sw, true);
@@ -584,7 +620,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[buf]);       // this warp is done with the buffer (and its mail)
     }
-    if (sizeof(T) == 4 && has_job && !self && !s.row0) {
+    if (sizeof(T) == 4 && has_job && ordinary) {
       // mirrored elements by warp shuffle (warp-uniform branch; lanes j >= R2 hold zeros and only take part)
       W::phase_b_shfl(p, ctx, s);
     } else {
