@@ -360,7 +360,12 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         sub_timers["ms_preprocess"] = lambda: prog.run(raw)
         units, unit = len(pairs), "pair-days/s"
         alg = b_alg(R, len(pairs), n, 1_620_000, b, n_raw)
-        extra = dict(passes=list(plan.dims), blocks=plan.n_blocks)
+        # the chain is bound by FP64 arithmetic, not by bytes: 10 second-order sections x 5 multiply-adds per raw
+        # sample in float64 (exact recurrence, scipy.signal.sosfilt order) -- reported beside the byte roofline
+        extra = dict(passes=list(plan.dims), blocks=plan.n_blocks,
+                     preprocess_fp64_fma_per_step=int(R * n_raw * 10 * 5),
+                     note="step_roofline_frac counts bytes only; the preprocessing chain (ms_preprocess) is FP64-throughput "
+                          "bound: fp64_fma_per_step / ms_preprocess is its achieved multiply-add rate")
         desc = "5 receivers / 10 pairs, 24h@250Hz raw -> detrend, taper, 3-12 Hz bandpass, decimate 5 -> cc at 50 Hz, lags (0, 9h)"
     elif name in ("cfg4", "cfg4_f64"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
@@ -394,7 +399,8 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         # the masked triangle of scripts/timelapse.py:348-360, tiled over the ranks; every rank transforms
         # its share of the days, the half spectra are all-gathered once per step
         pairs = timelapse_pairs(D)
-        mine = pairs[rank::world]
+        per_rank = -(-len(pairs) // world)                    # contiguous, equal shares of the (i-major) triangle: a rank's
+        mine = pairs[rank * per_rank:(rank + 1) * per_rank]   # day pairs share days, which the staged pair product needs
         plan = Correlate2dPlan(F, T, D, mine, dtype=dt, device=dev, day_shard=(rank, world) if world > 1 else None)
         g = torch.Generator(device=dev)
         g.manual_seed(5)
@@ -404,12 +410,15 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         def step():
             plan.forward(my_days)
             plan.correlate_argmax()
-        units, unit = len(pairs) / world, "day-pairs/s"      # per rank; x world below
+        units, unit = len(pairs) / world, "day-pairs/s"      # per rank on average; x world below
         A = 2 * plan.plan.fft_len // 2 * b                                  # bytes of one padded half spectrum
         alg = (D * (F * T * b + 3 * A) + len(pairs) * 4 * A) / len(pairs)   # F = FTb + 3A, I = 4A
         extra = dict(passes=list(plan.plan.dims), days=D, day_pairs=len(pairs),
                      collective="all_gather of the day half-spectra (NCCL)" if world > 1 else None,
                      scaling="strong")
+        if world > 1:
+            sub_timers["ms_all_gather"] = plan.all_gather      # the collective alone (day half-spectra, NCCL)
+            extra["all_gather_bytes_received_per_rank"] = int(plan.plan.spec.numel() * plan.plan.spec.element_size())
         desc = f"{D} day spectrograms 1024x128 -> {len(pairs)} day pairs (masked triangle), value + (dF, dT) per pair (timelapse kernel)"
     else:
         raise SystemExit(f"unknown config {name}")

@@ -82,6 +82,10 @@ class Correlate2dPlan:
         the spectra and the norms."""
         x = self.embed(images)
         self.fwd.forward(x)
+        self.all_gather()
+
+    def all_gather(self):
+        """The one collective of the sharded plan: every rank's half spectra and norms to every rank (NCCL)."""
         if self.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(torch.view_as_real(self.plan.spec), torch.view_as_real(self.fwd.spec))
