@@ -317,6 +317,37 @@ def test_staged_pair_product_chunks_stacking_and_groups(xb, orc, dtype):
         assert np.max(np.abs(got[q, 0] - ref)) <= tol * np.max(np.abs(ref))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_quarter_warp_row_axis_with_many_groups(xb, orc, dtype):
+    """8 x 8 row axis (the 64^3 transform of config 5): warp-synchronous row pass with a quarter-warp per row and
+    the staged pair product with two mirrored row pairs per warp.  40 receivers / 780 pairs give more job groups
+    than the kernel's shared-memory record table holds (records mailed with the rows); the number of row pairs is
+    odd (the last item holds one pair only); the first and the middle row mirror themselves."""
+    import torch
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    tol = TOL[np.dtype(dtype)]
+    n, R = 4_000, 40
+    pairs = xb.all_pairs(R)
+    rec = orc.synthetic_receivers(R, n, seed=4242, delay=5)
+    x = torch.from_numpy(rec.astype(dtype)).cuda().unsqueeze(1)
+    for kw in (dict(dims=(64, 64)), dict(dims=(64, 64), max_work_bytes=100 * 64 * 64 * (8 if dtype == np.float32 else 16))):
+        plan = xb.CorrelationPlan(n, R, pairs, dtype=tdt, n_blocks=1, **kw)
+        assert plan.dims == (64, 64) and plan.n_groups > 0, (plan.dims, plan.n_groups)
+        got = plan(x).cpu().numpy()
+        idx, val = plan.correlate_argmax()
+        torch.cuda.synchronize()
+        for q, (i, j) in enumerate(pairs):
+            ref = orc.cc(rec[i].astype(dtype).astype(np.float64), rec[j].astype(dtype).astype(np.float64), unbiased=False)
+            assert np.max(np.abs(got[q, 0] - ref)) <= tol * np.max(np.abs(ref)), (kw, q)
+            assert int(idx[q, 0]) == int(np.argmax(got[q, 0])), (kw, q)      # fused arg-max == arg-max of the stored CCF
+    # a lone pair keeps the plain warp kernel (no groups)
+    plan = xb.CorrelationPlan(n, 2, [(0, 1)], dtype=tdt, dims=(64, 64), n_blocks=1)
+    assert plan.n_groups == 0
+    got = plan(x[:2]).cpu().numpy()
+    ref = orc.cc(rec[0].astype(dtype).astype(np.float64), rec[1].astype(dtype).astype(np.float64), unbiased=False)
+    assert np.max(np.abs(got[0, 0] - ref)) <= tol * np.max(np.abs(ref))
+
+
 def test_graphed_step_equals_direct_launches(xb, orc):
     """Config 1 shape in small: the CUDA-graph replay of forward + correlate gives bit-identical CCFs, also after
     the input buffer is refilled in place."""
