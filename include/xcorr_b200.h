@@ -176,6 +176,13 @@ typedef struct xcb_sos {
                               * chunk to unit start states.  Given (decimate >= 2, chunk % decimate == 0, forward), the
                               * kept outputs are formed as zero-state output + response * start state instead of
                               * rerunning the cascade over every input sample (exact by linearity). */
+  int32_t carry_window;      /* K >= 1: the caller certifies ||carry^K||_inf <= 2^-80, i.e. a chunk's start state no
+                              * longer depends (to far below float64 rounding) on anything older than K chunks; the
+                              * start states are then formed in ONE parallel launch, every run of 32 chunks warmed up
+                              * over the K chunks before it, instead of fold / sweep / expand over the whole trace.
+                              * 0: unknown or slowly decaying filter (e.g. a 0.05 Hz high-pass at 250 Hz) -> the
+                              * hierarchical, unconditionally exact form */
+  int32_t reserved;
 } xcb_sos;
 
 /* stats[s] = {sum x, sum i*x, x[0], x[n-1]} (device double[n_signals][4]) */

@@ -158,3 +158,35 @@ def test_polyphase_fir_rate_change_matches_scipy(env, dtype, tol):
     with pytest.raises(RuntimeError):
         sp.process(torch.zeros((1, 100), device="cuda"), [("resample_poly", {"up": 1, "down": 5, "padtype": "line"})],
                    sampling_rate=fs, raise_error=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_windowed_carry_equals_hierarchical_carry(env, dtype):
+    """xcb_sos.carry_window (start states of fast-decaying cascades in one parallel launch, every run of chunks
+    warmed up over K chunks) against the unconditionally exact fold / sweep / expand form of the same program,
+    forward (decimating, zero-input fast path) and zero-phase (reverse pass, full-rate stores); a slowly decaying
+    high-pass must keep the hierarchical form."""
+    torch, _, sp, _, _ = env
+    fs, n = 250.0, 400_003                      # > 2 x 32 chunks, ragged last chunk, odd length
+    x = raw_traces(3, n, fs, 77)
+    x[1, 100_000:100_050] += 1e6                # a glitch eight orders above the noise
+    xt = torch.from_numpy(x.astype(dtype)).cuda()
+    for ops in (CFG2_OPS,
+                [("filter", {"type": "bandpass", "freqmin": 3.0, "freqmax": 12.0, "zerophase": True})]):
+        prog = sp.PreprocessProgram(ops, n, fs)
+        prog._host_design()
+        windows = [st[1].f.carry_window for st in prog.steps if st[0] == 'stage' and st[1].f is not None]
+        assert windows and all(1 <= w <= 16 for w in windows)
+        got = prog.run(xt, out_dtype=torch.float64).cpu().numpy()
+        for st in prog.steps:
+            if st[0] == 'stage' and st[1].f is not None:
+                st[1].f.carry_window = 0
+        ref = prog.run(xt, out_dtype=torch.float64).cpu().numpy()
+        assert np.isfinite(ref).all()
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(got - ref) / scale).max() <= 1e-14
+        half = got.shape[1] // 2                # long after the glitch: absolute agreement at the noise's own rounding
+        assert np.abs(got[1, half:] - ref[1, half:]).max() <= 1e-13
+    slow = sp.PreprocessProgram([("filter", {"type": "highpass", "freq": 0.05})], n, fs)
+    slow._host_design()
+    assert [st[1].f.carry_window for st in slow.steps if st[0] == 'stage' and st[1].f is not None] == [0]

@@ -89,6 +89,8 @@ class xcb_sos(ctypes.Structure):
         ("carry_group", ctypes.POINTER(ctypes.c_double)),
         ("init_state", ctypes.POINTER(ctypes.c_double)),
         ("zin_response", ctypes.POINTER(ctypes.c_double)),
+        ("carry_window", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 

@@ -155,6 +155,23 @@ template <int S> __device__ __forceinline__ void load_coefficients(const SosCoef
     }
 }
 
+// Uses every loaded coefficient (and start-state) register ONCE before the sample loop.  Their first use would
+// otherwise be a multiply-add inside the loop, which then carries the wait on the scoreboard of those loads for
+// good -- and the scoreboard is the one the loop's own batch loads signal, so every iteration waited for the
+// batch it had just requested (ncu source page: 25 % of the stall samples of phase 1 on one DFMA,
+// `long_scoreboard`).  The sum is NaN only if a coefficient or state is NaN / the states hold opposite
+// infinities -- then every output of the chunk is NaN anyway, which is what seeding z[0] with it gives.
+template <int S> __device__ __forceinline__ void settle_loaded_values(const SosRegs<S>& f, double (&z)[2 * S]) {
+  double acc = 0.0;
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc += f.c[s][k];
+#pragma unroll
+  for (int k = 0; k < 2 * S; ++k) acc += z[k];
+  if (acc != acc) z[0] = acc;
+}
+
 template <int S> __device__ __forceinline__ double cascade(const SosRegs<S>& f, double (&z)[2 * S], double v) {
 #pragma unroll
   for (int s = 0; s < S; ++s) {
@@ -166,8 +183,73 @@ template <int S> __device__ __forceinline__ double cascade(const SosRegs<S>& f, 
   return v;
 }
 
+constexpr int kBatchConst = 8;
+// ---- batches of kBatch consecutive samples of one thread's chunk, in processing order (dir = +1 / -1) ----
+template <class T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int V = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int V = 2; };
+template <class T> __device__ __forceinline__ void vec_unpack(const float4& t, T (&e)[4]) { e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
+template <class T> __device__ __forceinline__ void vec_unpack(const double2& t, T (&e)[2]) { e[0] = t.x; e[1] = t.y; }
+__device__ __forceinline__ float4 vec_pack(const float (&e)[4]) { return make_float4(e[0], e[1], e[2], e[3]); }
+__device__ __forceinline__ double2 vec_pack(const double (&e)[2]) { return make_double2(e[0], e[1]); }
+
+// is the batch that starts at p (first sample in processing order) one run of aligned 16-byte vectors?
+template <class T> __device__ __forceinline__ bool batch_aligned(const T* p, int dir) {
+  const uintptr_t lo = reinterpret_cast<uintptr_t>(dir > 0 ? p : p - (kBatchConst - 1));
+  return p != nullptr && (lo & 15u) == 0;
+}
+// The batch comes back in MEMORY order (d[k] = lowest address + k) whatever the direction: the caller picks
+// element b of the processing order when it consumes it.  (Reordering here put a select on every loaded
+// register right behind the load, i.e. the wait for the NEXT batch in front of the current batch's arithmetic:
+// a quarter of all stall samples of phase 1.)
+template <class T>
+__device__ __forceinline__ void load_batch(const T* __restrict__ p, int dir, bool vec, T (&d)[kBatchConst]) {
+  constexpr int V = Vec16<T>::V;
+  using VT = typename Vec16<T>::type;
+  const T* lo = dir > 0 ? p : p - (kBatchConst - 1);
+  if (vec) {
+    const VT* q = reinterpret_cast<const VT*>(lo);
+#pragma unroll
+    for (int k = 0; k < kBatchConst / V; ++k) {
+      T e[V];
+      vec_unpack(__ldg(q + k), e);
+#pragma unroll
+      for (int m = 0; m < V; ++m) d[k * V + m] = e[m];
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < kBatchConst; ++b) d[b] = __ldg(lo + b);
+  }
+}
+template <class T> __device__ __forceinline__ T batch_elem(const T (&d)[kBatchConst], int dir, int b) {
+  return dir > 0 ? d[b] : d[kBatchConst - 1 - b];
+}
+template <class T>
+__device__ __forceinline__ void store_batch(T* __restrict__ p, int dir, bool vec, const T (&d)[kBatchConst]) {
+  constexpr int V = Vec16<T>::V;
+  using VT = typename Vec16<T>::type;
+  if (vec) {
+    VT* q = reinterpret_cast<VT*>(dir > 0 ? p : p - (kBatchConst - 1));
+#pragma unroll
+    for (int k = 0; k < kBatchConst / V; ++k) {
+      T e[V];
+#pragma unroll
+      for (int m = 0; m < V; ++m) e[m] = dir > 0 ? d[k * V + m] : d[kBatchConst - 1 - (k * V + m)];
+      q[k] = vec_pack(e);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < kBatchConst; ++b) p[dir * b] = d[b];
+  }
+}
+
+constexpr int kPrefetch = 96;   // samples ahead of the current batch that the scan asks into L2
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// resident CTAs the scan kernels are compiled for: the register allocation of the long cascades flips between
+// 148 and 188 registers with unrelated edits; three CTAs (<= 168 registers) is what the 10-section chain needs
+template <int S> constexpr int kScanMinBlocks = S >= 11 ? 2 : (S >= 5 ? 3 : 4);
 constexpr int kIlp = 1;   // chunks per thread (the dispatch below sizes its grids with it)
-constexpr int kBatch = 8; // samples fetched ahead per thread: the loads leave the serial recurrence's critical path
+constexpr int kBatch = kBatchConst; // samples fetched ahead per thread: the loads leave the serial recurrence's critical path
 
 // One chunk of one signal through the cascade, from state z.  Everything that does not change inside a chunk
 // is decided once per chunk so that a sample costs its 5 S multiply-adds plus a handful of instructions (the
@@ -179,59 +261,109 @@ constexpr int kBatch = 8; // samples fetched ahead per thread: the loads leave t
 //   * kept (decimated) samples are tracked with a counter instead of a division.
 // MODE 1: phase 1 -- zero-state pass; writes the kept zero-state outputs to yzs when given.
 // MODE 3: phase 3 -- true start state; stores the (kept) outputs to y.
-template <int S, class TI, class TO, int MODE>
-__device__ __forceinline__ void scan_chunk(const TI* __restrict__ xi, int n, int t0, int len, const SosRegs<S>& fr,
-                                           double (&z)[2 * S], const PointwiseDev& pw, double c0, double c1,
-                                           int reverse, int decim, double* __restrict__ yz, TO* __restrict__ yo) {
+template <int S, class TI, class TO, int MODE, bool RAMPS>
+__device__ __forceinline__ void scan_chunk_impl(const TI* __restrict__ xi, int n, int t0, int len,
+                                                const SosRegs<S>& fr, double (&z)[2 * S], const PointwiseDev& pw,
+                                                double c0, double c1, int reverse, int decim,
+                                                double* __restrict__ yz, TO* __restrict__ yo) {
   const int dir = reverse ? -1 : 1;
-  int i = reverse ? n - 1 - t0 : t0;                       // signal index of the chunk's first sample
+  const int i = reverse ? n - 1 - t0 : t0;                 // signal index of the chunk's first sample
   const TI* px = xi + i;
-  // does the chunk touch a taper ramp?
-  const int i_lo = reverse ? i - (len - 1) : i, i_hi = reverse ? i : i + (len - 1);
-  const bool ramps = i_lo < pw.taper_left || i_hi >= n - pw.taper_right;
   const bool trend = pw.detrend != 0;
   double di = (double)i;
   const double ddir = (double)dir;
   int next_keep = ((t0 + decim - 1) / decim) * decim - t0;  // local index of the first kept sample (once per chunk)
   int64_t ko = ((int64_t)t0 + decim - 1) / decim;           // its output index
-  auto sample = [&](double v, int jl) {
+  auto sample = [&](double v, double w, int jl) -> double {
     if (trend) v -= fma(c1, di, c0);
-    if (ramps) {
-      const int ii = i + dir * jl;
-      if (ii < pw.taper_left) v *= __ldg(pw.ramp_left + ii);
-      else if (ii >= n - pw.taper_right) v *= __ldg(pw.ramp_right + (ii - (n - pw.taper_right)));
-    }
+    if (RAMPS) v *= w;
     di += ddir;
     const double y = cascade<S>(fr, z, v);
     if (MODE == 1) {
       if (yz && jl == next_keep) { yz[ko++] = y; next_keep += decim; }
-    } else {
-      if (decim == 1) yo[i + dir * jl] = (TO)y;
-      else if (jl == next_keep) { yo[ko++] = (TO)y; next_keep += decim; }
+    } else if (decim != 1) {                                  // (decim == 1: the caller stores whole batches)
+      if (jl == next_keep) { yo[ko++] = (TO)y; next_keep += decim; }
     }
+    return y;
   };
+  // taper weight of signal index ii (1 between the ramps).  The weights of a batch are fetched one batch ahead
+  // like the samples: read inside `sample` they put a dependent L2 load in front of every cascade step, the ~20
+  // ramp chunks of a trace ran several times longer than the others, and the one at the very end of the grid
+  // (right ramp of the last trace) held the whole launch: most SMs idle for the last quarter of phase 1 (ncu:
+  // sm__cycles_active avg 0.75 of max).
+  auto taper_w = [&](int ii) -> double {
+    if (ii < pw.taper_left) return __ldg(pw.ramp_left + ii);
+    if (ii >= n - pw.taper_right) return __ldg(pw.ramp_right + (ii - (n - pw.taper_right)));
+    return 1.0;
+  };
+  // Batches move as 16-byte vectors when the chunk's first batch is 16-byte aligned in its direction (chunk
+  // lengths are multiples of kBatch, so then every full batch is).  A thread walks its own chunk, so a warp-wide
+  // load touches 32 different lines either way: one L1 wavefront per lane and instruction -- with scalar loads
+  // that was one wavefront per SAMPLE and lane, and the L1 data stage (not FP64, not HBM) bound phases 1 and 3:
+  // 67 % `L1 wavefronts`, long_scoreboard the top stall, the 4-section cascade as slow as the 10-section one
+  // (profiles/ncu_r02_preprocess.md).
+  const bool vec_in = batch_aligned<TI>(px, dir);
+  TO* const py = (MODE == 3 && decim == 1) ? yo + i : nullptr;
+  const bool vec_out = MODE == 3 && decim == 1 && batch_aligned<TO>(py, dir);
   TI buf[kBatch], nxt[kBatch];
+  double wb[RAMPS ? kBatch : 1], wn[RAMPS ? kBatch : 1];
   const int full = len / kBatch * kBatch;
   if (full > 0) {
+    load_batch<TI>(px, dir, vec_in, buf);
+    if (RAMPS) {
 #pragma unroll
-    for (int b = 0; b < kBatch; ++b) buf[b] = __ldg(px + dir * b);
+      for (int b = 0; b < kBatch; ++b) wb[RAMPS ? b : 0] = taper_w(i + dir * b);
+    }
   }
   for (int j0 = 0; j0 < full; j0 += kBatch) {
+    // The lines a thread will need ~100 samples from now are requested into L2 (no register cost): with the next
+    // batch as the only load in flight a quarter of all stall samples sat on its first use (3 warps per scheduler
+    // and 32 different DRAM pages per warp-wide load: the latency exceeds the ~1000 cycles a batch computes).
+    if ((j0 & (2 * kBatch - 1)) == 0 && j0 + kPrefetch < len) prefetch_l2(px + dir * (j0 + kPrefetch));
     if (j0 + kBatch < full) {
+      load_batch<TI>(px + dir * (j0 + kBatch), dir, vec_in, nxt);
+      if (RAMPS) {
 #pragma unroll
-      for (int b = 0; b < kBatch; ++b) nxt[b] = __ldg(px + dir * (j0 + kBatch + b));
+        for (int b = 0; b < kBatch; ++b) wn[RAMPS ? b : 0] = taper_w(i + dir * (j0 + kBatch + b));
+      }
+    }
+    if (MODE == 3 && decim == 1) {
+      TO outv[kBatch];
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) outv[b] = (TO)sample((double)batch_elem(buf, dir, b), wb[RAMPS ? b : 0], j0 + b);
+      store_batch<TO>(py + dir * j0, dir, vec_out, outv);
+    } else {
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) sample((double)batch_elem(buf, dir, b), wb[RAMPS ? b : 0], j0 + b);
     }
 #pragma unroll
-    for (int b = 0; b < kBatch; ++b) sample((double)buf[b], j0 + b);
-#pragma unroll
     for (int b = 0; b < kBatch; ++b) buf[b] = nxt[b];
+    if (RAMPS) {
+#pragma unroll
+      for (int b = 0; b < kBatch; ++b) wb[RAMPS ? b : 0] = wn[RAMPS ? b : 0];
+    }
   }
-  for (int jl = full; jl < len; ++jl) sample((double)__ldg(px + dir * jl), jl);
+  for (int jl = full; jl < len; ++jl) {
+    const double y = sample((double)__ldg(px + dir * jl), RAMPS ? taper_w(i + dir * jl) : 1.0, jl);
+    if (MODE == 3 && decim == 1) py[dir * jl] = (TO)y;
+  }
+}
+
+template <int S, class TI, class TO, int MODE>
+__device__ __forceinline__ void scan_chunk(const TI* __restrict__ xi, int n, int t0, int len, const SosRegs<S>& fr,
+                                           double (&z)[2 * S], const PointwiseDev& pw, double c0, double c1,
+                                           int reverse, int decim, double* __restrict__ yz, TO* __restrict__ yo) {
+  // does the chunk touch a taper ramp?
+  const int i = reverse ? n - 1 - t0 : t0;
+  const int i_lo = reverse ? i - (len - 1) : i, i_hi = reverse ? i : i + (len - 1);
+  const bool ramps = i_lo < pw.taper_left || i_hi >= n - pw.taper_right;
+  if (ramps) scan_chunk_impl<S, TI, TO, MODE, true>(xi, n, t0, len, fr, z, pw, c0, c1, reverse, decim, yz, yo);
+  else scan_chunk_impl<S, TI, TO, MODE, false>(xi, n, t0, len, fr, z, pw, c0, c1, reverse, decim, yz, yo);
 }
 
 // phase 1: zero-state final state of every chunk (one thread per chunk)
 template <int S, class TI>
-__global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
+__global__ void __launch_bounds__(128, kScanMinBlocks<S>) sos_phase1(const TI* __restrict__ x, int64_t n, int64_t xs, int n_signals,
                                                   int chunk, int64_t n_chunks, const __grid_constant__ SosCoef<S> f,
                                                   PointwiseDev pw, const double* __restrict__ stats, int reverse,
                                                   double* __restrict__ zstate, double* __restrict__ yzs, int decim,
@@ -247,6 +379,7 @@ __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int6
   double z[2 * S];
 #pragma unroll
   for (int k = 0; k < 2 * S; ++k) z[k] = 0.0;
+  settle_loaded_values<S>(fr, z);
   const int t0 = c * chunk;
   const int len = (int)n - t0 < chunk ? (int)n - t0 : chunk;
   scan_chunk<S, TI, double, 1>(x + (int64_t)sig * xs, (int)n, t0, len, fr, z, pw, c0, c1, reverse, decim,
@@ -258,7 +391,7 @@ __global__ void __launch_bounds__(128) sos_phase1(const TI* __restrict__ x, int6
 
 // phase 3: rerun every chunk from its true start state and store
 template <int S, class TI, class TO>
-__global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int64_t n, int64_t xs, TO* __restrict__ y,
+__global__ void __launch_bounds__(128, kScanMinBlocks<S>) sos_phase3(const TI* __restrict__ x, int64_t n, int64_t xs, TO* __restrict__ y,
                                                   int64_t ys, int n_signals, int chunk, int64_t n_chunks,
                                                   const __grid_constant__ SosCoef<S> f, PointwiseDev pw,
                                                   const double* __restrict__ stats, int reverse, int decim,
@@ -275,6 +408,7 @@ __global__ void __launch_bounds__(128) sos_phase3(const TI* __restrict__ x, int6
   const double* in = sstart + ((int64_t)sig * n_chunks + c) * (2 * S);
 #pragma unroll
   for (int k = 0; k < 2 * S; ++k) z[k] = in[k];
+  settle_loaded_values<S>(fr, z);
   const int t0 = c * chunk;
   const int len = (int)n - t0 < chunk ? (int)n - t0 : chunk;
   scan_chunk<S, TI, TO, 3>(x + (int64_t)sig * xs, (int)n, t0, len, fr, z, pw, c0, c1, reverse, decim,
@@ -391,6 +525,47 @@ __global__ void __launch_bounds__(32) sos_carry_group(const double* __restrict__
     for (int u = 0; u < kPf; ++u) cur[u] = nxt[u];
   }
   if (mode == 0 && lane < d) gstate[sg * d + lane] = s;
+}
+
+// Start states of a fast-decaying cascade in one launch (xcb_sos::carry_window = K): one warp per (signal, run
+// of kRun chunks) starts K chunks before its run -- from the zero state, or from `init` when that is the start of
+// the trace -- and steps s <- P s + z through warm-up and run, storing the run's start states.  What the zero
+// start drops is P^K s with ||P^K|| <= 2^-80.  (cfg2: fold 56 us + sweep 28 us + expand 58 us of mostly idle
+// SMs -- 830 warps x 256 serial steps -- become one launch of 7000 warps x ~40 steps.)
+constexpr int kRun = 32;
+__global__ void __launch_bounds__(32) sos_carry_window(const double* __restrict__ zstate, int d, int64_t n_chunks,
+                                                       int64_t n_runs, int window, const double* __restrict__ P,
+                                                       const double* __restrict__ init, double* __restrict__ sstart) {
+  const int lane = threadIdx.x;
+  const int64_t sr = blockIdx.x;                 // sig * n_runs + run
+  const int64_t sig = sr / n_runs, r = sr - sig * n_runs;
+  double prow[24];
+#pragma unroll
+  for (int k = 0; k < 24; ++k) prow[k] = (lane < d && k < d) ? P[lane * d + k] : 0.0;
+  const int64_t r0 = r * kRun;
+  int64_t r1 = r0 + kRun;
+  if (r1 > n_chunks) r1 = n_chunks;
+  const int64_t c0 = r0 > window ? r0 - window : 0;
+  double s = (c0 == 0 && init && lane < d) ? init[sig * d + lane] : 0.0;
+  const double* zb = zstate + (sig * n_chunks) * d;
+  double* sb = sstart + (sig * n_chunks) * d;
+  constexpr int kPf = 8;
+  double cur[kPf], nxt[kPf];
+#pragma unroll
+  for (int u = 0; u < kPf; ++u) cur[u] = (lane < d && c0 + u < r1) ? zb[(c0 + u) * d + lane] : 0.0;
+  for (int64_t cb = c0; cb < r1; cb += kPf) {
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) nxt[u] = (lane < d && cb + kPf + u < r1) ? zb[(cb + kPf + u) * d + lane] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) {
+      if (cb + u < r1) {
+        if (cb + u >= r0 && lane < d) sb[(cb + u) * d + lane] = s;
+        s = carry_step(prow, s, cur[u], d);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPf; ++u) cur[u] = nxt[u];
+  }
 }
 
 // sequential sweep over groups (one warp per signal): gstate holds e_g on entry,
@@ -624,7 +799,8 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
                         const double* stats, void* workspace, void* stream) {
   if (!x || !y || !f || !workspace || n < 1 || n_signals < 1 || !dtype_ok(dtype_in) || !dtype_ok(dtype_out))
     return XCB_ERR_ARG;
-  if (f->n_sections < 1 || f->n_sections > kMaxSections || f->chunk < 1 || f->decimate < 1) return XCB_ERR_ARG;
+  if (f->n_sections < 1 || f->n_sections > kMaxSections || f->chunk < 1 || f->decimate < 1 || f->carry_window < 0)
+    return XCB_ERR_ARG;
   if (!f->carry || !f->carry_group) return XCB_ERR_ARG;
   if (f->reverse && f->decimate != 1) return XCB_ERR_UNSUPPORTED;
   if (n >= 2147483647LL) return XCB_ERR_UNSUPPORTED;             // the scan indexes samples with 32 bits
@@ -652,10 +828,16 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
   a.n_out = L.n_out;
   a.zin = f->zin_response;
   if (run_phase_s(f->n_sections, 1, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
-  const unsigned ng = (unsigned)((int64_t)n_signals * L.n_groups);
-  sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 0, dg, ds);
-  sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg, f->init_state);
-  sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 2, dg, ds);
+  if (f->carry_window >= 1 && L.n_chunks > 2 * kRun) {
+    const int64_t n_runs = (L.n_chunks + kRun - 1) / kRun;
+    sos_carry_window<<<(unsigned)((int64_t)n_signals * n_runs), 32, 0, st>>>(dz, L.d, L.n_chunks, n_runs,
+                                                                          f->carry_window, dP, f->init_state, ds);
+  } else {
+    const unsigned ng = (unsigned)((int64_t)n_signals * L.n_groups);
+    sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 0, dg, ds);
+    sos_carry_sweep<<<(unsigned)n_signals, 32, 0, st>>>(L.d, L.n_groups, dPG, dg, f->init_state);
+    sos_carry_group<<<ng, 32, 0, st>>>(dz, L.d, L.n_chunks, L.n_groups, dP, 2, dg, ds);
+  }
   if (cudaGetLastError() != cudaSuccess) return XCB_ERR_CUDA;
   if (zin) {
     const int rows = f->chunk / f->decimate;

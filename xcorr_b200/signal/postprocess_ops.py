@@ -33,7 +33,7 @@ import scipy.signal
 import torch
 
 from .. import _lib
-from ..stream.process import _carry_matrices, _SCAN_CHUNK
+from ..stream.process import _carry_matrices, _carry_window, _SCAN_CHUNK
 from ..util.cc import weight
 from .fft import _plan
 
@@ -207,6 +207,7 @@ def _sosfilt(x2, sos, reverse, init):
         for m, v in enumerate((sec[0] / a0, sec[1] / a0, sec[2] / a0, sec[4] / a0, sec[5] / a0)):
             f.coef[k][m] = float(v)
     P, PG = _carry_matrices(sos, _SCAN_CHUNK)
+    f.carry_window = _carry_window(P)
     dP, dPG = torch.from_numpy(P).to(x2.device), torch.from_numpy(PG).to(x2.device)
     f.carry = ctypes.cast(dP.data_ptr(), ctypes.POINTER(ctypes.c_double))
     f.carry_group = ctypes.cast(dPG.data_ptr(), ctypes.POINTER(ctypes.c_double))

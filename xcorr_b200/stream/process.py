@@ -70,7 +70,7 @@ _operations = {
 }
 
 _DETREND = {'demean': 1, 'constant': 1, 'linear': 2, 'simple': 3}
-_SCAN_CHUNK = 512
+_SCAN_CHUNK = 480      # samples per scan chunk: a multiple of 8 (16-byte vector batches of the scan kernels stay aligned)
 _GROUP = 256
 
 
@@ -250,6 +250,20 @@ def _carry_matrices(sos, chunk):
         _, zf = signal.sosfilt(sos, zero, zi=zi)
         P[:, i] = zf.reshape(-1)
     return np.ascontiguousarray(P), np.ascontiguousarray(np.linalg.matrix_power(P, _GROUP))
+
+
+def _carry_window(P, limit=2.0 ** -80, kmax=64):
+    """Smallest K with ||P^K||_inf <= 2^-80 (`xcb_sos.carry_window`): after K chunks the start state of a
+    chunk no longer matters (far below float64 rounding), so the start states can be formed in one parallel
+    launch.  0 when the filter decays too slowly (e.g. a 0.05 Hz high-pass at 250 Hz)."""
+    Pk = np.array(P, dtype=np.float64)
+    for k in range(1, kmax + 1):
+        if not np.all(np.isfinite(Pk)):
+            return 0
+        if np.abs(Pk).sum(axis=1).max() <= limit:
+            return k
+        Pk = Pk @ P
+    return 0
 
 
 def _zero_input_response(sos, chunk, decimate):
@@ -536,12 +550,19 @@ class PreprocessProgram:
                 f.reverse = int(s.reverse)
                 # decimating cascades: chunks of whole decimation periods enable the zero-input fast path
                 zin = s.decimate >= 2 and not s.reverse
-                f.chunk = (_SCAN_CHUNK // s.decimate) * s.decimate if zin else _SCAN_CHUNK
+                f.chunk = _SCAN_CHUNK
+                if zin:
+                    # ... and of 8 samples when that keeps the chunk near the nominal length (aligned vector batches)
+                    unit = int(np.lcm(s.decimate, 8))
+                    if unit > _SCAN_CHUNK // 2:
+                        unit = s.decimate
+                    f.chunk = max(1, round(_SCAN_CHUNK / unit)) * unit
                 for k, sec in enumerate(sos):
                     a0 = sec[3]
                     for m, v in enumerate((sec[0] / a0, sec[1] / a0, sec[2] / a0, sec[4] / a0, sec[5] / a0)):
                         f.coef[k][m] = float(v)
                 s.P, s.PG = _carry_matrices(sos, f.chunk)
+                f.carry_window = _carry_window(s.P)
                 s.G = _zero_input_response(sos, f.chunk, s.decimate) if zin else None
                 s.f = f
         self._designed = True
