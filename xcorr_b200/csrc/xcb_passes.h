@@ -320,6 +320,17 @@ XCB_HD void twiddle_chain(const PassParams<T>& p, uint32_t e0, uint32_t de, cx<T
   }
 }
 
+// the same with the two twiddles already looked up (the caller fetched them ahead of a wait)
+template <int R, bool CONJ_IN, class T> XCB_HD void twiddle_chain_from(cx<T> w, const cx<T> step, cx<T>* v) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cx<T> x = v[r];
+    if (CONJ_IN) x.y = -x.y;
+    v[r] = cmul(x, w);
+    if (r + 1 < R) w = cmul(w, step);
+  }
+}
+
 // v[r] <- v[r] * w^r, r = 1..R-1 (stage-2 twiddles W_N^(r*j), w = W_N^j)
 template <int R, bool PK = false, class T> XCB_HD void twiddle_powers(cx<T> w, cx<T>* v) {
   cx<T> wr = w;

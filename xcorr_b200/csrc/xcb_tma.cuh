@@ -54,13 +54,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // same, for waits that can be long (a consumer waiting for its producer): back off between polls so
 // the spinning warps do not take issue slots from the warps that have work
+#ifndef XCB_PROD_SLEEP_CAP
+#define XCB_PROD_SLEEP_CAP 0
+#endif
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+#if XCB_PROD_SLEEP_CAP == 0
+  while (!mbar_try_wait(bar, parity)) {}
+#else
   uint32_t ns = 32;
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(ns);
-    if (ns < 512) ns *= 2;
+    if (ns < XCB_PROD_SLEEP_CAP) ns *= 2;
   }
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile(
@@ -201,6 +208,17 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     const uint32_t colscale = (uint32_t)(col0 + c) * p.tw_scale;
 
     cx<T> v[K::TJ];
+    // the last inverse pass looks its input twiddles up BEFORE the wait for the tile (two L2-resident table reads
+    // per thread whose latency otherwise sits between the first barrier and the first butterfly).  Measured per
+    // role: last pass 2.80 -> 2.73 ms, but the run-time-moded N = 150 middle pass 3.68 -> 3.80 ms (four more live
+    // registers at its 80-register cap), so only the epilogue roles do it.
+    constexpr bool kHoistTw = ROLE == COL_INV_EPI || ROLE == COL_INV_AMAX;
+    cx<T> tw_w, tw_step;
+    tw_w.x = tw_step.x = T(1); tw_w.y = tw_step.y = T(0);
+    if (kHoistTw && j < R2) {
+      tw_w = tw_big(p, colscale * (uint32_t)j);
+      tw_step = tw_big(p, colscale * (uint32_t)R2);
+    }
     mbar_wait(&full[s], parity);
     if (j < R2) {
 #pragma unroll
@@ -217,7 +235,8 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     __syncthreads();
     if (kSumsq && p.sumsq_partial) block_sumsq<K::THREADS>(p.sumsq_partial + tile, red, tid);
     if (j < R2) {
-      if (kLoad == CL_CPLX_INV) twiddle_chain<R1, true>(p, colscale * (uint32_t)j, colscale * (uint32_t)R2, v);
+      if (kHoistTw) twiddle_chain_from<R1, true>(tw_w, tw_step, v);
+      else if (kLoad == CL_CPLX_INV) twiddle_chain<R1, true>(p, colscale * (uint32_t)j, colscale * (uint32_t)R2, v);
       fft_reg<R1>(v);
 #pragma unroll
       for (int r = 0; r < R1; ++r) sm[(j * R1 + r) * C + c] = v[r];
