@@ -20,7 +20,7 @@ Printed JSON line:
                 the timed region, against the PCIe ceiling measured in the same run
   roofline      dominant kernel vs the measured HBM peak (traffic: ncu capture under profiles/)
   step_roofline whole step vs SURVEY 8d's minimal-traffic model
-  configs       short legs of the other named configurations (cfg1, cfg3/f64, cfg2, cfg4, cfg5)
+  configs       short legs of the other named configurations (cfg1, cfg3/f64, cfg2 (+ its FIR-decimator variant), cfg4, cfg5)
   cpu_baseline  the reference's own xcorr/util/cc.py (oracle/_ref) on the host cores, FULL-SIZE windows
 
 `--impl reference` times the reference's util/cc.py alone (full-size 24 h @ 250 Hz windows, one
@@ -345,12 +345,16 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         alg = b_alg(R, 1, n, K, b)
         extra = dict(passes=list(plan.dims), blocks=plan.n_blocks, launch="CUDA graph replay of forward + correlate")
         desc = "1 pair, 24h@50Hz, lags (0, 9h) (the reference's CPU-runnable case)"
-    elif name in ("cfg2", "cfg2_f64"):
+    elif name in ("cfg2", "cfg2_f64", "cfg2_fir"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
         b = 8 if dt == torch.float64 else 4
         n_raw, R = 21_600_000, 5
         pairs = xb.all_pairs(R)
-        prog = PreprocessProgram(CFG2_OPS, n_raw, 250.0)
+        # cfg2_fir: the same chain with the north-star decimator (polyphase FIR, scipy.signal.resample_poly
+        # semantics) in place of obspy's Chebyshev-II `decimate`
+        ops = CFG2_OPS if name != "cfg2_fir" else [
+            op if op[0] != "decimate" else ("resample_poly", {"up": 1, "down": 5}) for op in CFG2_OPS]
+        prog = PreprocessProgram(ops, n_raw, 250.0)
         n = prog.npts_out
         plan = xb.CorrelationPlan(n, R, pairs, dtype=dt, index_min=n - 1, index_max=n - 1 + 1_620_000, device=dev)
         raw = make_inputs(torch, R, n_raw, dev, dt, 2 + rank) + 3.0
@@ -362,11 +366,14 @@ def config_leg(name, torch, dev, steps, warmup, rank=0, world=1, dist=None):
         alg = b_alg(R, len(pairs), n, 1_620_000, b, n_raw)
         # the chain is bound by FP64 arithmetic, not by bytes: 10 second-order sections x 5 multiply-adds per raw
         # sample in float64 (exact recurrence, scipy.signal.sosfilt order) -- reported beside the byte roofline
+        n_sec, fir_fma = (10, 0) if name != "cfg2_fir" else (4, R * n * 101)
         extra = dict(passes=list(plan.dims), blocks=plan.n_blocks,
-                     preprocess_fp64_fma_per_step=int(R * n_raw * 10 * 5),
+                     preprocess_fp64_fma_per_step=int(R * n_raw * n_sec * 5 + fir_fma),
                      note="step_roofline_frac counts bytes only; the preprocessing chain (ms_preprocess) is FP64-throughput "
                           "bound: fp64_fma_per_step / ms_preprocess is its achieved multiply-add rate")
         desc = "5 receivers / 10 pairs, 24h@250Hz raw -> detrend, taper, 3-12 Hz bandpass, decimate 5 -> cc at 50 Hz, lags (0, 9h)"
+        if name == "cfg2_fir":
+            desc = desc.replace("decimate 5", "polyphase-FIR decimation by 5 (resample_poly, 101 taps)")
     elif name in ("cfg4", "cfg4_f64"):
         dt = torch.float64 if name.endswith("f64") else torch.float32
         b = 8 if dt == torch.float64 else 4
@@ -555,7 +562,7 @@ def run_gpu(args):
     # ---------------- the other named configurations (short legs) ----------------
     legs = []
     if not args.no_legs and args.workload == "cfg3" and args.dtype == "f32":
-        for name in ("cfg1", "cfg3_f64", "cfg2", "cfg4", "cfg5"):
+        for name in ("cfg1", "cfg3_f64", "cfg2", "cfg2_fir", "cfg4", "cfg5"):
             try:
                 legs.append(config_leg(name, torch, dev, 3, 2, rank, world, dist))
             except Exception as error:                      # a leg must not take the headline down

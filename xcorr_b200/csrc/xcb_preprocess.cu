@@ -536,6 +536,7 @@ constexpr int kRun = 32;
 __global__ void __launch_bounds__(32) sos_carry_window(const double* __restrict__ zstate, int d, int64_t n_chunks,
                                                        int64_t n_runs, int window, const double* __restrict__ P,
                                                        const double* __restrict__ init, double* __restrict__ sstart) {
+  __shared__ __align__(16) double sh[32];
   const int lane = threadIdx.x;
   const int64_t sr = blockIdx.x;                 // sig * n_runs + run
   const int64_t sig = sr / n_runs, r = sr - sig * n_runs;
@@ -560,7 +561,22 @@ __global__ void __launch_bounds__(32) sos_carry_window(const double* __restrict_
     for (int u = 0; u < kPf; ++u) {
       if (cb + u < r1) {
         if (cb + u >= r0 && lane < d) sb[(cb + u) * d + lane] = s;
-        s = carry_step(prow, s, cur[u], d);
+        // the state goes round through shared memory and is read back as 16-byte broadcasts (13 wavefronts per
+        // step; the shuffle form of carry_step issues 48 and bound this launch at 87 % L1 wavefronts)
+        sh[lane] = s;
+        __syncwarp();
+        double a0 = cur[u], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const double2* s2 = reinterpret_cast<const double2*>(sh);
+#pragma unroll
+        for (int k = 0; k < 24; k += 4) {
+          const double2 p0 = s2[k / 2], p1 = s2[k / 2 + 1];
+          a0 = fma(prow[k], p0.x, a0);          // rows are zero padded beyond d
+          a1 = fma(prow[k + 1], p0.y, a1);
+          a2 = fma(prow[k + 2], p1.x, a2);
+          a3 = fma(prow[k + 3], p1.y, a3);
+        }
+        s = (a0 + a1) + (a2 + a3);
+        __syncwarp();
       }
     }
 #pragma unroll
