@@ -1,4 +1,4 @@
-"""Value-level parity at the NAMED sizes of BASELINE.json (configs 3, 4, 5), through the
+"""Value-level parity at the NAMED sizes of BASELINE.json (configs 2, 3, 4, 5), through the
 C ABI, against the oracle -- in float32 (<= 1e-5 of the peak) and float64 (<= 1e-12),
 arg-max lag exact.  Cell semantics: core/process.py:155-162 (cc of the first npts
 samples, crop [index_min:index_max]).
@@ -8,6 +8,9 @@ samples, crop [index_min:index_max]).
   full with the smooth-length oracle (the reference's own 2n-1 Bluestein transform takes ~75 s
   per cell; `cc_smooth` agrees with it to 1e-15, tests/test_oracle.py) and the arrival is checked
   for all 120 pairs.
+* config 2: 5 receivers of 24 h @ 250 Hz raw samples through bench.py's op-list (detrend, taper, 3-12 Hz
+  band-pass, decimate 5, detrend, taper) against the scipy restatement of the obspy chain (oracle unpinned, see
+  oracle/preprocess_oracle.py), then all 10 pairs with lags (0, 9 h) against the smooth-length cc oracle.
 * config 4: 4 receivers, 64 stacked 1 h windows at 250 Hz against the SUM of per-window oracle CCFs.
 * config 5: 1024 x 128 spectrograms against oracle.correlate2d, full cc2 and (value, dF, dT).
 """
@@ -211,3 +214,65 @@ def test_cfg5_spectrogram_pairs_full_size(env, dtype):
         if q % 4 == 0:
             got = cc2[q].cpu().numpy()
             assert np.max(np.abs(got - ref)) <= TOL[dtype] * np.max(np.abs(ref)), (i, j)
+
+
+# ---------------------------------------------------------------------------
+# config 2: raw 250 Hz traces -> preprocessing chain -> cc at 50 Hz, full size
+# ---------------------------------------------------------------------------
+CFG2_NRAW, CFG2_R, CFG2_K = 21_600_000, 5, 1_620_000
+
+
+@pytest.fixture(scope="module")
+def cfg2(env):
+    """SURVEY 8d raw inputs (common source + noise, 7.5 Hz line, trend, offset) as float32 values, the float64
+    oracle chain of every trace and the oracle CCF of all 10 pairs (spectra shared between the cells)."""
+    torch, xb, orc = env
+    from bench import CFG2_OPS
+    from oracle import preprocess_oracle as pre
+    fs = 250.0
+    src = orc.synthetic_receivers(CFG2_R, CFG2_NRAW, seed=2000, delay=137 * 5)
+    t = np.arange(CFG2_NRAW)
+    raw = (src + np.sin(2 * np.pi * 7.5 * t / fs) + 1e-6 * t + 3.0).astype(np.float32)
+    del src, t
+    ref = np.stack([pre.process(row.astype(np.float64), fs, CFG2_OPS)[0] for row in raw])
+    n = ref.shape[1]
+    L = 2 * n
+    spec = [np.fft.rfft(r, L) for r in ref]
+    norm = [np.linalg.norm(r) for r in ref]
+    cells = {}
+    for (i, j) in xb.all_pairs(CFG2_R):
+        r = np.fft.irfft(spec[i] * np.conjugate(spec[j]) / (norm[i] * norm[j]), L)
+        peak = max(np.max(np.abs(r[:n])), np.max(np.abs(r[L - (n - 1):])))
+        cells[(i, j)] = (r[:CFG2_K].copy(), peak)
+    return raw, ref, cells, CFG2_OPS
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_cfg2_full_size_chain_and_cells(env, cfg2, dtype):
+    torch, xb, orc = env
+    from xcorr_b200.stream.process import PreprocessProgram
+    raw, ref, cells, ops = cfg2
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(raw).to(dev)
+    if dtype == "f64":
+        x = x.double()
+    prog = PreprocessProgram(ops, CFG2_NRAW, 250.0)
+    y = prog.run(x)
+    assert tuple(y.shape) == ref.shape == (CFG2_R, CFG2_NRAW // 5) and prog.fs_out == 50.0
+    got = y.cpu().numpy().astype(np.float64)
+    err = float(np.max(np.abs(got - ref)) / np.max(np.abs(ref)))
+    assert err <= (1e-12 if dtype == "f64" else 2e-6), err
+    n = y.shape[1]
+    pairs = xb.all_pairs(CFG2_R)
+    plan = xb.CorrelationPlan(n, CFG2_R, pairs, dtype=_tdt(torch, dtype), index_min=n - 1, index_max=n - 1 + CFG2_K,
+                              device=dev)
+    ccf = plan(y)
+    worst = 0.0
+    for q, (i, j) in enumerate(pairs):
+        r, peak = cells[(i, j)]
+        g = ccf[q, 0].cpu().numpy().astype(np.float64)
+        assert int(np.argmax(g)) == int(np.argmax(r))
+        e = float(np.max(np.abs(g - r))) / peak
+        worst = max(worst, e)
+        assert e <= TOL[dtype], ((i, j), e)
+    print(f"cfg2 {dtype}: trace error {err:.2e}, worst cell {worst:.2e} of peak, dims {plan.dims}")
