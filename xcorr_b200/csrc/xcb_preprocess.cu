@@ -437,34 +437,53 @@ __global__ void __launch_bounds__(128) sos_phase3_zin(const double* __restrict__
   const int64_t c0 = (blockIdx.x - (int64_t)sig * blocks_per_sig) * kZinChunks;
   const int nc = (int)(n_chunks - c0 < kZinChunks ? n_chunks - c0 : kZinChunks);
   const double* in = sstart + ((int64_t)sig * n_chunks + c0) * d;
-  for (int i = threadIdx.x; i < nc * 24; i += 128) {
+  for (int i = threadIdx.x; i < nc * 24; i += blockDim.x) {
     const int c = i / 24, k = i - c * 24;
     zin_sm[i] = k < d ? in[c * d + k] : 0.0;
   }
   __syncthreads();
   const double* src = yzs + (int64_t)sig * n_out;
   TO* dst = y + (int64_t)sig * ys;
-  for (int r = threadIdx.x; r < rows; r += 128) {
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
     double g[24];
 #pragma unroll
     for (int k = 0; k < 24; ++k) g[k] = k < d ? __ldg(G + (int64_t)r * d + k) : 0.0;
-    int64_t o = c0 * rows + r;
-    double cur = o < n_out ? src[o] : 0.0;
-    for (int c = 0; c < nc; ++c, o += rows) {
-      const int64_t on = o + rows;
-      const double nxt = (c + 1 < nc && on < n_out) ? src[on] : 0.0;      // next zero-state output in flight
-      const double2* s0 = reinterpret_cast<const double2*>(zin_sm + c * 24);
-      double a0 = cur, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    // zero-state outputs are fetched kZinAhead chunks ahead (one ahead left the loads exposed: long_scoreboard
+    // 6.5 warps per issue at 14 resident warps per SM)
+    constexpr int kZinAhead = 4;
+    const int64_t o0 = c0 * rows + r;
+    double cur[kZinAhead], nxt[kZinAhead];
 #pragma unroll
-      for (int k = 0; k < 24; k += 4) {
-        const double2 p0 = s0[k / 2], p1 = s0[k / 2 + 1];
-        a0 = fma(g[k], p0.x, a0);
-        a1 = fma(g[k + 1], p0.y, a1);
-        a2 = fma(g[k + 2], p1.x, a2);
-        a3 = fma(g[k + 3], p1.y, a3);
+    for (int u = 0; u < kZinAhead; ++u) {
+      const int64_t o = o0 + (int64_t)u * rows;
+      cur[u] = (u < nc && o < n_out) ? src[o] : 0.0;
+    }
+    for (int cb = 0; cb < nc; cb += kZinAhead) {
+#pragma unroll
+      for (int u = 0; u < kZinAhead; ++u) {
+        const int64_t o = o0 + (int64_t)(cb + kZinAhead + u) * rows;
+        nxt[u] = (cb + kZinAhead + u < nc && o < n_out) ? src[o] : 0.0;
       }
-      if (o < n_out) dst[o] = (TO)((a0 + a1) + (a2 + a3));
-      cur = nxt;
+#pragma unroll
+      for (int u = 0; u < kZinAhead; ++u) {
+        const int c = cb + u;
+        const int64_t o = o0 + (int64_t)c * rows;
+        if (c < nc && o < n_out) {
+          const double2* s0 = reinterpret_cast<const double2*>(zin_sm + c * 24);
+          double a0 = cur[u], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+          for (int k = 0; k < 24; k += 4) {
+            const double2 p0 = s0[k / 2], p1 = s0[k / 2 + 1];
+            a0 = fma(g[k], p0.x, a0);
+            a1 = fma(g[k + 1], p0.y, a1);
+            a2 = fma(g[k + 2], p1.x, a2);
+            a3 = fma(g[k + 3], p1.y, a3);
+          }
+          dst[o] = (TO)((a0 + a1) + (a2 + a3));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kZinAhead; ++u) cur[u] = nxt[u];
     }
   }
 }
@@ -969,12 +988,14 @@ XCB_API int xcb_sosfilt(int32_t dtype_in, const void* x, int64_t x_stride, int32
     const int64_t blocks_per_sig = (L.n_chunks + kZinChunks - 1) / kZinChunks;
     const size_t smem = sizeof(double) * (size_t)kZinChunks * 24;
     const unsigned grid = (unsigned)((int64_t)n_signals * blocks_per_sig);
+    // one thread per kept local sample: no idle lanes beyond the last partial warp (96 rows: 96 threads, not 128)
+    const unsigned zin_threads = (unsigned)(rows >= 128 ? 128 : (rows + 31) / 32 * 32);
     if (dtype_out == XCB_F32)
-      sos_phase3_zin<float><<<grid, 128, smem, st>>>(a.yzs, static_cast<float*>(y), y_stride, L.n_out, rows, L.n_chunks,
-                                                     L.d, a.zin, ds);
+      sos_phase3_zin<float><<<grid, zin_threads, smem, st>>>(a.yzs, static_cast<float*>(y), y_stride, L.n_out, rows,
+                                                             L.n_chunks, L.d, a.zin, ds);
     else
-      sos_phase3_zin<double><<<grid, 128, smem, st>>>(a.yzs, static_cast<double*>(y), y_stride, L.n_out, rows,
-                                                      L.n_chunks, L.d, a.zin, ds);
+      sos_phase3_zin<double><<<grid, zin_threads, smem, st>>>(a.yzs, static_cast<double*>(y), y_stride, L.n_out, rows,
+                                                              L.n_chunks, L.d, a.zin, ds);
     return cudaGetLastError() == cudaSuccess ? XCB_OK : XCB_ERR_CUDA;
   }
   if (run_phase_s(f->n_sections, 3, dtype_in, dtype_out, a, st) != cudaSuccess) return XCB_ERR_CUDA;
