@@ -48,6 +48,7 @@ with the reference's client (``stream/client.py:996``); they raise
 import ctypes
 import hashlib
 import json
+import os
 import warnings
 
 import numpy as np
@@ -70,7 +71,7 @@ _operations = {
 }
 
 _DETREND = {'demean': 1, 'constant': 1, 'linear': 2, 'simple': 3}
-_SCAN_CHUNK = 480      # samples per scan chunk: a multiple of 8 (16-byte vector batches of the scan kernels stay aligned)
+_SCAN_CHUNK = int(os.environ.get("XCB_SCAN_CHUNK", "480"))      # samples per scan chunk: a multiple of 8 (16-byte vector batches of the scan kernels stay aligned)
 _GROUP = 256
 
 
