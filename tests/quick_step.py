@@ -4,10 +4,11 @@ import xcorr_b200 as xb
 from bench import make_inputs
 n,R,K=21_600_000,16,8_100_000
 dev=torch.device("cuda:0")
+dt=torch.float64 if os.environ.get("XCB_DTYPE","f32")=="f64" else torch.float32
 pairs=xb.all_pairs(R)
-plan=xb.CorrelationPlan(n,R,pairs,dtype=torch.float32,index_min=n-1,index_max=n-1+K,device=dev)
-x=make_inputs(torch,R,n,dev,torch.float32,3000)
-ccf=torch.empty((len(pairs),1,K),dtype=torch.float32,device=dev)
+plan=xb.CorrelationPlan(n,R,pairs,dtype=dt,index_min=n-1,index_max=n-1+K,device=dev)
+x=make_inputs(torch,R,n,dev,dt,3000)
+ccf=torch.empty((len(pairs),1,K),dtype=dt,device=dev)
 for _ in range(3): plan.forward(x); plan.correlate(out=ccf)
 torch.cuda.synchronize()
 plan.profile(True)

@@ -114,6 +114,9 @@ __device__ __forceinline__ void amax_warp_reduce(unsigned live, double& v, uint3
   v = m == ~0ull ? __longlong_as_double(0x7ff8000000000000ll) : __longlong_as_double((long long)back);
 }
 
+#ifndef XCB_HOIST_TW
+#define XCB_HOIST_TW 1
+#endif
 #ifndef XCB_COL_MINB_SMALL
 #define XCB_COL_MINB_SMALL 8
 #endif
@@ -212,7 +215,7 @@ xcb_col_pass_tma(const __grid_constant__ CUtensorMap tmap, const __grid_constant
     // per thread whose latency otherwise sits between the first barrier and the first butterfly).  Measured per
     // role: last pass 2.80 -> 2.73 ms, but the run-time-moded N = 150 middle pass 3.68 -> 3.80 ms (four more live
     // registers at its 80-register cap), so only the epilogue roles do it.
-    constexpr bool kHoistTw = ROLE == COL_INV_EPI || ROLE == COL_INV_AMAX;
+    constexpr bool kHoistTw = XCB_HOIST_TW && (ROLE == COL_INV_EPI || ROLE == COL_INV_AMAX);
     cx<T> tw_w, tw_step;
     tw_w.x = tw_step.x = T(1); tw_w.y = tw_step.y = T(0);
     if (kHoistTw && j < R2) {
@@ -384,7 +387,10 @@ template <class T, int R1, int R2> struct PairGrouped {
   static constexpr int NBUF = W::LN == 8 ? XCB_NBUF8 : (sizeof(T) == 4 ? 3 : 2);   // staging ring
   static constexpr int ROW_BYTES = N * 2 * (int)sizeof(T);
   static constexpr int STAGE_BYTES = MAX_ROWS * PP * 2 * ROW_BYTES;      // [row][pair][side]
-  static constexpr int MINB = W::THREADS <= 128 ? 4 : 2;                 // resident CTAs the kernel is compiled for
+  // resident CTAs the kernel is compiled for: four for the float 8 x 8 kernel (128 consumer threads, 64 registers);
+  // two otherwise.  (`W::THREADS <= 128` also matched the DOUBLE 16 x R2 kernels -- 8 columns of 16 lanes -- and capped
+  // them at 96 registers: 132 spill instructions, config 3 in float64 30.3 -> 36.6 ms until this was noticed.)
+  static constexpr int MINB = (W::LN == 8 && sizeof(T) == 4) ? 4 : 2;
   static constexpr int EXCH_OFF = NBUF * STAGE_BYTES;
   static constexpr int BAR_OFF = EXCH_OFF + C * W::COLBUF * 2 * (int)sizeof(T);
   static constexpr int MAIL_OFF = BAR_OFF + 64;
