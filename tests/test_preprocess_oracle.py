@@ -166,3 +166,41 @@ def test_time_based_trim_matches_the_obspy_restatement():
     prog = PreprocessProgram(ops, n_raw, fs, trace_start=-0.05 * wl)
     assert (prog.npts_out, prog.fs_out, prog.trace_start_out) == (int(wl * 50) + 1, 50.0, 0.0)
     assert inject_dynamic_parameters("trim", {"start": 3}, starttime=0.0, endtime=1.0) == {"start": 3}
+
+
+def test_scan_host_design_carry_window_and_chunk_model():
+    """Host side of the chunked scan (stream/process.py): the state-transition matrix over a chunk reproduces
+    scipy's sosfilt across chunk boundaries, `carry_window` is a valid certificate (||P^K||_inf <= 2^-80, and the
+    truncated recurrence reproduces the true chunk start states), slowly decaying filters get 0, and decimating
+    chunk lengths are whole periods and multiples of 8 samples."""
+    from xcorr_b200.stream import process as sp
+    sos = np.vstack([pre.butter_sos(250.0, "bandpass", freqmin=3.0, freqmax=12.0, corners=4),
+                     pre.cheby2_lowpass_sos(250.0, 25.0)])
+    chunk = 480
+    P, _ = sp._carry_matrices(sos, chunk)
+    K = sp._carry_window(P)
+    assert 1 <= K <= 16
+    assert np.abs(np.linalg.matrix_power(P, K)).sum(axis=1).max() <= 2.0 ** -80
+    # true chunk start states from one long sosfilt run vs the windowed recurrence s <- P s + z over K chunks
+    rng = np.random.default_rng(5)
+    nchunks = 3 * K
+    x = rng.standard_normal(nchunks * chunk)
+    S = sos.shape[0]
+    zi = np.zeros((S, 2))
+    starts, zfinal = [], []
+    for c in range(nchunks):
+        starts.append(zi.reshape(-1).copy())
+        _, zi = signal.sosfilt(sos, x[c * chunk:(c + 1) * chunk], zi=zi)
+        _, z0 = signal.sosfilt(sos, x[c * chunk:(c + 1) * chunk], zi=np.zeros((S, 2)))
+        zfinal.append(z0.reshape(-1))
+    for c in range(K, nchunks):
+        s = np.zeros(2 * S)
+        for k in range(c - K, c):
+            s = P @ s + zfinal[k]
+        assert np.max(np.abs(s - starts[c])) <= 1e-12 * max(1.0, np.max(np.abs(starts[c])))
+    slow = pre.butter_sos(250.0, "highpass", freq=0.05, corners=4)
+    assert sp._carry_window(sp._carry_matrices(slow, chunk)[0]) == 0
+    prog = sp.PreprocessProgram([("decimate", {"factor": 5})], 100_000, 250.0)
+    prog._host_design()
+    f = [st[1].f for st in prog.steps if st[0] == "stage" and st[1].f is not None][0]
+    assert f.chunk % 5 == 0 and f.chunk % 8 == 0 and f.carry_window >= 1
