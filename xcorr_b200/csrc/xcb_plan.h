@@ -594,10 +594,20 @@ inline void build_pair_groups(const Job* jobs, int n_jobs, int max_jobs, int max
   size_t k = 0;
   for (size_t a = 0; a < out.size(); ++a) if (!dead[a]) out[k++] = out[a];
   out.resize(k);
+  // `pad` = bit mask of the staged rows this group is the FIRST to hold: the producer of that group requests those
+  // spectra rows into L2 for a row pair well ahead of the grid's front, so every row is requested exactly once
+  std::vector<int64_t> seen;
   for (PairGroup& g : out) {
     for (int a = 0; a < g.n_i; ++a) g.rows[a] = g.spec_i[a];
     for (int b = 0; b < g.n_j; ++b) g.rows[g.n_i + b] = g.spec_j[b];
     g.n_rows = g.n_i + g.n_j;
+    g.pad = 0;
+    for (int r = 0; r < g.n_rows; ++r) {
+      if (std::find(seen.begin(), seen.end(), g.rows[r]) == seen.end()) {
+        seen.push_back(g.rows[r]);
+        g.pad |= 1 << r;
+      }
+    }
   }
 }
 

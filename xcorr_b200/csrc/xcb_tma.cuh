@@ -368,10 +368,17 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                : "memory");
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef XCB_PAIR_PREFETCH
+#define XCB_PAIR_PREFETCH 0     // row pairs ahead (0 = off: 24 / 48 pairs ahead measured 3.80 -> 4.20 ms)
+#endif
 #ifndef XCB_NBUF8
 #define XCB_NBUF8 3
 #endif
@@ -480,7 +487,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     // of item k+1 is in flight and the counter of item k+2 is being claimed. ----
     struct Raw {                                        // loads issued, values not yet used
       int64_t item, ra, rb, spec;                       // ra, rb: the rows of THIS lane's pair
-      int32_t n_i, n_rows;
+      int32_t n_i, n_rows, own;
       cx<T> hi, lo;
     };
     const int r = lane / (2 * PP), pp = (lane >> 1) % PP, sd = lane & 1;   // staged row, row pair, side of this lane
@@ -488,7 +495,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
     auto start = [&](unsigned long long tok) {
       Raw w;
       w.item = (int64_t)__shfl_sync(0xffffffffu, tok, 0);
-      w.ra = w.rb = w.spec = 0; w.n_i = w.n_rows = 0;
+      w.ra = w.rb = w.spec = 0; w.n_i = w.n_rows = w.own = 0;
       w.hi.x = w.lo.x = T(1); w.hi.y = w.lo.y = T(0);
       if (w.item < n_items) {
         const int64_t q = w.item / p.n_groups;
@@ -496,6 +503,7 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
         if (!RP::pair_rows(p, q * PP + pp, w.ra, w.rb)) w.ra = w.rb = -1;      // past the last row pair
         w.n_i = g.n_i;
         w.n_rows = g.n_rows;
+        w.own = g.pad;
         w.spec = g.rows[r < 2 * kGroupJobs ? r : 0];
         if (lane < 2 * PP && w.ra >= 0) {
           const uint32_t kl = RP::klow_of_row(p, sd ? w.rb : w.ra);
@@ -522,6 +530,22 @@ xcb_pair_product_grouped(const __grid_constant__ PassParams<T> p) {
       const uint32_t n_copies = __popc(__ballot_sync(0xffffffffu, mine));
       const int64_t src = cur.spec + (sd ? cur.rb : cur.ra) * N;
       const cx<T> wr = cmul(cur.hi, cur.lo);
+#if XCB_PAIR_PREFETCH > 0
+      // EXPERIMENT (off): the rows this group is the first to hold are requested into L2 for the row pair
+      // XCB_PAIR_PREFETCH pairs ahead (the ~300 resident CTAs spread over ~17 row pairs), so that the bulk copies
+      // of the staging ring hit L2.  Each row is requested once (owner mask from the planner) with one
+      // cp.async.bulk.prefetch.L2 -- and the kernel still got 10 % SLOWER, like the per-line prefetch of round 2.
+      if (((cur.own >> r) & 1) && r < K::MAX_ROWS) {
+        int64_t pa, pb;
+        if (RP::pair_rows(p, (cur.item / p.n_groups + XCB_PAIR_PREFETCH) * PP + pp, pa, pb) && (sd == 0 || pa != pb)) {
+          const int64_t psrc = cur.spec + (sd ? pb : pa) * N;
+          for (int w = 0; w < n_terms; ++w) {
+            const int64_t toff = p.use_blk_off ? (r < cur.n_i ? p.blk_off_i[w] : p.blk_off_j[w]) : w * p.stack_spec_stride;
+            bulk_prefetch_l2(p.spec + psrc + toff, K::ROW_BYTES);
+          }
+        }
+      }
+#endif
       for (int w = 0; w < n_terms; ++w, ++step) {
         const int buf = (int)(step % NBUF);
         mbar_wait_backoff(&empty[buf], ((step / NBUF) & 1u) ^ 1u);
