@@ -705,7 +705,10 @@ struct SosArgs {
 // zero-padded by kFirR - 1 on both sides (no bounds in the loop); the input span is laid out with one pad word
 // per kFirR * down samples so that the lanes' stride is odd (no bank conflicts).
 constexpr int kFirR = 8;
-constexpr int kFirThreads = 128;
+#ifndef XCB_FIR_THREADS
+#define XCB_FIR_THREADS 128
+#endif
+constexpr int kFirThreads = XCB_FIR_THREADS;
 constexpr int kFirTileR = kFirR * kFirThreads;
 template <class TI, class TO>
 __global__ void __launch_bounds__(kFirThreads) fir_decimate_kernel(const TI* __restrict__ x, int64_t xs, int64_t n_in,
